@@ -1,0 +1,162 @@
+/*
+ * memflow_b200.h -- C ABI of the B200-native MEMFlow hot path.
+ *
+ * Drop-in boundary for the batched per-event evaluation path of MEMFlow
+ * (reference: themrluke/memflow-msci-project, citations are file:line relative
+ * to the reference tree):
+ *
+ *   - RAMBO-on-diet phase-space map + Jacobian
+ *       memflow/phasespace/rambo_generator.py:168-398  (generateKinematics_batch)
+ *       memflow/phasespace/rambo_generator.py:615-736  (getPSpoint_batch)
+ *       memflow/unfolding_flow/utils.py:1056-1152      (Compute_ParticlesTensor.get_PS)
+ *   - conditional rational-quadratic-spline masked autoregressive flow
+ *       zuko (third party, pinned zuko=1.2.0 in env.yml:40): NSF/MAF .log_prob / .sample,
+ *       called from e.g. memflow/unfolding_flow/unfolding_flow.py:179,186 and
+ *       memflow/transfer_flow/transfer_flow_paper_AllPartons_btag.py:202-213
+ *
+ * Conventions
+ *   - every pointer named d_* is a DEVICE pointer on the current CUDA device,
+ *     every other pointer is a HOST pointer that is only read during the call;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - all functions are asynchronous w.r.t. the host, re-entrant, keep no global
+ *     mutable state apart from a thread-local last-error string;
+ *   - return value: MF_OK (0) or a negative MF_E* code; mf_last_error() returns a
+ *     human readable message for the calling thread.  No exception crosses the ABI;
+ *   - four-vectors are (E, px, py, pz), array-of-structures, row-major contiguous,
+ *     exactly as the reference torch tensors are laid out.
+ */
+#ifndef MEMFLOW_B200_H
+#define MEMFLOW_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MF_ABI_VERSION 1
+
+/* error codes */
+#define MF_OK 0
+#define MF_EINVAL -1   /* bad argument (null pointer, n out of range, unsupported shape) */
+#define MF_ECUDA -2    /* CUDA runtime error (launch failure, ...) */
+#define MF_EUNSUPPORTED -3
+
+/* dtypes of device buffers */
+#define MF_F32 0
+#define MF_F64 1
+
+/* arithmetic used inside the RAMBO kernels */
+#define MF_COMPUTE_F64 0 /* reference arithmetic (the reference works in fp64), parity mode */
+#define MF_COMPUTE_F32 1 /* cancellation-free fp32 formulation, throughput mode */
+
+#define MF_MAX_FINAL 16 /* largest supported final-state multiplicity */
+
+/* reference quirks that can be reproduced bit-for-bit on request */
+#define MF_QUIRK_F32_VOLUME 1 /* get_flatWeights casts E_cm to fp32 (rambo_generator.py:132):
+                                 (E_cm^2)^(n-2) overflows to +inf for n=8 above ~1.6 TeV */
+
+/* per-event anomaly flags (optional int32 buffer, one word per event) */
+#define MF_FLAG_NAN_INPUT 1      /* NaN in the uniforms (reference raises, rambo_generator.py:191-199) */
+#define MF_FLAG_NOT_CM 2         /* |sum p|^2 >= 1e-3 in the inverse (reference raises, :630-635) */
+#define MF_FLAG_BELOW_THRESHOLD 4 /* E_cm <= sum of masses */
+
+/*
+ * Process constants of one FlatInvertiblePhasespace instance.
+ * The reference evaluates every mass-only quantity in fp32 because masses_t is an
+ * fp32 tensor (rambo_generator.py:57-58); the host shim computes them with the same
+ * torch fp32 ops and hands the (fp32-representable) results over as doubles so that
+ * device code and oracle reproduce the reference exactly.
+ */
+typedef struct mf_rambo_desc {
+  int32_t n_final;  /* n, 3..MF_MAX_FINAL (the reference fails below 3) */
+  int32_t quirks;   /* MF_QUIRK_* */
+  double sqrt_s;    /* collider_energy */
+  double mass[MF_MAX_FINAL];         /* masses_t[i] */
+  double mass_sq[MF_MAX_FINAL];      /* float32(masses_t[i]**2), set_square_t argument (:337,339) */
+  double tail_sum_fwd[MF_MAX_FINAL]; /* flip(cumsum(flip(masses_t)))[i] (:484-486) */
+  double tail_sum_inv[MF_MAX_FINAL]; /* torch.sum(masses_t[i:]) (:660) */
+  double sum_mass;                   /* tot_final_state_masses (:58) */
+  double x_q;    /* q = -log((sum_mass/sqrt_s)**2), fp32 (phasespace/utils.py:266-268) */
+  double x_A;    /* A = (m/2) q^2 + q^2 with m=-1, fp32 (:269) */
+  double x_c1;   /* float32(-q/A) (:272) */
+  double x_c1sq; /* float32((-q/A)**2) */
+  double x_c2;   /* float32(m/A) = float32(-1/A) */
+  double last_plus_sq;  /* float32((m[n-1]+m[n-2])**2) (rambo_generator.py:489-493) */
+  double last_minus_sq; /* float32((m[n-1]-m[n-2])**2) */
+  double vol_coef; /* (2 pi)^(4-3n) (pi/2)^(n-1) (:134-135) */
+  double vol_fact; /* (n-1)! (n-2)! (:138) */
+  double pt_min_cut;   /* <=0: disabled.  (:352-365) */
+  double delr_min_cut; /* <=0: disabled.  (:367-381) */
+  double rap_max_cut;  /* <=0: disabled.  (:383-391) */
+} mf_rambo_desc;
+
+/* ------------------------------------------------------------------------- */
+/* library                                                                    */
+int mf_abi_version(void);
+const char* mf_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+unsigned long long mf_launch_count(void);
+
+/* ------------------------------------------------------------------------- */
+/* RAMBO on diet                                                              */
+
+/*
+ * Forward map, replaces FlatInvertiblePhasespace.generateKinematics_batch
+ * (rambo_generator.py:168-398) as called by PhaseSpace.get_momenta_from_ps
+ * (phasespace.py:82-103).
+ *   d_r        [N, 3n-2]   uniforms: [0:n-2] masses, [n-2:3n-4] (cos theta, phi) pairs, [-2:] x1x2
+ *   d_momenta  [N, n+2, 4] CM-frame momenta, rows 0,1 incoming            (may be NULL)
+ *   d_weight   [N]         Jacobian weight (times 0/1 for cuts)           (may be NULL)
+ *   d_logw     [N]         log of the un-cut weight, finite where d_weight overflows (may be NULL)
+ *   d_x1,d_x2  [N]                                                        (may be NULL)
+ *   d_flags    [N] int32   MF_FLAG_*                                      (may be NULL)
+ * io_dtype selects fp32 or fp64 for ALL floating buffers of the call.
+ */
+int mf_rambo_forward(const mf_rambo_desc* desc, const void* d_r, int64_t n_events,
+                     void* d_momenta, void* d_weight, void* d_logw, void* d_x1, void* d_x2,
+                     int32_t* d_flags, int io_dtype, int compute, void* stream);
+int mf_rambo_forward_f32(const mf_rambo_desc* desc, const float* d_r, int64_t n_events,
+                         float* d_momenta, float* d_weight, float* d_logw, float* d_x1,
+                         float* d_x2, int32_t* d_flags, void* stream);
+int mf_rambo_forward_f64(const mf_rambo_desc* desc, const double* d_r, int64_t n_events,
+                         double* d_momenta, double* d_weight, double* d_logw, double* d_x1,
+                         double* d_x2, int32_t* d_flags, void* stream);
+
+/*
+ * Inverse map, replaces getPSpoint_batch (rambo_generator.py:615-736) as called by
+ * PhaseSpace.get_ps_from_momenta (phasespace.py:105-109).
+ *   d_momenta  [N, n, 4]  final-state momenta in the CM frame
+ *   d_x1,d_x2  [N]
+ *   perm       [n] host   `order` argument (NULL = identity); desc must hold the PERMUTED masses
+ *   d_r        [N, 3n-2]  uniforms
+ *   d_detjacinv[N]        1/weight                                        (may be NULL)
+ *   d_flags    [N] int32  MF_FLAG_NOT_CM, ...                             (may be NULL)
+ */
+int mf_rambo_inverse(const mf_rambo_desc* desc, const void* d_momenta, const void* d_x1,
+                     const void* d_x2, const int32_t* perm, int64_t n_events, void* d_r,
+                     void* d_detjacinv, int32_t* d_flags, int io_dtype, int compute,
+                     void* stream);
+int mf_rambo_inverse_f32(const mf_rambo_desc* desc, const float* d_momenta, const float* d_x1,
+                         const float* d_x2, const int32_t* perm, int64_t n_events, float* d_r,
+                         float* d_detjacinv, int32_t* d_flags, void* stream);
+int mf_rambo_inverse_f64(const mf_rambo_desc* desc, const double* d_momenta, const double* d_x1,
+                         const double* d_x2, const int32_t* perm, int64_t n_events, double* d_r,
+                         double* d_detjacinv, int32_t* d_flags, void* stream);
+
+/*
+ * Compute_ParticlesTensor.get_PS (unfolding_flow/utils.py:1056-1152): n=4 inverse
+ * without Jacobian; x1,x2 from the boost four-vector; bool problem mask.
+ *   d_momenta [N,4,4], d_boost [N,4] (E,px,py,pz of the total system in the lab)
+ *   d_ps      [N,10]   cat(r, r_x1x2)
+ *   d_mask    [N] uint8 (torch.bool) mask_problems
+ * desc->sqrt_s is E_CM, desc masses are target_mass[perm].
+ */
+int mf_rambo_get_ps(const mf_rambo_desc* desc, const void* d_momenta, const void* d_boost,
+                    const int32_t* perm, int64_t n_events, void* d_ps, uint8_t* d_mask,
+                    int io_dtype, int compute, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MEMFLOW_B200_H */
