@@ -1,0 +1,102 @@
+"""ctypes binding of libmemflow_b200.so (the C ABI declared in include/memflow_b200.h).
+
+There is deliberately NO fallback: if the shared library is missing or a call fails, the
+product path raises.  PyTorch only provides device memory and streams here.
+"""
+import ctypes
+import os
+
+import torch
+
+from .phasespace._desc import RamboDesc
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libmemflow_b200.so")
+
+MF_F32, MF_F64 = 0, 1
+MF_COMPUTE_F64, MF_COMPUTE_F32 = 0, 1
+MF_FLAG_NAN_INPUT, MF_FLAG_NOT_CM, MF_FLAG_BELOW_THRESHOLD = 1, 2, 4
+
+_lib = None
+
+
+class MemflowB200Error(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the CUDA extension; raise loudly if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MemflowB200Error(
+                f"{LIB_PATH} not found: build it with `python -m memflow_msci_project_b200.build` "
+                "(there is no CPU or eager fallback on purpose)")
+        L = ctypes.CDLL(LIB_PATH)
+        L.mf_last_error.restype = ctypes.c_char_p
+        L.mf_launch_count.restype = ctypes.c_ulonglong
+        L.mf_abi_version.restype = ctypes.c_int
+        _lib = L
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().mf_last_error().decode(errors="replace")
+        raise MemflowB200Error(f"{what} failed (rc={rc}): {msg}")
+
+
+def launch_count():
+    return int(lib().mf_launch_count())
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def io_dtype_of(t):
+    if t.dtype == torch.float32:
+        return MF_F32
+    if t.dtype == torch.float64:
+        return MF_F64
+    raise TypeError(f"unsupported dtype {t.dtype} (float32/float64 only)")
+
+
+def require_cuda(t, name):
+    if not t.is_cuda:
+        raise MemflowB200Error(
+            f"{name} lives on {t.device}: the B200 path has no CPU fallback, move it to a CUDA device")
+
+
+def rambo_forward(desc: RamboDesc, r, momenta, weight, logw, x1, x2, flags, compute):
+    with torch.cuda.device(r.device):
+        rc = lib().mf_rambo_forward(ctypes.byref(desc), _ptr(r), ctypes.c_int64(r.shape[0]),
+                                    _ptr(momenta), _ptr(weight), _ptr(logw), _ptr(x1), _ptr(x2),
+                                    _ptr(flags), ctypes.c_int(io_dtype_of(r)), ctypes.c_int(compute),
+                                    _stream(r.device))
+    check(rc, "mf_rambo_forward")
+
+
+def rambo_inverse(desc: RamboDesc, momenta, x1, x2, perm, r, detjacinv, flags, compute):
+    n = desc.n_final
+    perm_arr = (ctypes.c_int32 * n)(*perm) if perm is not None else None
+    with torch.cuda.device(momenta.device):
+        rc = lib().mf_rambo_inverse(ctypes.byref(desc), _ptr(momenta), _ptr(x1), _ptr(x2), perm_arr,
+                                    ctypes.c_int64(momenta.shape[0]), _ptr(r), _ptr(detjacinv),
+                                    _ptr(flags), ctypes.c_int(io_dtype_of(momenta)),
+                                    ctypes.c_int(compute), _stream(momenta.device))
+    check(rc, "mf_rambo_inverse")
+
+
+def rambo_get_ps(desc: RamboDesc, momenta, boost, perm, ps, mask, compute):
+    perm_arr = (ctypes.c_int32 * 4)(*perm) if perm is not None else None
+    with torch.cuda.device(momenta.device):
+        rc = lib().mf_rambo_get_ps(ctypes.byref(desc), _ptr(momenta), _ptr(boost), perm_arr,
+                                   ctypes.c_int64(momenta.shape[0]), _ptr(ps), _ptr(mask),
+                                   ctypes.c_int(io_dtype_of(momenta)), ctypes.c_int(compute),
+                                   _stream(momenta.device))
+    check(rc, "mf_rambo_get_ps")

@@ -1,0 +1,203 @@
+"""GPU parity tests of the fused RAMBO kernels, called through the C ABI via the drop-in shims.
+
+Oracle = oracle/rambo_oracle.c (pinned to the reference by tests/golden) and the golden vectors
+themselves.  Tolerances (north star: 1e-5 relative for fp32 momenta, exact masks):
+  * parity mode (compute="f64"): |dP| <= 1e-5 * E_particle for every component of every particle,
+    weight / x1 / x2 to 1e-5 relative, r to 1e-5 absolute (phi columns modulo 1), masks exact;
+  * throughput mode (compute="f32"): reported as quantiles, gated relative to the event scale.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN_RAMBO, momenta_rel_err, rel_err, wrap_diff
+from memflow_msci_project_b200.phasespace._desc import build_rambo_desc
+from memflow_msci_project_b200.phasespace.phasespace import PhaseSpace
+from memflow_msci_project_b200.phasespace.rambo_generator import PhaseSpaceGeneratorError
+from memflow_msci_project_b200.unfolding_flow.utils import Compute_ParticlesTensor
+from oracle import rambo as orc
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def load(golden_dir, name):
+    return dict(np.load(f"{golden_dir}/rambo_{name}.npz"))
+
+
+def make_ps(masses, dev, **kw):
+    return PhaseSpace(13000, [21, 21], [0] * len(masses), final_masses=torch.tensor(masses), dev=dev, **kw)
+
+
+@pytest.mark.parametrize("name", GOLDEN_RAMBO)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_forward_golden(cuda, golden_dir, name, dtype):
+    g = load(golden_dir, name)
+    ps = make_ps(g["masses"].tolist(), cuda)
+    r = torch.from_numpy(g["r"]).to(cuda, dtype)
+    mom, w, x1, x2 = ps.get_momenta_from_ps(r)
+    assert mom.dtype == dtype and mom.shape == g["momenta"].shape
+    mom, w, x1, x2 = (t.double().cpu().numpy() for t in (mom, w, x1, x2))
+    assert momenta_rel_err(mom, g["momenta"]).max() < RTOL
+    assert rel_err(x1, g["x1"]).max() < RTOL and rel_err(x2, g["x2"]).max() < RTOL
+    fin = np.isfinite(g["weight"])
+    assert np.array_equal(np.isfinite(w), fin)  # reference's fp32 volume overflow reproduced
+    assert rel_err(w[fin], g["weight"][fin]).max() < RTOL
+
+
+@pytest.mark.parametrize("name", GOLDEN_RAMBO)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_inverse_golden(cuda, golden_dir, name, dtype):
+    g = load(golden_dir, name)
+    ps = make_ps(g["masses"].tolist(), cuda)
+    # fp64 inputs reproduce the reference exactly; fp32 inputs are compared to the oracle fed the
+    # SAME fp32-rounded momenta (rounding 1e-5-GeV gluon masses changes the answer itself)
+    P = torch.from_numpy(g["momenta"][:, 2:]).to(cuda, dtype)
+    x1 = torch.from_numpy(g["x1"]).to(cuda, dtype)
+    x2 = torch.from_numpy(g["x2"]).to(cuda, dtype)
+    r, prob = ps.get_ps_from_momenta(P, x1, x2)
+    desc = build_rambo_desc(torch.tensor(g["masses"]), 13000)
+    r_ref, prob_ref, _ = orc.inverse(desc, P.double().cpu().numpy(), x1.double().cpu().numpy(),
+                                     x2.double().cpu().numpy())
+    r, prob = r.double().cpu().numpy(), prob.double().cpu().numpy()
+    ok = np.isfinite(r_ref).all(1)
+    assert ok.mean() > 0.95
+    assert wrap_diff(r[ok], r_ref[ok]).max() < RTOL
+    okp = ok & np.isfinite(prob_ref) & (prob_ref != 0)
+    assert rel_err(prob[okp], prob_ref[okp]).max() < 10 * RTOL if dtype == torch.float32 else RTOL
+    if dtype == torch.float64:
+        assert wrap_diff(r, g["r_inv"]).max() < RTOL
+        okg = np.isfinite(g["detjacinv"]) & (g["detjacinv"] != 0)
+        assert rel_err(prob[okg], g["detjacinv"][okg]).max() < RTOL
+
+
+@pytest.mark.parametrize("name", ["n3_Htt", "n4_HttG"])
+def test_cuts_golden(cuda, golden_dir, name):
+    g = load(golden_dir, name)
+    ps = make_ps(g["masses"].tolist(), cuda)
+    pt, dr, eta = (float(v) for v in g["cuts"])
+    r = torch.from_numpy(g["r"]).to(cuda, torch.float64)
+    _, w, _, _ = ps.get_momenta_from_ps(r, pT_mincut=pt, delR_mincut=dr, rap_maxcut=eta)
+    w = w.cpu().numpy()
+    assert np.array_equal(w == 0, g["weight_cuts"] == 0)
+    keep = w != 0
+    assert rel_err(w[keep], g["weight_cuts"][keep]).max() < RTOL
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_get_ps_golden(cuda, golden_dir, dtype):
+    g = dict(np.load(f"{golden_dir}/rambo_get_PS.npz"))
+    P = torch.from_numpy(g["momenta"]).to(cuda, dtype)
+    B = torch.from_numpy(g["boost"]).to(cuda, dtype)
+    ps, jac, mask = Compute_ParticlesTensor.get_PS(P, B)
+    assert mask.dtype == torch.bool and jac.abs().max().item() == 0
+    tm = torch.Tensor([[125.25, 172.5, 172.5, 1e-5]])
+    desc = build_rambo_desc(tm[0], 13000, sum_mass=tm.sum())
+    ps_ref, mask_ref = orc.get_ps(desc, P.double().cpu().numpy(), B.double().cpu().numpy())
+    assert np.array_equal(mask.cpu().numpy(), mask_ref)  # exact mask parity
+    good = ~mask_ref
+    assert wrap_diff(ps.double().cpu().numpy()[good], ps_ref[good]).max() < RTOL
+    if dtype == torch.float64:
+        assert np.array_equal(mask.cpu().numpy(), g["mask"])
+        assert wrap_diff(ps.cpu().numpy()[~g["mask"]], g["ps"][~g["mask"]]).max() < RTOL
+        perm = [int(i) for i in g["perm"]]
+        ps2, _, mask2 = Compute_ParticlesTensor.get_PS(P, B, order=perm, target_mass=tm)
+        assert np.array_equal(mask2.cpu().numpy(), g["mask_perm"])
+        assert wrap_diff(ps2.cpu().numpy()[~g["mask_perm"]], g["ps_perm"][~g["mask_perm"]]).max() < RTOL
+
+
+@pytest.mark.parametrize("masses,N", [([125.25, 172.5, 172.5, 1e-5], 100003),
+                                      ([4.7, 4.7, 4.7, 1e-3, 1e-3, 4.7, 1e-3, 1e-3], 50001),
+                                      ([80.4, 91.2, 1.0, 2.0, 3.0, 0.5, 0.1], 4097),   # generic-n kernel
+                                      ([125.25, 172.5, 172.5, 1e-5], 4), ([125.25, 172.5, 172.5, 1e-5], 1)])
+def test_forward_vs_oracle_seeded(cuda, masses, N):
+    """Seeded uniforms, ragged tile counts, oracle fed the same fp32 values cast to fp64."""
+    n = len(masses)
+    g = torch.Generator().manual_seed(1234)
+    r32 = torch.rand(N, 3 * n - 2, generator=g).clamp_(1e-6, 1 - 1e-6)
+    desc = build_rambo_desc(torch.tensor(masses), 13000)
+    mom_ref, w_ref, logw_ref, x1_ref, x2_ref, _ = orc.forward(desc, r32.double().numpy())
+    ps = make_ps(masses, cuda)
+    mom, w, x1, x2, logw = ps.generator.generateKinematics_batch(r32.to(cuda), want_logw=True)
+    mom, w, x1, x2, logw = (t.double().cpu().numpy() for t in (mom, w, x1, x2, logw))
+    assert momenta_rel_err(mom, mom_ref).max() < RTOL
+    fin = np.isfinite(w_ref)
+    assert np.array_equal(np.isfinite(w), fin)
+    assert rel_err(w[fin], w_ref[fin]).max() < RTOL
+    assert np.abs(logw - logw_ref).max() < 1e-5 * np.maximum(1, np.abs(logw_ref)).max()
+    assert rel_err(x1, x1_ref).max() < RTOL and rel_err(x2, x2_ref).max() < RTOL
+
+
+def test_empty_batch(cuda):
+    ps = make_ps([125.25, 172.5, 172.5, 1e-5], cuda)
+    mom, w, x1, x2 = ps.get_momenta_from_ps(torch.empty(0, 10, device=cuda))
+    assert mom.shape == (0, 6, 4) and w.shape == (0,)
+    r, p = ps.get_ps_from_momenta(mom[:, 2:], x1, x2)
+    assert r.shape == (0, 10)
+
+
+def test_unaligned_view_input(cuda):
+    """Inputs that are not 16-byte aligned take the plain ld/st staging path."""
+    masses = [125.25, 172.5, 172.5, 1e-5]
+    ps = make_ps(masses, cuda)
+    g = torch.Generator().manual_seed(5)
+    base = torch.rand(1 + 1000 * 10, generator=g).clamp_(1e-6, 1 - 1e-6).to(cuda)
+    r = base[1:].view(1000, 10)  # 4-byte offset
+    assert r.data_ptr() % 16 != 0
+    a = ps.get_momenta_from_ps(r)
+    b = ps.get_momenta_from_ps(r.clone())
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+
+
+def test_error_conventions(cuda):
+    ps = make_ps([125.25, 172.5, 172.5, 1e-5], cuda)
+    r = torch.rand(16, 10, device=cuda)
+    r[3, 2] = float("nan")
+    with pytest.raises(PhaseSpaceGeneratorError):   # rambo_generator.py:191-199
+        ps.get_momenta_from_ps(r)
+    with pytest.raises(AssertionError):             # :251
+        ps.get_momenta_from_ps(torch.rand(16, 9, device=cuda))
+    mom, w, x1, x2 = ps.get_momenta_from_ps(torch.rand(16, 10, device=cuda))
+    bad = mom[:, 2:].clone()
+    bad[2, 0, 1] += 5.0
+    with pytest.raises(Exception, match="not in the CM"):  # :630-635
+        ps.get_ps_from_momenta(bad, x1, x2)
+
+
+def test_million_event_round_trip(cuda):
+    """Full-size property test: r -> momenta -> r at 1e6 events (fp64 I/O), conservation, masses."""
+    masses = [125.25, 172.5, 172.5, 1e-5]
+    ps = make_ps(masses, cuda, reference_quirks=False)
+    g = torch.Generator(device=cuda).manual_seed(99)
+    r = torch.rand(1_000_000, 10, generator=g, device=cuda, dtype=torch.float64).clamp_(1e-6, 1 - 1e-6)
+    mom, w, x1, x2 = ps.get_momenta_from_ps(r)
+    tot = mom[:, 2:].sum(1) - mom[:, :2].sum(1)
+    assert tot.abs().max().item() < 2e-3
+    m = torch.sqrt((mom[:, 2:5, 0] ** 2 - (mom[:, 2:5, 1:] ** 2).sum(-1)).clamp_min(0))
+    assert (m - torch.tensor(masses[:3], device=cuda, dtype=torch.float64)).abs().max().item() < 1e-6
+    r2, prob = ps.get_ps_from_momenta(mom[:, 2:], x1, x2)
+    d = (r2 - r).abs()
+    d = torch.minimum(d, 1 - d)
+    assert d.max().item() < 5e-6
+    assert (w * prob - 1).abs().max().item() < 1e-5
+
+
+def test_fp32_compute_mode_quantiles(cuda):
+    """Throughput mode (fp32 arithmetic): accuracy relative to the event scale E_cm, as quantiles."""
+    masses = [125.25, 172.5, 172.5, 1e-5]
+    g = torch.Generator().manual_seed(4)
+    r32 = torch.rand(200000, 10, generator=g).clamp_(1e-6, 1 - 1e-6)
+    desc = build_rambo_desc(torch.tensor(masses), 13000)
+    mom_ref, w_ref, _, x1_ref, x2_ref, _ = orc.forward(desc, r32.double().numpy())
+    ps = make_ps(masses, cuda, compute="f32")
+    mom, w, x1, x2 = ps.get_momenta_from_ps(r32.to(cuda))
+    mom, w = mom.double().cpu().numpy(), w.double().cpu().numpy()
+    scale = mom_ref[:, 0:1, 0:1] * 2  # E_cm
+    err = (np.abs(mom - mom_ref) / scale).max(axis=(1, 2))
+    werr = rel_err(w, w_ref)
+    print("fp32-compute |dP|/E_cm quantiles 50/99/99.9/max:", np.quantile(err, [0.5, 0.99, 0.999, 1.0]))
+    print("fp32-compute dW/W quantiles 50/99/99.9/max:", np.quantile(werr, [0.5, 0.99, 0.999, 1.0]))
+    assert np.quantile(err, 0.999) < 1e-5 and np.median(err) < 1e-6
+    assert np.quantile(werr, 0.99) < 1e-4
