@@ -156,6 +156,85 @@ int mf_rambo_get_ps(const mf_rambo_desc* desc, const void* d_momenta, const void
                     const int32_t* perm, int64_t n_events, void* d_ps, uint8_t* d_mask,
                     int io_dtype, int compute, void* stream);
 
+/* ------------------------------------------------------------------------- */
+/* conditional RQ-spline masked autoregressive flow (zuko NSF / MAF family)  */
+
+#define MF_MAX_HIDDEN_LAYERS 8
+#define MF_MAX_FEATURES 64
+#define MF_MAX_TRANSFORMS 64
+
+/* univariate transformation of every feature (zuko.transforms) */
+#define MF_UNIV_RQS 0          /* MonotonicRQSTransform(*phi, bound) */
+#define MF_UNIV_CIRCULAR_RQS 1 /* CircularShiftTransform(bound) then RQS: NCSF, periodicNSF_gaussian.py:15-21 */
+#define MF_UNIV_PS_RQS 2       /* PSTransform ((x+1)/2, ladj log 1/2) then RQS(bound=1): ttH/transfer_flow/custom_flows.py:10-48 */
+
+/* base distribution (zuko.distributions) */
+#define MF_BASE_DIAG_NORMAL 0 /* base_a = loc, base_b = scale */
+#define MF_BASE_BOX_UNIFORM 1 /* base_a = lower, base_b = upper; log_prob = -inf outside [lower, upper) */
+
+/* arithmetic of the conditioner (hyper-network) GEMMs */
+#define MF_GEMM_EXACT 0  /* CUDA-core FMA in the I/O dtype (fp32 or fp64): bit-for-bit class of torch fp32 */
+#define MF_GEMM_TC_3XF16 1 /* tcgen05, fp16 hi/lo split operands, 3 MMAs per product, fp32 accumulate */
+#define MF_GEMM_TC_BF16 2  /* tcgen05, bf16 operands, fp32 accumulate: throughput mode */
+
+/*
+ * Static description of one flow = zuko.flows.NSF(features, context, transforms, bins,
+ * hidden_features, passes, ...) and its local subclasses (a13 in SURVEY.md section 8).
+ * All transforms share one shape; masks are already folded into the packed weights.
+ */
+typedef struct mf_flow_desc {
+  int32_t features;   /* D */
+  int32_t context;    /* C */
+  int32_t bins;       /* K: 3K-1 spline parameters per feature */
+  int32_t transforms; /* T */
+  int32_t n_hidden;   /* L hidden layers */
+  int32_t hidden[MF_MAX_HIDDEN_LAYERS];
+  int32_t passes;     /* AutoregressiveTransform.passes (fixed-point sweeps of the inverse) */
+  int32_t univariate; /* MF_UNIV_* */
+  int32_t base;       /* MF_BASE_* */
+  int32_t reserved;
+  double bound;       /* spline domain [-bound, bound] */
+  double slope;       /* soft-clip slope of MonotonicRQSTransform (1e-3 in zuko >= 0.2); <= 0 disables */
+  double base_a[MF_MAX_FEATURES];
+  double base_b[MF_MAX_FEATURES];
+} mf_flow_desc;
+
+/* bytes of the packed-weight blob for (desc, dtype, gemm mode) */
+int64_t mf_flow_blob_bytes(const mf_flow_desc* desc, int dtype, int gemm);
+
+/*
+ * Pack zuko-layout parameters into the kernel blob (mask folded in, transposed, padded).
+ *   d_weights[t*(L+1)+l]  device pointer to MaskedLinear.weight [out_l, in_l] (dtype)
+ *   d_biases [t*(L+1)+l]  device pointer to MaskedLinear.bias   [out_l]
+ *   d_masks  [t*(L+1)+l]  device pointer to MaskedLinear.mask   [out_l, in_l] (uint8 / torch.bool)
+ * The three pointer tables live on the HOST.  Replaces the per-call `mask * weight` of
+ * zuko.nn.MaskedLinear.forward.
+ */
+int mf_flow_pack_weights(const mf_flow_desc* desc, const void* const* d_weights,
+                         const void* const* d_biases, const uint8_t* const* d_masks, int dtype,
+                         int gemm, void* d_blob, int64_t blob_bytes, void* stream);
+
+/*
+ * flow(c).log_prob(x) / flow(c).transform(x)  (a14, a15).
+ *   d_x [N,D], d_ctx [N,C] (NULL when C = 0)
+ *   d_logprob [N]  base.log_prob(z) + ladj           (may be NULL)
+ *   d_z [N,D], d_ladj [N]                             (may be NULL)
+ *   d_bins [T,N,D] int8 bin index of every spline evaluation, d_inside [T,N,D] uint8 in-range mask
+ *                                                     (parity instrumentation, may be NULL)
+ */
+int mf_flow_log_prob(const mf_flow_desc* desc, const void* d_blob, const void* d_x,
+                     const void* d_ctx, int64_t n, void* d_logprob, void* d_z, void* d_ladj,
+                     int8_t* d_bins, uint8_t* d_inside, int dtype, int gemm, void* stream);
+
+/*
+ * flow(c).sample() / .rsample()  (a16): x = T^-1(z), z = base sample built from caller-supplied
+ * noise (standard normals for DiagNormal, uniforms in [0,1) for BoxUniform) so that reference and
+ * kernel can be fed identical noise.
+ *   d_noise [N,D] -> d_x [N,D];  d_ctx [N,C]
+ */
+int mf_flow_sample(const mf_flow_desc* desc, const void* d_blob, const void* d_noise,
+                   const void* d_ctx, int64_t n, void* d_x, int dtype, int gemm, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -100,3 +100,48 @@ def rambo_get_ps(desc: RamboDesc, momenta, boost, perm, ps, mask, compute):
                                    ctypes.c_int(io_dtype_of(momenta)), ctypes.c_int(compute),
                                    _stream(momenta.device))
     check(rc, "mf_rambo_get_ps")
+
+
+# ---- conditional spline flows ---------------------------------------------------------------------
+def _dtype_code(dtype):
+    return {torch.float32: MF_F32, torch.float64: MF_F64}[dtype]
+
+
+def flow_blob_bytes(desc, dtype, gemm):
+    L = lib()
+    L.mf_flow_blob_bytes.restype = ctypes.c_int64
+    n = L.mf_flow_blob_bytes(ctypes.byref(desc), ctypes.c_int(_dtype_code(dtype)), ctypes.c_int(gemm))
+    if n < 0:
+        check(-1, "mf_flow_blob_bytes")
+    return int(n)
+
+
+def flow_pack_weights(desc, weights, biases, masks, dtype, gemm, blob):
+    n = len(weights)
+    arr_t = ctypes.c_void_p * n
+    w = arr_t(*[t.data_ptr() for t in weights])
+    b = arr_t(*[t.data_ptr() for t in biases])
+    m = arr_t(*[t.data_ptr() for t in masks])
+    with torch.cuda.device(blob.device):
+        rc = lib().mf_flow_pack_weights(ctypes.byref(desc), w, b, m, ctypes.c_int(_dtype_code(dtype)),
+                                        ctypes.c_int(gemm), _ptr(blob), ctypes.c_int64(blob.numel()),
+                                        _stream(blob.device))
+    check(rc, "mf_flow_pack_weights")
+
+
+def flow_log_prob(desc, blob, x, ctx, logprob, z, ladj, bins, inside, gemm):
+    with torch.cuda.device(x.device):
+        rc = lib().mf_flow_log_prob(ctypes.byref(desc), _ptr(blob), _ptr(x), _ptr(ctx),
+                                    ctypes.c_int64(x.shape[0]), _ptr(logprob), _ptr(z), _ptr(ladj),
+                                    _ptr(bins), _ptr(inside), ctypes.c_int(_dtype_code(x.dtype)),
+                                    ctypes.c_int(gemm), _stream(x.device))
+    check(rc, "mf_flow_log_prob")
+
+
+def flow_sample(desc, blob, noise, ctx, x, gemm):
+    with torch.cuda.device(noise.device):
+        rc = lib().mf_flow_sample(ctypes.byref(desc), _ptr(blob), _ptr(noise), _ptr(ctx),
+                                  ctypes.c_int64(noise.shape[0]), _ptr(x),
+                                  ctypes.c_int(_dtype_code(noise.dtype)), ctypes.c_int(gemm),
+                                  _stream(noise.device))
+    check(rc, "mf_flow_sample")

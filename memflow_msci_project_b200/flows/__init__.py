@@ -1,0 +1,10 @@
+"""zuko-shaped conditional spline flows on fused sm_100a kernels (see modules.py)."""
+from .modules import (MAF, NCSF, NSF, BoxUniform, DiagNormal, MaskedAutoregressiveTransform, MaskedLinear,
+                      MaskedMLP, NormalizingFlow, SimpleAffineTransform, Unconditional,
+                      UnconditionalDistribution)
+from .custom import NCSF_gaussian, Custom_spline_flow_ps, PSNSF, UniformNCSF, UniformNSF
+
+__all__ = ["MAF", "NSF", "NCSF", "BoxUniform", "DiagNormal", "MaskedAutoregressiveTransform", "MaskedLinear",
+           "MaskedMLP", "NormalizingFlow", "SimpleAffineTransform", "Unconditional",
+           "UnconditionalDistribution", "NCSF_gaussian", "Custom_spline_flow_ps", "PSNSF", "UniformNCSF",
+           "UniformNSF"]

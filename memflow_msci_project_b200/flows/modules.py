@@ -1,0 +1,476 @@
+"""``nn.Module`` surface of the conditional spline flows, shaped like the zuko objects MEMFlow uses.
+
+What the reference does with these objects (b):
+  ``flow = zuko.flows.NSF(features=D, context=C, transforms=T, bins=K, hidden_features=[H]*L,
+  randperm=..., passes=..., base=..., base_args=[a, b], univariate_kwargs={"bound": B})``
+  (memflow/unfolding_flow/unfolding_flow.py:88-97, transfer_flow_paper_AllPartons_btag.py:80-129),
+  then ``flow(c).log_prob(x)``, ``flow(c).rsample((S,))`` / ``.sample((S,))``, ``flow(c).transform(x)``,
+  ``flow.transforms`` (list-like), ``flow.base()``, ``.float()/.double()/.to()``, state dicts.
+
+Parameters keep zuko's layout (``transforms.{t}.hyper.{2l}.{weight,bias,mask}``, ``transforms.{t}.order``,
+``base._0/_1``) so reference checkpoints load; the compute is ONE fused sm_100a kernel per call through
+the C ABI (include/memflow_b200.h: mf_flow_log_prob / mf_flow_sample) on a packed copy of the weights
+that is rebuilt whenever a parameter changes.  There is no torch/CPU fallback.
+"""
+import ctypes
+import math
+
+import torch
+import torch.nn as nn
+
+from .. import _cabi
+from . import masks as _masks
+
+MF_MAX_HIDDEN_LAYERS = 8
+MF_MAX_FEATURES = 64
+
+UNIV_RQS, UNIV_CIRCULAR_RQS, UNIV_PS_RQS = 0, 1, 2
+BASE_DIAG_NORMAL, BASE_BOX_UNIFORM = 0, 1
+GEMM_EXACT, GEMM_TC_3XF16, GEMM_TC_BF16 = 0, 1, 2
+
+
+class FlowDesc(ctypes.Structure):
+    """ctypes mirror of ``struct mf_flow_desc``."""
+
+    _fields_ = [
+        ("features", ctypes.c_int32), ("context", ctypes.c_int32), ("bins", ctypes.c_int32),
+        ("transforms", ctypes.c_int32), ("n_hidden", ctypes.c_int32),
+        ("hidden", ctypes.c_int32 * MF_MAX_HIDDEN_LAYERS),
+        ("passes", ctypes.c_int32), ("univariate", ctypes.c_int32), ("base", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+        ("bound", ctypes.c_double), ("slope", ctypes.c_double),
+        ("base_a", ctypes.c_double * MF_MAX_FEATURES), ("base_b", ctypes.c_double * MF_MAX_FEATURES),
+    ]
+
+
+# ------------------------------------------------------------------------------------------------
+# distributions (zuko.distributions.DiagNormal / BoxUniform are thin torch.distributions wrappers)
+class DiagNormal(torch.distributions.Independent):
+    def __init__(self, loc=0.0, scale=1.0, ndims=1):
+        super().__init__(torch.distributions.Normal(torch.as_tensor(loc), torch.as_tensor(scale)), ndims)
+
+    KIND = BASE_DIAG_NORMAL
+
+
+class BoxUniform(torch.distributions.Independent):
+    def __init__(self, lower=0.0, upper=1.0, ndims=1):
+        super().__init__(torch.distributions.Uniform(torch.as_tensor(lower), torch.as_tensor(upper),
+                                                     validate_args=False), ndims)
+
+    KIND = BASE_BOX_UNIFORM
+
+
+class Unconditional(nn.Module):
+    """zuko.flows.core.Unconditional / UnconditionalDistribution: ``meta(*args)`` with the positional
+    tensors registered as buffers (``buffer=True``) or parameters, under the names ``_0``, ``_1``..."""
+
+    def __init__(self, meta, *args, buffer=False, **kwargs):
+        super().__init__()
+        self.meta = meta
+        for i, arg in enumerate(args):
+            arg = torch.as_tensor(arg)
+            if buffer:
+                self.register_buffer(f"_{i}", arg)
+            else:
+                self.register_parameter(f"_{i}", nn.Parameter(arg))
+        self.kwargs = kwargs
+
+    def tensors(self):
+        return [t for n, t in sorted(list(self.named_buffers()) + list(self.named_parameters()))]
+
+    def forward(self, c=None):
+        return self.meta(*self.tensors(), **self.kwargs)
+
+    def extra_repr(self):
+        return getattr(self.meta, "__name__", repr(self.meta))
+
+
+UnconditionalDistribution = Unconditional
+
+
+# ------------------------------------------------------------------------------------------------
+class MaskedLinear(nn.Linear):
+    """zuko.nn.MaskedLinear: ``F.linear(x, mask * weight, bias)`` with a fixed boolean ``mask`` buffer.
+    Only holds the parameters here; the product is formed inside the fused kernel."""
+
+    def __init__(self, adjacency):
+        super().__init__(adjacency.shape[1], adjacency.shape[0])
+        self.register_buffer("mask", adjacency.to(torch.bool))
+
+    def forward(self, x):  # pragma: no cover - the hot path never calls this
+        raise _cabi.MemflowB200Error("MaskedLinear is evaluated inside the fused flow kernel only")
+
+
+class MaskedMLP(nn.Sequential):
+    """zuko.nn.MaskedMLP layout: MaskedLinear at even indices, ReLU in between."""
+
+    def __init__(self, adjacency, hidden_features=(64, 64)):
+        layers = []
+        for mask in _masks.mlp_masks(adjacency, hidden_features):
+            layers.extend([MaskedLinear(mask), nn.ReLU()])
+        super().__init__(*layers[:-1])
+
+    def linears(self):
+        return [m for m in self if isinstance(m, MaskedLinear)]
+
+
+class MaskedAutoregressiveTransform(nn.Module):
+    """zuko.flows.autoregressive.MaskedAutoregressiveTransform with a rational-quadratic-spline
+    univariate: hyper-network ``(x | c) -> D x (3K-1)`` spline parameters."""
+
+    def __init__(self, features, context=0, passes=None, order=None, bins=8, hidden_features=(64, 64),
+                 univariate=UNIV_RQS, bound=5.0, slope=1e-3):
+        super().__init__()
+        self.features, self.context, self.bins = features, context, bins
+        self.univariate, self.bound, self.slope = univariate, float(bound), slope
+        self.total = 3 * bins - 1
+        adjacency, eff_order, self.passes = _masks.autoregressive_adjacency(features, context, passes,
+                                                                            order, self.total)
+        self.register_buffer("order", eff_order)
+        self.hyper = MaskedMLP(adjacency, hidden_features)
+        self.hidden_features = tuple(int(h) for h in hidden_features)
+
+    def extra_repr(self):
+        kinds = {UNIV_RQS: "MonotonicRQSTransform", UNIV_CIRCULAR_RQS: "CircularShift+MonotonicRQSTransform",
+                 UNIV_PS_RQS: "PSTransform+MonotonicRQSTransform"}
+        return f"(base): {kinds[self.univariate]}(bins={self.bins})\n(order): {self.order.tolist()}"
+
+
+class SimpleAffineTransform(nn.Module):
+    """Element-wise affine map of the interval [a_in, b_in] onto [a_out, b_out] (the zuko fork's
+    ``SimpleAffineTransform``; notebooks/TestFlows_ImportanceSampling.ipynb cell 7 puts one in front
+    of the spline transforms).  Evaluated with torch element-wise ops around the fused kernel."""
+
+    def __init__(self, a_in, b_in, a_out, b_out):
+        super().__init__()
+        for n, v in (("a_in", a_in), ("b_in", b_in), ("a_out", a_out), ("b_out", b_out)):
+            self.register_buffer(n, torch.as_tensor(v, dtype=torch.get_default_dtype()))
+
+    def scale(self):
+        return (self.b_out - self.a_out) / (self.b_in - self.a_in)
+
+    def call_and_ladj(self, x):
+        s = self.scale()
+        return self.a_out + (x - self.a_in) * s, torch.log(torch.abs(s)).sum(-1).expand(x.shape[:-1])
+
+    def inv(self, y):
+        return self.a_in + (y - self.a_out) / self.scale()
+
+
+# ------------------------------------------------------------------------------------------------
+class _Transform:
+    """What ``flow(c).transform`` returns: callable forward map with ``.inv`` and ``.call_and_ladj``."""
+
+    def __init__(self, bound_flow):
+        self._bf = bound_flow
+
+    def __call__(self, x):
+        return self._bf._forward(x, want_logprob=False)[0]
+
+    def call_and_ladj(self, x):
+        z, ladj, _ = self._bf._forward(x, want_logprob=False)
+        return z, ladj
+
+    def inv(self, z):
+        return self._bf._inverse(z)
+
+
+class NormalizingFlow:
+    """``flow(c)``: zuko.distributions.NormalizingFlow bound to a context (a14-a16)."""
+
+    def __init__(self, module, c):
+        self._m = module
+        self._c = c
+
+    # -- properties used by the reference
+    @property
+    def transform(self):
+        return _Transform(self)
+
+    @property
+    def base(self):
+        d = self._m.base()
+        return d if self._c is None else d.expand(self._c.shape[:-1])
+
+    # -- helpers
+    def _split(self):
+        pre, core, post, seen = [], [], [], False
+        for t in self._m.transforms:
+            if isinstance(t, MaskedAutoregressiveTransform):
+                if post:
+                    raise _cabi.MemflowB200Error("element-wise transforms between spline transforms are not supported")
+                core.append(t)
+                seen = True
+            elif isinstance(t, SimpleAffineTransform):
+                (post if seen else pre).append(t)
+            else:
+                raise _cabi.MemflowB200Error(f"unsupported transform module {type(t).__name__}")
+        return pre, core, post
+
+    def _rows(self, x):
+        """Broadcast x [..., D] against the context [..., C] and flatten to rows."""
+        D = self._m.features
+        if x.shape[-1] != D:
+            raise ValueError(f"expected last dimension {D}, got {tuple(x.shape)}")
+        c = self._c
+        if c is None:
+            return x.reshape(-1, D), None, x.shape[:-1]
+        batch = torch.broadcast_shapes(x.shape[:-1], c.shape[:-1])
+        xb = x.expand(*batch, D).reshape(-1, D)
+        cb = c.expand(*batch, c.shape[-1]).reshape(-1, c.shape[-1])
+        return xb, cb, batch
+
+    def _forward(self, x, want_logprob, debug=False):
+        m = self._m
+        pre, core, post = self._split()
+        _cabi.require_cuda(x, "x")
+        if torch.is_grad_enabled() and (x.requires_grad or (self._c is not None and self._c.requires_grad)
+                                        or any(p.requires_grad for p in m.parameters())):
+            from ._autograd import flow_log_prob_autograd
+            return flow_log_prob_autograd(self, x, want_logprob)
+        dtype = m.compute_dtype()
+        ladj_pre = None
+        x = x.to(dtype)
+        for t in pre:
+            x, l = t.call_and_ladj(x)
+            ladj_pre = l if ladj_pre is None else ladj_pre + l
+        xb, cb, batch = self._rows(x)
+        xb = xb.contiguous()
+        cb = cb.to(dtype).contiguous() if cb is not None else None
+        N, D = xb.shape
+        desc, blob = m.packed(xb.device, dtype)
+        z = torch.empty_like(xb)
+        ladj = torch.empty(N, dtype=dtype, device=xb.device)
+        need_lp = want_logprob and not post
+        logprob = torch.empty(N, dtype=dtype, device=xb.device) if need_lp else None
+        bins = inside = None
+        if debug:
+            bins = torch.empty((len(core), N, D), dtype=torch.int8, device=xb.device)
+            inside = torch.empty((len(core), N, D), dtype=torch.uint8, device=xb.device)
+        _cabi.flow_log_prob(desc, blob, xb, cb, logprob, z, ladj, bins, inside, m.gemm)
+        z = z.reshape(*batch, D)
+        ladj = ladj.reshape(batch)
+        if ladj_pre is not None:
+            ladj = ladj + ladj_pre
+            if logprob is not None:
+                logprob = logprob + ladj_pre.reshape(-1)
+        for t in post:
+            z, l = t.call_and_ladj(z)
+            ladj = ladj + l
+        if want_logprob and logprob is None:
+            logprob = self.base.log_prob(z).reshape(-1) + ladj.reshape(-1)
+        if logprob is not None:
+            logprob = logprob.reshape(batch)
+        if debug:
+            return z, ladj, logprob, bins.reshape(len(core), *batch, D), inside.reshape(len(core), *batch, D).bool()
+        return z, ladj, logprob
+
+    def _inverse(self, z, noise_is_base_sample=True):
+        """x = T^-1(z) for z already distributed like the base."""
+        m = self._m
+        pre, core, post = self._split()
+        _cabi.require_cuda(z, "z")
+        dtype = m.compute_dtype()
+        z = z.to(dtype)
+        for t in reversed(post):
+            z = t.inv(z)
+        zb, cb, batch = self._rows(z)
+        zb = zb.contiguous()
+        cb = cb.to(dtype).contiguous() if cb is not None else None
+        desc, blob = m.packed(zb.device, dtype, identity_base=True)
+        x = torch.empty_like(zb)
+        _cabi.flow_sample(desc, blob, zb, cb, x, m.gemm)
+        x = x.reshape(*batch, m.features)
+        for t in reversed(pre):
+            x = t.inv(x)
+        return x
+
+    # -- distribution API
+    def log_prob(self, x):
+        return self._forward(x, want_logprob=True)[2]
+
+    def rsample(self, shape=()):
+        base = self.base
+        z = base.rsample(torch.Size(shape)) if base.has_rsample else base.sample(torch.Size(shape))
+        if torch.is_grad_enabled() and (z.requires_grad or any(p.requires_grad for p in self._m.parameters())):
+            from ._autograd import flow_rsample_autograd
+            return flow_rsample_autograd(self, z)
+        return self._inverse(z)
+
+    def sample(self, shape=()):
+        with torch.no_grad():
+            base = self.base
+            z = base.sample(torch.Size(shape))
+            return self._inverse(z)
+
+    def sample_from_noise(self, noise):
+        """Deterministic sampling from caller-supplied noise [..., D] (standard normals for a
+        DiagNormal base, uniforms in [0,1) for BoxUniform): the identical-noise parity protocol."""
+        m = self._m
+        a, b = m.base_tensors()
+        a, b = a.to(noise), b.to(noise)
+        z = a + b * noise if m.base_kind() == BASE_DIAG_NORMAL else a + (b - a) * noise
+        with torch.no_grad():
+            return self._inverse(z)
+
+    def log_prob_debug(self, x):
+        """(log_prob, z, ladj, bin indices [T,...,D] int8, in-range masks [T,...,D] bool)."""
+        z, ladj, lp, bins, inside = self._forward(x, want_logprob=True, debug=True)
+        return lp, z, ladj, bins, inside
+
+
+# ------------------------------------------------------------------------------------------------
+def _base_kind(meta):
+    kind = getattr(meta, "KIND", None)
+    if kind is None:
+        name = getattr(meta, "__name__", "")
+        kind = {"DiagNormal": BASE_DIAG_NORMAL, "BoxUniform": BASE_BOX_UNIFORM}.get(name)
+    if kind is None:
+        raise _cabi.MemflowB200Error(f"unsupported base distribution {meta!r} (DiagNormal / BoxUniform only)")
+    return kind
+
+
+class MAF(nn.Module):
+    """zuko.flows.autoregressive.MAF with spline univariates = the NSF family.
+
+    Accepts both constructor generations found in the reference: upstream
+    zuko 1.x (``bins, transforms, randperm, passes, hidden_features``) and the valsdav fork
+    (``base=, base_args=, univariate_kwargs={"bound": B}, dtype=``).
+    """
+
+    def __init__(self, features, context=0, transforms=3, randperm=False, bins=8, hidden_features=(64, 64),
+                 passes=None, univariate=UNIV_RQS, bound=5.0, slope=1e-3, base=None, base_args=None,
+                 univariate_kwargs=None, dtype=None, gemm="exact", **unused):
+        super().__init__()
+        if unused:
+            raise TypeError(f"unsupported keyword arguments: {sorted(unused)}")
+        if univariate_kwargs:
+            bound = univariate_kwargs.get("bound", bound)
+            slope = univariate_kwargs.get("slope", slope)
+        self.features, self.context = int(features), int(context)
+        orders = [torch.arange(features), torch.flipud(torch.arange(features))]
+        self.transforms = nn.ModuleList([
+            MaskedAutoregressiveTransform(features=features, context=context, passes=passes,
+                                          order=torch.randperm(features) if randperm else orders[i % 2],
+                                          bins=bins, hidden_features=hidden_features, univariate=univariate,
+                                          bound=bound, slope=slope)
+            for i in range(transforms)])
+        if base is None:
+            self.base = Unconditional(DiagNormal, torch.zeros(features), torch.ones(features), buffer=True)
+        else:
+            args = base_args if base_args is not None else [torch.zeros(features), torch.ones(features)]
+            self.base = Unconditional(base, *args)  # the fork registers base_args as parameters
+        self.gemm = {"exact": GEMM_EXACT, "tc_3xf16": GEMM_TC_3XF16, "tc_bf16": GEMM_TC_BF16}[gemm]
+        self._blob_cache = None
+        self._desc_cache = {}
+        self._register_load_state_dict_pre_hook(self._rename_legacy_keys)
+        if dtype is not None:
+            self.to(dtype)
+
+    # zuko >= 1.0 nests the transforms: transform.transforms.{t}.*  ->  transforms.{t}.*
+    @staticmethod
+    def _rename_legacy_keys(state_dict, prefix, *args):
+        for k in list(state_dict.keys()):
+            if k.startswith(prefix + "transform.transforms."):
+                state_dict[prefix + k[len(prefix) + len("transform."):]] = state_dict.pop(k)
+
+    def forward(self, c=None):
+        if c is not None and c.shape[-1] != self.context:
+            raise ValueError(f"expected context with last dimension {self.context}, got {tuple(c.shape)}")
+        return NormalizingFlow(self, c)
+
+    # -- descriptors / packed weights ---------------------------------------------------------
+    def core_transforms(self):
+        return [t for t in self.transforms if isinstance(t, MaskedAutoregressiveTransform)]
+
+    def compute_dtype(self):
+        p = next(self.core_transforms()[0].hyper.parameters())
+        if p.dtype not in (torch.float32, torch.float64):
+            raise _cabi.MemflowB200Error(f"flow parameters are {p.dtype}; float32/float64 only")
+        return p.dtype
+
+    def base_kind(self):
+        return _base_kind(self.base.meta)
+
+    def base_tensors(self):
+        t = self.base.tensors()
+        if len(t) != 2:
+            raise _cabi.MemflowB200Error("base distribution must have exactly two tensor arguments")
+        return t[0].detach(), t[1].detach()
+
+    def make_desc(self, identity_base=False):
+        core = self.core_transforms()
+        t0 = core[0]
+        for t in core[1:]:
+            same = (t.features, t.context, t.bins, t.hidden_features, t.passes, t.univariate, t.bound, t.slope) == \
+                   (t0.features, t0.context, t0.bins, t0.hidden_features, t0.passes, t0.univariate, t0.bound, t0.slope)
+            if not same:
+                raise _cabi.MemflowB200Error("all spline transforms of a flow must share one shape")
+        if len(t0.hidden_features) > MF_MAX_HIDDEN_LAYERS or t0.features > MF_MAX_FEATURES:
+            raise _cabi.MemflowB200Error("flow exceeds MF_MAX_HIDDEN_LAYERS / MF_MAX_FEATURES")
+        d = FlowDesc()
+        d.features, d.context, d.bins = t0.features, t0.context, t0.bins
+        d.transforms, d.n_hidden = len(core), len(t0.hidden_features)
+        for i, h in enumerate(t0.hidden_features):
+            d.hidden[i] = h
+        d.passes, d.univariate = t0.passes, t0.univariate
+        d.bound = t0.bound
+        d.slope = float(t0.slope) if t0.slope else 0.0
+        if identity_base:  # sampling entry is fed base samples directly: z = 0 + 1 * noise
+            d.base = BASE_DIAG_NORMAL
+            for f in range(t0.features):
+                d.base_a[f], d.base_b[f] = 0.0, 1.0
+        else:
+            d.base = self.base_kind()
+            a, b = self.base_tensors()
+            a, b = a.double().cpu(), b.double().cpu()
+            for f in range(t0.features):
+                d.base_a[f], d.base_b[f] = float(a[f]), float(b[f])
+        return d
+
+    def packed(self, device, dtype, identity_base=False):
+        """(desc, blob): the kernel-side copy of the weights, rebuilt when any parameter changed."""
+        core = self.core_transforms()
+        params = []
+        for t in core:
+            for lin in t.hyper.linears():
+                params += [lin.weight, lin.bias, lin.mask]
+        key = (str(device), dtype, self.gemm, tuple((p.data_ptr(), p._version) for p in params))
+        if self._blob_cache is None or self._blob_cache[0] != key:
+            for p in params:
+                if p.device != device:
+                    raise _cabi.MemflowB200Error(f"flow parameters live on {p.device}, data on {device}")
+            desc = self.make_desc(identity_base=True)
+            ws = [p.detach().to(dtype).contiguous() for p in params[0::3]]
+            bs = [p.detach().to(dtype).contiguous() for p in params[1::3]]
+            ms = [p.detach().to(torch.uint8).contiguous() for p in params[2::3]]
+            nbytes = _cabi.flow_blob_bytes(desc, dtype, self.gemm)
+            blob = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            _cabi.flow_pack_weights(desc, ws, bs, ms, dtype, self.gemm, blob)
+            self._blob_cache = (key, blob)
+        base_key = tuple((t.data_ptr(), t._version) for t in self.base.tensors())
+        dent = self._desc_cache.get(identity_base)
+        if dent is None or dent[0] != base_key:
+            dent = (base_key, self.make_desc(identity_base))
+            self._desc_cache[identity_base] = dent
+        return dent[1], self._blob_cache[1]
+
+
+class NSF(MAF):
+    """zuko.flows.NSF: MAF with MonotonicRQSTransform univariates, shapes [(K,), (K,), (K-1,)]."""
+
+    def __init__(self, features, context=0, bins=8, **kwargs):
+        kwargs.setdefault("univariate", UNIV_RQS)
+        super().__init__(features=features, context=context, bins=bins, **kwargs)
+
+
+class NCSF(MAF):
+    """zuko.flows.NCSF: circular shift + RQS on [-pi, pi], BoxUniform(-pi-1e-5, pi+1e-5) base."""
+
+    def __init__(self, features, context=0, bins=8, **kwargs):
+        kwargs.pop("univariate", None)
+        kwargs.pop("bound", None)
+        super().__init__(features=features, context=context, bins=bins, univariate=UNIV_CIRCULAR_RQS,
+                         bound=math.pi, **kwargs)
+        self.base = Unconditional(BoxUniform, torch.full((features,), -math.pi - 1e-5),
+                                  torch.full((features,), math.pi + 1e-5), buffer=True)

@@ -23,3 +23,19 @@ def rel_err(a, b):
 
 
 GOLDEN_RAMBO = ["n3_Htt", "n4_HttG", "n8_ttH_decay"]
+
+
+def spec_from_module(flow):
+    """Build the oracle's FlowSpec from a product flow module (parameters copied to numpy)."""
+    from oracle import flow_oracle as fo
+    core = flow.core_transforms()
+    t0 = core[0]
+    transforms = []
+    for t in core:
+        layers = [(lin.weight.detach().double().cpu().numpy(), lin.bias.detach().double().cpu().numpy(),
+                   lin.mask.detach().cpu().numpy().astype(bool)) for lin in t.hyper.linears()]
+        transforms.append({"order": t.order.cpu().numpy(), "passes": t.passes, "layers": layers})
+    a, b = flow.base_tensors()
+    return fo.FlowSpec(t0.features, t0.context, t0.bins, transforms, bound=t0.bound, slope=t0.slope,
+                       univariate=t0.univariate, base=flow.base_kind(), base_a=a.double().cpu().numpy(),
+                       base_b=b.double().cpu().numpy())

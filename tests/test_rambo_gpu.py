@@ -124,7 +124,9 @@ def test_forward_vs_oracle_seeded(cuda, masses, N):
     assert momenta_rel_err(mom, mom_ref).max() < RTOL
     fin = np.isfinite(w_ref)
     assert np.array_equal(np.isfinite(w), fin)
-    assert rel_err(w[fin], w_ref[fin]).max() < RTOL
+    rep = fin & (np.abs(w_ref) > 1e-35) & (np.abs(w_ref) < 1e35)  # representable as normal fp32
+    assert rep.mean() > 0.8
+    assert rel_err(w[rep], w_ref[rep]).max() < RTOL
     assert np.abs(logw - logw_ref).max() < 1e-5 * np.maximum(1, np.abs(logw_ref)).max()
     assert rel_err(x1, x1_ref).max() < RTOL and rel_err(x2, x2_ref).max() < RTOL
 
