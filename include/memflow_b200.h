@@ -235,6 +235,14 @@ int mf_flow_log_prob(const mf_flow_desc* desc, const void* d_blob, const void* d
 int mf_flow_sample(const mf_flow_desc* desc, const void* d_blob, const void* d_noise,
                    const void* d_ctx, int64_t n, void* d_x, int dtype, int gemm, void* stream);
 
+/*
+ * Per-event likelihood tail: out[e] = sum_p logprob[e,p] * mask[e,p] - logw[e]
+ * (transfer_flow_paper_AllPartons_btag.py:216; notebooks/TestFlows_ImportanceSampling.ipynb cell 52).
+ *   d_logprob [B,P]; d_mask [B,P] uint8 (NULL = all objects exist); d_logw [B] (NULL = none)
+ */
+int mf_event_reduce(const void* d_logprob, const uint8_t* d_mask, const void* d_logw, int64_t n_events,
+                    int32_t n_objects, void* d_out, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -145,3 +145,12 @@ def flow_sample(desc, blob, noise, ctx, x, gemm):
                                   ctypes.c_int(_dtype_code(noise.dtype)), ctypes.c_int(gemm),
                                   _stream(noise.device))
     check(rc, "mf_flow_sample")
+
+
+def event_reduce(logprob, mask, logw, out):
+    """out[e] = sum_p logprob[e,p]*mask[e,p] - logw[e]  (mf_event_reduce)."""
+    B, P = logprob.shape
+    with torch.cuda.device(logprob.device):
+        rc = lib().mf_event_reduce(_ptr(logprob), _ptr(mask), _ptr(logw), ctypes.c_int64(B), ctypes.c_int32(P),
+                                   _ptr(out), ctypes.c_int(_dtype_code(logprob.dtype)), _stream(logprob.device))
+    check(rc, "mf_event_reduce")

@@ -454,7 +454,7 @@ static int flow_run(const mf_flow_desc* desc, const FlowKernelArgs& a, int dtype
   FlowLayout L;
   rc = make_flow_layout(*desc, &L);
   if (rc != MF_OK) return rc;
-  MF_REQUIRE(desc->context == 0 || a.ctx != nullptr, "context pointer is null but context=%d", desc->context);
+  MF_REQUIRE(desc->context == 0 || a.ctx != nullptr || a.n == 0, "context pointer is null but context=%d", desc->context);
   MF_REQUIRE(desc->bound > 0.0, "bound must be positive");
   if (a.n == 0) return MF_OK;
   BaseParams bp;
@@ -466,8 +466,8 @@ static int flow_run(const mf_flow_desc* desc, const FlowKernelArgs& a, int dtype
 int mf_flow_log_prob(const mf_flow_desc* desc, const void* d_blob, const void* d_x, const void* d_ctx,
                      int64_t n, void* d_logprob, void* d_z, void* d_ladj, int8_t* d_bins,
                      uint8_t* d_inside, int dtype, int gemm, void* stream) {
-  MF_REQUIRE(desc && d_blob && d_x, "mf_flow_log_prob: null argument");
   MF_REQUIRE(n >= 0, "mf_flow_log_prob: negative count");
+  MF_REQUIRE(desc && d_blob && (d_x || n == 0), "mf_flow_log_prob: null argument");
   FlowKernelArgs a{};
   a.blob = d_blob; a.x = d_x; a.ctx = d_ctx; a.n = n;
   a.logprob = d_logprob; a.z = d_z; a.ladj = d_ladj; a.bins = d_bins; a.inside = d_inside;
@@ -478,8 +478,8 @@ int mf_flow_log_prob(const mf_flow_desc* desc, const void* d_blob, const void* d
 
 int mf_flow_sample(const mf_flow_desc* desc, const void* d_blob, const void* d_noise, const void* d_ctx,
                    int64_t n, void* d_x, int dtype, int gemm, void* stream) {
-  MF_REQUIRE(desc && d_blob && d_noise && d_x, "mf_flow_sample: null argument");
   MF_REQUIRE(n >= 0, "mf_flow_sample: negative count");
+  MF_REQUIRE(desc && d_blob && ((d_noise && d_x) || n == 0), "mf_flow_sample: null argument");
   MF_REQUIRE(desc->passes >= 1 && desc->passes <= desc->features, "passes=%d outside 1..features", desc->passes);
   FlowKernelArgs a{};
   a.blob = d_blob; a.x = d_noise; a.ctx = d_ctx; a.n = n;

@@ -695,8 +695,8 @@ extern "C" {
 int mf_rambo_forward(const mf_rambo_desc* desc, const void* d_r, int64_t n_events, void* d_momenta,
                      void* d_weight, void* d_logw, void* d_x1, void* d_x2, int32_t* d_flags,
                      int io_dtype, int compute, void* stream) {
-  MF_REQUIRE(desc && d_r, "mf_rambo_forward: null desc or uniforms");
   MF_REQUIRE(n_events >= 0, "mf_rambo_forward: negative event count");
+  MF_REQUIRE(desc && (d_r || n_events == 0), "mf_rambo_forward: null desc or uniforms");
   RamboAux aux;
   int rc = fill_aux(desc, nullptr, &aux);
   if (rc != MF_OK) return rc;
@@ -760,8 +760,8 @@ static int inverse_dispatch(const mf_rambo_desc* desc, const void* mom, const vo
 int mf_rambo_inverse(const mf_rambo_desc* desc, const void* d_momenta, const void* d_x1,
                      const void* d_x2, const int32_t* perm, int64_t n_events, void* d_r,
                      void* d_detjacinv, int32_t* d_flags, int io_dtype, int compute, void* stream) {
-  MF_REQUIRE(desc && d_momenta && d_x1 && d_x2 && d_r, "mf_rambo_inverse: null argument");
   MF_REQUIRE(n_events >= 0, "mf_rambo_inverse: negative event count");
+  MF_REQUIRE(desc && ((d_momenta && d_x1 && d_x2 && d_r) || n_events == 0), "mf_rambo_inverse: null argument");
   return inverse_dispatch(desc, d_momenta, d_x1, d_x2, nullptr, perm, n_events, d_r, d_detjacinv,
                           d_flags, nullptr, 0, io_dtype, compute, stream);
 }
@@ -783,7 +783,7 @@ int mf_rambo_inverse_f64(const mf_rambo_desc* desc, const double* d_momenta, con
 int mf_rambo_get_ps(const mf_rambo_desc* desc, const void* d_momenta, const void* d_boost,
                     const int32_t* perm, int64_t n_events, void* d_ps, uint8_t* d_mask, int io_dtype,
                     int compute, void* stream) {
-  MF_REQUIRE(desc && d_momenta && d_boost && d_ps, "mf_rambo_get_ps: null argument");
+  MF_REQUIRE(desc && ((d_momenta && d_boost && d_ps) || n_events == 0), "mf_rambo_get_ps: null argument");
   MF_REQUIRE(desc->n_final == 4, "mf_rambo_get_ps: the reference hard-codes n = 4 (got %d)",
              desc->n_final);
   MF_REQUIRE(n_events >= 0, "mf_rambo_get_ps: negative event count");

@@ -51,6 +51,10 @@ class DiagNormal(torch.distributions.Independent):
 
     KIND = BASE_DIAG_NORMAL
 
+    def expand(self, batch_shape, new=None):
+        new = self._get_checked_instance(DiagNormal, new)
+        return super().expand(batch_shape, new)
+
 
 class BoxUniform(torch.distributions.Independent):
     def __init__(self, lower=0.0, upper=1.0, ndims=1):
@@ -58,6 +62,10 @@ class BoxUniform(torch.distributions.Independent):
                                                      validate_args=False), ndims)
 
     KIND = BASE_BOX_UNIFORM
+
+    def expand(self, batch_shape, new=None):
+        new = self._get_checked_instance(BoxUniform, new)
+        return super().expand(batch_shape, new)
 
 
 class Unconditional(nn.Module):

