@@ -154,3 +154,13 @@ def event_reduce(logprob, mask, logw, out):
         rc = lib().mf_event_reduce(_ptr(logprob), _ptr(mask), _ptr(logw), ctypes.c_int64(B), ctypes.c_int32(P),
                                    _ptr(out), ctypes.c_int(_dtype_code(logprob.dtype)), _stream(logprob.device))
     check(rc, "mf_event_reduce")
+
+
+def tc_probe_gemm(a, w, mode):
+    """out[128,N] = a[128,K] @ w[N,K]^T on the tensor cores (test hook, mf_tc_probe_gemm)."""
+    out = torch.empty((128, w.shape[0]), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        rc = lib().mf_tc_probe_gemm(_ptr(a), _ptr(w), _ptr(out), ctypes.c_int32(a.shape[1]), ctypes.c_int32(w.shape[0]),
+                                    ctypes.c_int32(mode), _stream(a.device))
+    check(rc, "mf_tc_probe_gemm")
+    return out

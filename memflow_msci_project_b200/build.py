@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(OUT_DIR, "libmemflow_b200.so")
-SOURCES = ["abi.cu", "rambo.cu", "flow.cu", "reduce.cu"]
+SOURCES = ["abi.cu", "rambo.cu", "flow.cu", "reduce.cu", "tc_probe.cu", "flow_tc.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -176,28 +176,6 @@ __device__ __forceinline__ void gemm_pass(const T* A, int lda, int K, const T* _
   }
 }
 
-struct FlowKernelArgs {
-  const void* blob;
-  const void* x;      // mode 0: data x; mode 1: noise
-  const void* ctx;
-  long long n;
-  void* logprob;
-  void* z;            // mode 0: z; mode 1: sampled x
-  void* ladj;
-  int8_t* bins;
-  uint8_t* inside;
-  int mode;           // 0 = log_prob / transform, 1 = sample
-  int passes;
-  int base;
-  int univariate;
-  double bound, slope;
-};
-
-struct BaseParams {
-  double a[MF_MAX_FEATURES];
-  double b[MF_MAX_FEATURES];
-};
-
 template <typename T, int RM>
 __global__ void __launch_bounds__(kThreads, 1)
 flow_kernel(const __grid_constant__ FlowLayout L, const __grid_constant__ FlowKernelArgs args,
@@ -387,8 +365,9 @@ int launch_flow(const FlowLayout& L, const FlowKernelArgs& a, const BaseParams& 
 int check_flow_common(const mf_flow_desc* desc, int dtype, int gemm) {
   MF_REQUIRE(desc != nullptr, "null flow descriptor");
   MF_REQUIRE(dtype == MF_F32 || dtype == MF_F64, "unsupported dtype %d", dtype);
-  if (gemm != MF_GEMM_EXACT) {
-    set_error("gemm mode %d is not available in this build (only MF_GEMM_EXACT)", gemm);
+  MF_REQUIRE(gemm == MF_GEMM_EXACT || gemm == MF_GEMM_TC_3XF16 || gemm == MF_GEMM_TC_BF16, "unknown gemm mode %d", gemm);
+  if (gemm != MF_GEMM_EXACT && dtype != MF_F32) {
+    set_error("tensor-core gemm modes take fp32 tensors (fp64 flows use MF_GEMM_EXACT)");
     return MF_EUNSUPPORTED;
   }
   return MF_OK;
@@ -403,6 +382,10 @@ extern "C" {
 
 int64_t mf_flow_blob_bytes(const mf_flow_desc* desc, int dtype, int gemm) {
   if (check_flow_common(desc, dtype, gemm) != MF_OK) return -1;
+  if (gemm != MF_GEMM_EXACT) {
+    long long b = 0;
+    return flow_tc_blob_bytes(*desc, gemm, &b) == MF_OK ? (int64_t)b : -1;
+  }
   FlowLayout L;
   if (make_flow_layout(*desc, &L) != MF_OK) return -1;
   return (int64_t)L.t_stride * L.T * (dtype == MF_F32 ? 4 : 8);
@@ -414,6 +397,8 @@ int mf_flow_pack_weights(const mf_flow_desc* desc, const void* const* d_weights,
   int rc = check_flow_common(desc, dtype, gemm);
   if (rc != MF_OK) return rc;
   MF_REQUIRE(d_weights && d_biases && d_masks && d_blob, "mf_flow_pack_weights: null argument");
+  if (gemm != MF_GEMM_EXACT)
+    return flow_tc_pack(*desc, d_weights, d_biases, d_masks, gemm, d_blob, blob_bytes, static_cast<cudaStream_t>(stream));
   FlowLayout L;
   rc = make_flow_layout(*desc, &L);
   if (rc != MF_OK) return rc;
@@ -454,6 +439,14 @@ static int flow_run(const mf_flow_desc* desc, const FlowKernelArgs& a, int dtype
   FlowLayout L;
   rc = make_flow_layout(*desc, &L);
   if (rc != MF_OK) return rc;
+  if (gemm != MF_GEMM_EXACT) {
+    MF_REQUIRE(desc->context == 0 || a.ctx != nullptr || a.n == 0, "context pointer is null but context=%d", desc->context);
+    MF_REQUIRE(desc->bound > 0.0, "bound must be positive");
+    if (a.n == 0) return MF_OK;
+    BaseParams bpt;
+    for (int f = 0; f < MF_MAX_FEATURES; ++f) { bpt.a[f] = desc->base_a[f]; bpt.b[f] = desc->base_b[f]; }
+    return flow_tc_run(*desc, a, bpt, gemm, static_cast<cudaStream_t>(stream));
+  }
   MF_REQUIRE(desc->context == 0 || a.ctx != nullptr || a.n == 0, "context pointer is null but context=%d", desc->context);
   MF_REQUIRE(desc->bound > 0.0, "bound must be positive");
   if (a.n == 0) return MF_OK;

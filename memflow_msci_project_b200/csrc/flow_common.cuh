@@ -78,6 +78,35 @@ inline int make_flow_layout(const mf_flow_desc& d, FlowLayout* L) {
   return MF_OK;
 }
 
+struct FlowKernelArgs {
+  const void* blob;
+  const void* x;      // mode 0: data x; mode 1: noise
+  const void* ctx;
+  long long n;
+  void* logprob;
+  void* z;            // mode 0: z; mode 1: sampled x
+  void* ladj;
+  int8_t* bins;
+  uint8_t* inside;
+  int mode;           // 0 = log_prob / transform, 1 = sample
+  int passes;
+  int base;
+  int univariate;
+  double bound, slope;
+};
+
+struct BaseParams {
+  double a[MF_MAX_FEATURES];
+  double b[MF_MAX_FEATURES];
+};
+
+
+// tcgen05 path (flow_tc.cu)
+int flow_tc_blob_bytes(const mf_flow_desc& d, int gemm, long long* bytes);
+int flow_tc_pack(const mf_flow_desc& d, const void* const* w, const void* const* b, const uint8_t* const* m,
+                 int gemm, void* blob, long long blob_bytes, cudaStream_t st);
+int flow_tc_run(const mf_flow_desc& d, const FlowKernelArgs& a, const BaseParams& bp, int gemm, cudaStream_t st);
+
 #ifdef __CUDACC__
 template <typename T> struct FM;
 template <> struct FM<float> {

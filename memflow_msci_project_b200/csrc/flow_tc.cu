@@ -1,0 +1,619 @@
+// flow_tc.cu -- fused conditional RQ-spline MAF log_prob with the conditioner GEMMs on tcgen05.
+//
+// One persistent CTA per SM works on PAIRS of 128-object tiles.  Warp roles (320 threads):
+//   warp 0        weight loader: streams the packed, pre-swizzled weight K-blocks from L2 into a 3-stage
+//                 shared-memory ring with 1-D bulk async copies (TMA engine) completing on mbarriers
+//   warp 1        MMA issuer: one elected thread issues tcgen05.mma (M=128, N<=128, K=16, fp32 accumulate in
+//                 TMEM) for tile 0 and tile 1 back to back on the same weight stage, then tcgen05.commit
+//   warps 2-5     epilogue group of tile slot 0 (thread = object = TMEM lane)
+//   warps 6-9     epilogue group of tile slot 1
+// The two tile slots ping-pong: while the tensor core works on one tile's layer, the other tile's epilogue
+// (TMEM -> registers -> bias + ReLU -> operand conversion -> swizzled shared memory) runs on the CUDA cores.
+// Activations never leave the SM; the spline parameters of the last layer are consumed straight out of TMEM
+// by the thread that owns the object, so they never touch shared memory or HBM either.
+//
+// Numerics.  MF_GEMM_TC_3XF16: every fp32 operand value v is split into fp16 hi = rn(v), lo = rn(v - hi) and
+// each product is formed as hi*hi + hi*lo + lo*hi with fp32 accumulation: 22 significant bits, i.e. fp32-class
+// accuracy (measured 4e-7 of sum|terms|, tests/test_tc_probe_gpu.py).  MF_GEMM_TC_BF16: single bf16 MMA.
+//
+// Supported shapes (others are served by the CUDA-core kernel in flow.cu): D + C <= 128, every hidden width
+// <= 128, 3 * roundup(K, 8) <= 128.
+#include <algorithm>
+
+#include "flow_common.cuh"
+#include "tc_common.cuh"
+
+namespace mf {
+namespace {
+
+constexpr int kTcThreads = 320;
+constexpr int kStages = 3;
+constexpr int kMaxJobs = 40;
+constexpr uint32_t kABufBytes = 128 * 128 * 2;  // one [128 x 128] 16-bit operand (two K-blocks)
+constexpr uint32_t kWPartBytes = 128 * 128;     // one [<=128 rows x 64] 16-bit weight K-block
+
+struct TcJob {
+  int N;        // MMA N (multiple of 16, <= 128)
+  int ksteps;   // K / 16
+  int nkb;      // K-blocks of 64
+  int needs_a;  // a new A operand is produced right before this job
+  int last;     // 1: spline chunk of the last layer
+  int feat0, nfeat;
+  int layer;    // source layer in zuko layout
+  int row0;     // last layer: first zuko output row of the chunk is feat0 * (3K-1)
+  int in_dim, out_dim;
+  long long w_off;  // bytes from the transform base to K-block 0 ([hi block][lo block] per K-block)
+  int b_off;        // floats from the transform bias base
+};
+
+struct TcLayout {
+  int D, C, K, T, L, nsplit;
+  int Kp;      // roundup(K, 8): widths at [0,Kp), heights at [Kp,2Kp), derivatives at [2Kp, 3Kp) of a feature
+  int PFt;     // 3 * Kp
+  int njobs;
+  int in0_ksteps;
+  long long t_stride;    // bytes per transform (weights)
+  long long bias_off;    // byte offset of the fp32 bias region in the blob
+  int bias_stride;       // floats per transform
+  TcJob job[kMaxJobs];
+};
+
+int make_tc_layout(const mf_flow_desc& d, int gemm, TcLayout* L) {
+  MF_REQUIRE(gemm == MF_GEMM_TC_3XF16 || gemm == MF_GEMM_TC_BF16, "not a tensor-core gemm mode: %d", gemm);
+  MF_REQUIRE(d.features >= 1 && d.features <= MF_MAX_FEATURES && d.context >= 0, "bad features/context");
+  MF_REQUIRE(d.transforms >= 1 && d.transforms <= MF_MAX_TRANSFORMS, "bad transforms");
+  MF_REQUIRE(d.n_hidden >= 1 && d.n_hidden <= MF_MAX_HIDDEN_LAYERS, "bad n_hidden");
+  L->D = d.features; L->C = d.context; L->K = d.bins; L->T = d.transforms; L->L = d.n_hidden;
+  L->nsplit = (gemm == MF_GEMM_TC_3XF16) ? 3 : 1;
+  L->Kp = round_up(d.bins, 8);
+  L->PFt = 3 * L->Kp;
+  if (d.features + d.context > 128 || L->PFt > 128 || d.bins < 2) {
+    set_error("tensor-core flow path needs D+C <= 128 and 3*roundup(bins,8) <= 128 (got D+C=%d, bins=%d)",
+              d.features + d.context, d.bins);
+    return MF_EUNSUPPORTED;
+  }
+  for (int l = 0; l < d.n_hidden; ++l)
+    if (d.hidden[l] > 128 || d.hidden[l] < 1) {
+      set_error("tensor-core flow path needs hidden widths <= 128 (layer %d has %d)", l, d.hidden[l]);
+      return MF_EUNSUPPORTED;
+    }
+  const int parts = (L->nsplit == 3) ? 2 : 1;
+  int nj = 0;
+  long long woff = 0;
+  int boff = 0;
+  for (int l = 0; l < d.n_hidden; ++l) {
+    TcJob& j = L->job[nj++];
+    j.in_dim = (l == 0) ? d.features + d.context : d.hidden[l - 1];
+    j.out_dim = d.hidden[l];
+    j.N = round_up(j.out_dim, 16);
+    j.ksteps = round_up(j.in_dim, 16) / 16;
+    j.nkb = (j.ksteps + 3) / 4;
+    j.needs_a = 1; j.last = 0; j.feat0 = 0; j.nfeat = 0; j.layer = l; j.row0 = 0;
+    j.w_off = woff; woff += (long long)j.nkb * parts * j.N * 128;
+    j.b_off = boff; boff += j.N;
+  }
+  L->in0_ksteps = L->job[0].ksteps;
+  const int fpc = std::max(1, 128 / L->PFt);
+  for (int f0 = 0; f0 < d.features; f0 += fpc) {
+    MF_REQUIRE(nj < kMaxJobs, "too many last-layer chunks for the tensor-core path");
+    TcJob& j = L->job[nj++];
+    j.in_dim = d.hidden[d.n_hidden - 1];
+    j.nfeat = std::min(fpc, d.features - f0);
+    j.feat0 = f0;
+    j.out_dim = j.nfeat * L->PFt;
+    j.N = round_up(j.out_dim, 16);
+    j.ksteps = round_up(j.in_dim, 16) / 16;
+    j.nkb = (j.ksteps + 3) / 4;
+    j.needs_a = (f0 == 0) ? 1 : 0; j.last = 1; j.layer = d.n_hidden; j.row0 = f0 * (3 * d.bins - 1);
+    j.w_off = woff; woff += (long long)j.nkb * parts * j.N * 128;
+    j.b_off = boff; boff += j.N;
+  }
+  L->njobs = nj;
+  L->t_stride = woff;
+  L->bias_off = woff * d.transforms;
+  L->bias_stride = boff;
+  return MF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pack: zuko-layout parameters -> swizzled fp16 hi/lo (or bf16) K-blocks + fp32 biases
+template <typename T>
+struct TcPackArgs {
+  const T* w[kMaxLayers];
+  const T* b[kMaxLayers];
+  const uint8_t* m[kMaxLayers];
+};
+
+template <typename T>
+__global__ void flow_tc_pack_kernel(TcLayout L, TcPackArgs<T> a, unsigned char* blob_t, float* bias_t) {
+  const int parts = (L.nsplit == 3) ? 2 : 1;
+  const int P = 3 * L.K - 1;
+  for (int ji = 0; ji < L.njobs; ++ji) {
+    const TcJob j = L.job[ji];
+    const int kdim = j.nkb * 64;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < j.N * kdim; i += gridDim.x * blockDim.x) {
+      const int n = i / kdim, k = i % kdim;
+      // source row in zuko layout
+      int src_row = -1;
+      if (!j.last) {
+        if (n < j.out_dim) src_row = n;
+      } else {
+        const int fl = n / L.PFt, c = n % L.PFt;
+        if (fl < j.nfeat) {
+          const int seg = c / L.Kp, jj = c % L.Kp;  // 0 widths, 1 heights, 2 derivatives
+          const int len = (seg == 2) ? L.K - 1 : L.K;
+          if (jj < len) src_row = (j.feat0 + fl) * P + seg * L.K + jj;
+        }
+      }
+      float v = 0.f;
+      if (src_row >= 0 && k < j.in_dim) {
+        const long long s = (long long)src_row * j.in_dim + k;
+        v = a.m[j.layer][s] ? (float)a.w[j.layer][s] : 0.f;
+      }
+      const int kb = k >> 6;
+      unsigned char* blk = blob_t + j.w_off + (long long)kb * parts * j.N * 128;
+      const uint32_t off = tc::sw128_offset(n, k & 63, j.N);
+      if (L.nsplit == 3) {
+        const __half h = __float2half_rn(v);
+        *reinterpret_cast<__half*>(blk + off) = h;
+        *reinterpret_cast<__half*>(blk + (size_t)j.N * 128 + off) = __float2half_rn(v - __half2float(h));
+      } else {
+        *reinterpret_cast<__nv_bfloat16*>(blk + off) = __float2bfloat16_rn(v);
+      }
+      if (k == 0) {
+        float bv = 0.f;
+        if (src_row >= 0) bv = (float)a.b[j.layer][src_row];
+        bias_t[j.b_off + n] = bv;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  tc::tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+
+__device__ __forceinline__ float softclipf(float v, float inv) { return __fdividef(v, 1.f + fabsf(v * inv)); }
+
+// Spline of one feature with its 3K-1 unconstrained parameters in TMEM (this thread's lane):
+// columns [0,K) widths, [Kp,Kp+K) heights, [2Kp, 2Kp+K-1) derivatives.  Forward transform + log-det.
+// sb: the parameters' biases in shared memory (same column layout).
+__device__ __forceinline__ void ld8b(uint32_t taddr, const float* sb, float* v) {
+  tmem_ld8(taddr, v);
+  const float4 b0 = *reinterpret_cast<const float4*>(sb), b1 = *reinterpret_cast<const float4*>(sb + 4);
+  v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+  v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+}
+
+__device__ __forceinline__ void rqs_forward_tmem(uint32_t taddr, const float* sb, const SplineCfg<float>& cfg, int Kp,
+                                                 float v, float& out, float& ladj, int& bin, bool& inside) {
+  const int K = cfg.K;
+  const int nch = Kp >> 3;
+  float ladj0 = 0.f;
+  if (cfg.univariate == MF_UNIV_CIRCULAR_RQS) v = circular_wrap(v, cfg.bound);
+  if (cfg.univariate == MF_UNIV_PS_RQS) { v = (v + 1.f) * 0.5f; ladj0 = -0.6931471805599453f; }
+  const bool clipped = cfg.inv_ls2 != 0.f;  // soft-clipped logits are bounded by |ln slope| / 2: no max pass
+  float mw = 0.f, mh = 0.f;
+  if (!clipped) {
+    mw = -INFINITY; mh = -INFINITY;
+    for (int c = 0; c < nch; ++c) {
+      float a[8], b[8];
+      ld8b(taddr + c * 8, sb + c * 8, a);
+      ld8b(taddr + Kp + c * 8, sb + Kp + c * 8, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (c * 8 + j < K) {
+          mw = fmaxf(mw, softclipf(a[j], cfg.inv_ls2));
+          mh = fmaxf(mh, softclipf(b[j], cfg.inv_ls2));
+        }
+    }
+  }
+  float sw = 0.f, sh = 0.f;
+  for (int c = 0; c < nch; ++c) {
+    float a[8], b[8];
+    ld8b(taddr + c * 8, sb + c * 8, a);
+    ld8b(taddr + Kp + c * 8, sb + Kp + c * 8, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (c * 8 + j < K) {
+        sw += __expf(softclipf(a[j], cfg.inv_ls2) - mw);
+        sh += __expf(softclipf(b[j], cfg.inv_ls2) - mh);
+      }
+  }
+  // scan the horizontal knots: bound * (2 cumsum(softmax(w)) - 1); k = #(knots < v) - 1
+  int k = -1;
+  float x0 = 0.f, x1 = 1.f, cum = 0.f, prev = -cfg.bound;
+  for (int c = 0; c < nch; ++c) {
+    float a[8];
+    ld8b(taddr + c * 8, sb + c * 8, a);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (c * 8 + j < K) {
+        cum += __expf(softclipf(a[j], cfg.inv_ls2) - mw) / sw;
+        const float knot = cfg.bound * (2.f * cum - 1.f);
+        if (prev < v) { k = c * 8 + j; x0 = prev; x1 = knot; }
+        prev = knot;
+      }
+  }
+  if (prev < v) k = K;
+  inside = (k >= 0) && (k < K);
+  k = k < 0 ? k + K : (k >= K ? k - K : k);
+  bin = k;
+  // vertical knots of bin k
+  float part = 0.f, ek = 0.f;
+  for (int c = 0; c < nch; ++c) {
+    float b[8];
+    ld8b(taddr + Kp + c * 8, sb + Kp + c * 8, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int jj = c * 8 + j;
+      if (jj <= k) {
+        const float e = __expf(softclipf(b[j], cfg.inv_ls2) - mh) / sh;
+        if (jj < k) part += e; else ek = e;
+      }
+    }
+  }
+  const float y0 = cfg.bound * (2.f * part - 1.f), y1 = cfg.bound * (2.f * (part + ek) - 1.f);
+  // derivatives at the two knots (boundary derivatives are 1)
+  float d0 = 1.f, d1 = 1.f;
+  {
+    // tcgen05.ld is a warp-collective (.sync.aligned) with a warp-uniform address: all derivative chunks
+    // are loaded by every lane and each lane picks the two columns of its own bin in registers
+    const int i0 = k - 1, i1 = k;  // indices into the K-1 derivative logits
+    float t0 = 0.f, t1 = 0.f;
+    for (int c = 0; c < nch; ++c) {
+      float dv[8];
+      ld8b(taddr + 2 * Kp + c * 8, sb + 2 * Kp + c * 8, dv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        t0 = (c * 8 + j == i0) ? dv[j] : t0;
+        t1 = (c * 8 + j == i1) ? dv[j] : t1;
+      }
+    }
+    if (i0 >= 0) d0 = __expf(softclipf(t0, cfg.inv_ls1));
+    if (i1 < K - 1) d1 = __expf(softclipf(t1, cfg.inv_ls1));
+  }
+  if (!inside) { x0 = 0.f; x1 = 1.f; }
+  const float s = (y1 - y0) / (x1 - x0);
+  const float msk = inside ? 1.f : 0.f;
+  const float z = msk * (v - x0) / (x1 - x0);
+  const float omz = 1.f - z;
+  const float den = s + (d0 + d1 - 2.f * s) * z * omz;
+  const float y = y0 + (y1 - y0) * (s * z * z + d0 * z * omz) / den;
+  const float jac = s * s * (2.f * s * z * omz + d0 * omz * omz + d1 * z * z) / (den * den);
+  out = inside ? y : v;
+  ladj = (inside ? __logf(jac) : 0.f) + ladj0;
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int NSPLIT>
+__global__ void __launch_bounds__(kTcThreads, 1)
+flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowKernelArgs args,
+               const __grid_constant__ BaseParams bp) {
+  constexpr int kParts = (NSPLIT == 3) ? 2 : 1;           // operand planes (hi, lo)
+  constexpr uint32_t kStageBytes = kParts * kWPartBytes;  // one weight K-block, all planes
+  extern __shared__ __align__(1024) unsigned char smem[];
+  // [tile][part] activation operands, then the weight ring
+  unsigned char* a_buf = smem;
+  unsigned char* w_ring = smem + 2 * kParts * kABufBytes;
+  __shared__ __align__(8) uint64_t w_full[kStages], w_empty[kStages], a_ready[2], acc_full[2][2], acc_free[2][2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float sbias[2][2][128];  // [tile slot][job parity][column]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long n = args.n;
+  const long long n_tiles = (n + 127) / 128;
+  const long long n_pairs = (n_tiles + 1) / 2;
+  const unsigned char* blob = static_cast<const unsigned char*>(args.blob);
+  const float* bias_all = reinterpret_cast<const float*>(blob + L.bias_off);
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&a_ready[t], 128);
+      for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[t][b], 1); mbar_init(&acc_free[t][b], 128); }
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tc::tmem_alloc(&tmem_base_s, 512);
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 0) {
+    // ===================== weight loader =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long long p = blockIdx.x; p < n_pairs; p += gridDim.x) {
+        for (int tr = 0; tr < L.T; ++tr) {
+          const unsigned char* tb = blob + (long long)tr * L.t_stride;
+          for (int ji = 0; ji < L.njobs; ++ji) {
+            const TcJob& j = L.job[ji];
+            const uint32_t part_bytes = (uint32_t)j.N * 128u;
+            for (int kb = 0; kb < j.nkb; ++kb, ++it) {
+              const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+              mbar_wait(&w_empty[s], ph ^ 1);
+              mbar_expect_tx(&w_full[s], kParts * part_bytes);
+              const unsigned char* src = tb + j.w_off + (long long)kb * kParts * part_bytes;
+              unsigned char* dst = w_ring + s * kStageBytes;
+#pragma unroll
+              for (int q = 0; q < kParts; ++q) bulk_g2s(dst + q * kWPartBytes, src + (size_t)q * part_bytes, part_bytes, &w_full[s]);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t it = 0;             // weight stages consumed so far
+      uint32_t jobctr[2] = {0, 0};  // accumulator uses per tile slot
+      uint32_t aph[2] = {0, 0};     // a_ready phases
+      for (long long p = blockIdx.x; p < n_pairs; p += gridDim.x) {
+        const int ntile = (2 * p + 1 < n_tiles) ? 2 : 1;
+        for (int tr = 0; tr < L.T; ++tr) {
+          for (int ji = 0; ji < L.njobs; ++ji) {
+            const TcJob& j = L.job[ji];
+            const uint32_t idesc = tc::make_idesc_f16(NSPLIT == 3 ? 0 : 1, 128, j.N);
+            for (int t = 0; t < ntile; ++t) {
+              if (j.needs_a) { mbar_wait(&a_ready[t], aph[t]); aph[t] ^= 1; }
+              const uint32_t u = jobctr[t] >> 1, buf = jobctr[t] & 1;
+              if (u >= 1) mbar_wait(&acc_free[t][buf], (u - 1) & 1);
+              tc::fence_after_thread_sync();
+              const uint32_t d_tmem = tmem + (uint32_t)(t * 256 + buf * 128);
+              const uint32_t a_base = smem_u32(a_buf + (size_t)t * kParts * kABufBytes);
+              for (int kb = 0; kb < j.nkb; ++kb) {
+                const uint32_t s = (it + kb) % kStages, ph = ((it + kb) / kStages) & 1;
+                mbar_wait(&w_full[s], ph);
+                tc::fence_after_thread_sync();
+                const uint32_t w_base = smem_u32(w_ring + s * kStageBytes);
+                const int ks_n = min(4, j.ksteps - kb * 4);
+                for (int ks = 0; ks < ks_n; ++ks) {
+                  const uint32_t acc = (kb | ks) ? 1u : 0u;
+                  const uint64_t dah = tc::make_smem_desc(a_base + kb * (128u * 128u) + ks * 32u);
+                  const uint64_t dbh = tc::make_smem_desc(w_base + ks * 32u);
+                  tc::mma_f16_ss(d_tmem, dah, dbh, idesc, acc);
+                  if (NSPLIT == 3) {
+                    const uint64_t dal = tc::make_smem_desc(a_base + kABufBytes + kb * (128u * 128u) + ks * 32u);
+                    const uint64_t dbl = tc::make_smem_desc(w_base + kWPartBytes + ks * 32u);
+                    tc::mma_f16_ss(d_tmem, dah, dbl, idesc, 1u);
+                    tc::mma_f16_ss(d_tmem, dal, dbh, idesc, 1u);
+                  }
+                }
+                if (t == ntile - 1) tc::mma_commit(&w_empty[s]);  // stage free once these MMAs retire
+              }
+              tc::mma_commit(&acc_full[t][buf]);
+              jobctr[t]++;
+            }
+            it += j.nkb;
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue groups =====================
+    const int t = (warp - 2) >> 2;            // tile slot
+    const int q = warp & 3;                   // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;            // object inside the tile
+    const int gt = ((warp - 2) & 3) * 32 + lane;  // thread index inside the group (for cooperative loops)
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    unsigned char* a_hi = a_buf + (size_t)t * kParts * kABufBytes;
+    unsigned char* a_lo = a_hi + kABufBytes;
+    const float* gx = static_cast<const float*>(args.x);
+    const float* gc = static_cast<const float*>(args.ctx);
+    float* gz = static_cast<float*>(args.z);
+    const int D = L.D, C = L.C;
+    SplineCfg<float> cfg;
+    cfg.K = L.K; cfg.univariate = args.univariate; cfg.bound = (float)args.bound;
+    cfg.inv_ls2 = args.slope > 0.0 ? (float)(2.0 / log(args.slope)) : 0.f;
+    cfg.inv_ls1 = args.slope > 0.0 ? (float)(1.0 / log(args.slope)) : 0.f;
+    uint32_t jobctr = 0;
+
+    auto put2 = [&](int r, int k, float v0, float v1) {  // two consecutive columns k, k+1 (k even)
+      const uint32_t off = tc::sw128_offset(r, k, 128);
+      if (NSPLIT == 3) {
+        uint32_t hi, lo;
+        tc::split_f16(v0, v1, hi, lo);
+        *reinterpret_cast<uint32_t*>(a_hi + off) = hi;
+        *reinterpret_cast<uint32_t*>(a_lo + off) = lo;
+      } else {
+        *reinterpret_cast<uint32_t*>(a_hi + off) = tc::pack_bf16(v0, v1);
+      }
+    };
+    auto put1 = [&](int r, int k, float v) {
+      const uint32_t off = tc::sw128_offset(r, k, 128);
+      if (NSPLIT == 3) {
+        const __half h = __float2half_rn(v);
+        *reinterpret_cast<__half*>(a_hi + off) = h;
+        *reinterpret_cast<__half*>(a_lo + off) = __float2half_rn(v - __half2float(h));
+      } else {
+        *reinterpret_cast<__nv_bfloat16*>(a_hi + off) = __float2bfloat16_rn(v);
+      }
+    };
+
+    for (long long p = blockIdx.x; p < n_pairs; p += gridDim.x) {
+      const long long tile = 2 * p + t;
+      if (tile >= n_tiles) break;  // odd tile count: slot 1 idles in the last pair (the MMA warp skips it too)
+      const long long tile0 = tile * 128;
+      const int rows = (int)min((long long)128, n - tile0);
+      const bool valid = row < rows;
+      const long long g = tile0 + row;
+      // working copy of x lives in the z buffer (each thread touches only its own row)
+      if (valid)
+        for (int f = 0; f < D; ++f) gz[g * D + f] = gx[g * D + f];
+      float ladj = 0.f;
+      for (int tr = 0; tr < L.T; ++tr) {
+        const float* bias_t = bias_all + (size_t)tr * L.bias_stride;
+        // ---- stage (x | ctx | 0) as the layer-0 operand
+        {
+          const int kfill = L.in0_ksteps * 16;
+          for (int f = 0; f < D; ++f) put1(row, f, valid ? gz[g * D + f] : 0.f);
+          for (int k = D + C; k < kfill; ++k) put1(row, k, 0.f);
+          // context: coalesced over the flat [rows x C] range of this tile
+          int r = 0, c = gt;
+          while (C > 0 && c >= C) { c -= C; ++r; }
+          const int dr = C > 0 ? 128 / C : 0, dc = C > 0 ? 128 % C : 0;
+          for (int idx = gt; idx < 128 * C; idx += 128) {
+            const float v = (r < rows) ? gc[tile0 * C + idx] : 0.f;
+            put1(r, D + c, v);
+            r += dr; c += dc;
+            if (c >= C) { c -= C; ++r; }
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(&a_ready[t]);
+        }
+        for (int ji = 0; ji < L.njobs; ++ji) {
+          const TcJob& j = L.job[ji];
+          const uint32_t u = jobctr >> 1, buf = jobctr & 1;
+          ++jobctr;
+          // this job's biases -> shared memory (double-buffered by job parity), overlapping the MMA
+          float* sb = sbias[t][buf];
+          if (gt < j.N) sb[gt] = __ldg(bias_t + j.b_off + gt);
+          group_bar(1 + t);
+          mbar_wait(&acc_full[t][buf], u & 1);
+          tc::fence_after_thread_sync();
+          const uint32_t taddr = tmem + lane_off + (uint32_t)(t * 256 + buf * 128);
+          if (!j.last) {
+            // hidden layer: TMEM -> +bias -> ReLU -> operand planes of the next layer (in place)
+            for (int c0 = 0; c0 < j.N; c0 += 16) {
+              float v[16];
+              tc::tmem_ld16(taddr + c0, v);
+              tc::tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(sb + c0 + i);
+                v[i] = fmaxf(v[i] + b4.x, 0.f); v[i + 1] = fmaxf(v[i + 1] + b4.y, 0.f);
+                v[i + 2] = fmaxf(v[i + 2] + b4.z, 0.f); v[i + 3] = fmaxf(v[i + 3] + b4.w, 0.f);
+              }
+#pragma unroll
+              for (int h8 = 0; h8 < 2; ++h8) {  // two 16-byte chunks of 8 columns
+                const uint32_t off = tc::sw128_offset(row, c0 + h8 * 8, 128);
+                if (NSPLIT == 3) {
+                  uint32_t hi[4], lo[4];
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) tc::split_f16(v[h8 * 8 + 2 * i], v[h8 * 8 + 2 * i + 1], hi[i], lo[i]);
+                  *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                  *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                } else {
+                  uint32_t pk[4];
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) pk[i] = tc::pack_bf16(v[h8 * 8 + 2 * i], v[h8 * 8 + 2 * i + 1]);
+                  *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
+              }
+            }
+            tc::fence_before_thread_sync();
+            mbar_arrive(&acc_free[t][buf]);
+            fence_proxy_async_smem();
+            mbar_arrive(&a_ready[t]);
+          } else {
+            // last-layer chunk: splines of the chunk's features straight out of TMEM
+            for (int fl = 0; fl < j.nfeat; ++fl) {
+              const int f = j.feat0 + fl;
+              const float xv = valid ? gz[g * D + f] : 0.f;
+              float out, la;
+              int bin;
+              bool ins;
+              rqs_forward_tmem(taddr + fl * L.PFt, sb + fl * L.PFt, cfg, L.Kp, xv, out, la, bin, ins);
+              if (valid) {
+                gz[g * D + f] = out;
+                ladj += la;
+                if (args.bins) args.bins[((size_t)tr * n + g) * D + f] = (int8_t)bin;
+                if (args.inside) args.inside[((size_t)tr * n + g) * D + f] = ins ? 1 : 0;
+              }
+            }
+            tc::fence_before_thread_sync();
+            mbar_arrive(&acc_free[t][buf]);
+          }
+        }
+      }
+      if (valid) {
+        if (args.ladj) static_cast<float*>(args.ladj)[g] = ladj;
+        if (args.logprob) {
+          float lp = 0.f;
+          for (int f = 0; f < D; ++f) lp += base_log_prob_1<float>(args.base, gz[g * D + f], (float)bp.a[f], (float)bp.b[f]);
+          static_cast<float*>(args.logprob)[g] = lp + ladj;
+        }
+      }
+    }
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+int flow_tc_blob_bytes(const mf_flow_desc& d, int gemm, long long* bytes) {
+  TcLayout L;
+  int rc = make_tc_layout(d, gemm, &L);
+  if (rc != MF_OK) return rc;
+  *bytes = L.bias_off + (long long)L.bias_stride * L.T * 4;
+  return MF_OK;
+}
+
+int flow_tc_pack(const mf_flow_desc& d, const void* const* w, const void* const* b, const uint8_t* const* m,
+                 int gemm, void* blob, long long blob_bytes, cudaStream_t st) {
+  // parameters are fp32 on this path
+  TcLayout L;
+  int rc = make_tc_layout(d, gemm, &L);
+  if (rc != MF_OK) return rc;
+  const long long need = L.bias_off + (long long)L.bias_stride * L.T * 4;
+  MF_REQUIRE(blob_bytes >= need, "blob too small: %lld < %lld bytes", blob_bytes, need);
+  const int nl = d.n_hidden + 1;
+  for (int t = 0; t < L.T; ++t) {
+    TcPackArgs<float> a;
+    for (int l = 0; l < nl; ++l) {
+      a.w[l] = (const float*)w[t * nl + l];
+      a.b[l] = (const float*)b[t * nl + l];
+      a.m[l] = m[t * nl + l];
+      MF_REQUIRE(a.w[l] && a.b[l] && a.m[l], "null parameter pointer (transform %d layer %d)", t, l);
+    }
+    flow_tc_pack_kernel<float><<<148, 256, 0, st>>>(L, a, (unsigned char*)blob + (long long)t * L.t_stride,
+                                                   reinterpret_cast<float*>((unsigned char*)blob + L.bias_off) +
+                                                       (size_t)t * L.bias_stride);
+    rc = post_launch("flow_tc_pack_kernel");
+    if (rc != MF_OK) return rc;
+  }
+  return MF_OK;
+}
+
+int flow_tc_run(const mf_flow_desc& d, const FlowKernelArgs& a, const BaseParams& bp, int gemm, cudaStream_t st) {
+  TcLayout L;
+  int rc = make_tc_layout(d, gemm, &L);
+  if (rc != MF_OK) return rc;
+  MF_REQUIRE(a.mode == 0, "tensor-core path implements log_prob / transform only (sampling uses MF_GEMM_EXACT)");
+  MF_REQUIRE(a.z != nullptr, "tensor-core flow path needs the z output buffer (it is the working copy of x)");
+  const int parts = (L.nsplit == 3) ? 2 : 1;
+  const size_t smem = (size_t)2 * parts * kABufBytes + (size_t)kStages * parts * kWPartBytes;
+  const long long n_pairs = ((a.n + 127) / 128 + 1) / 2;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const unsigned grid = (unsigned)std::min<long long>(n_pairs, sms);
+  if (L.nsplit == 3) {
+    MF_CUDA_CHECK(cudaFuncSetAttribute(flow_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    flow_tc_kernel<3><<<grid, kTcThreads, smem, st>>>(L, a, bp);
+  } else {
+    MF_CUDA_CHECK(cudaFuncSetAttribute(flow_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    flow_tc_kernel<1><<<grid, kTcThreads, smem, st>>>(L, a, bp);
+  }
+  return post_launch("flow_tc_kernel");
+}
+
+}  // namespace mf

@@ -1,0 +1,104 @@
+// tc_probe.cu -- single-CTA tcgen05 GEMM used by the tests to validate the tensor-core building blocks
+// (swizzled operand layout, shared-memory / instruction descriptors, TMEM allocation, MMA issue, commit,
+// TMEM read-back) in isolation:  out[128, N] = A[128, K] * W[N, K]^T  with fp32 inputs.
+//   mode 0: fp16 hi/lo split of both operands, 3 MMAs per k-step (hi*hi + hi*lo + lo*hi)
+//   mode 1: bf16 single MMA        mode 2: fp16 single MMA
+#include "tc_common.cuh"
+
+namespace mf {
+namespace {
+
+__global__ void __launch_bounds__(128, 1)
+tc_probe_kernel(const float* __restrict__ A, const float* __restrict__ W, float* __restrict__ out, int K, int N,
+                int mode) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Kp = (K + 63) / 64 * 64;                  // K-blocks are 64 wide
+  const uint32_t a_bytes = 128u * (uint32_t)Kp * 2u;  // one [128 x Kp] 16-bit operand
+  const uint32_t b_bytes = (uint32_t)N * (uint32_t)Kp * 2u;
+  unsigned char* a_hi = smem;
+  unsigned char* a_lo = a_hi + a_bytes;
+  unsigned char* b_hi = a_lo + a_bytes;
+  unsigned char* b_lo = b_hi + b_bytes;
+
+  // zero-fill, then convert + scatter into the swizzled layout
+  for (uint32_t i = tid; i < (2 * a_bytes + 2 * b_bytes) / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  auto put = [&](unsigned char* hi, unsigned char* lo, int R, int r, int k, float v) {
+    const uint32_t off = tc::sw128_offset(r, k, R);
+    if (mode == 1) {
+      *reinterpret_cast<__nv_bfloat16*>(hi + off) = __float2bfloat16_rn(v);
+    } else {
+      const __half h = __float2half_rn(v);
+      *reinterpret_cast<__half*>(hi + off) = h;
+      *reinterpret_cast<__half*>(lo + off) = __float2half_rn(v - __half2float(h));
+    }
+  };
+  for (int i = tid; i < 128 * K; i += 128) put(a_hi, a_lo, 128, i / K, i % K, A[i]);
+  for (int i = tid; i < N * K; i += 128) put(b_hi, b_lo, N, i / K, i % K, W[i]);
+
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 256);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  const uint32_t tmem = tmem_base_s;
+
+  if (tid == 0) {
+    const uint32_t idesc = tc::make_idesc_f16(mode == 1 ? 1 : 0, 128, N);
+    const int ksteps = (K + 15) / 16;
+    uint32_t acc = 0;
+    for (int ks = 0; ks < ksteps; ++ks) {
+      const uint32_t kb = ks >> 2, kin = (ks & 3) * 32;
+      const uint64_t dah = tc::make_smem_desc(smem_u32(a_hi) + kb * 128u * 128u + kin);
+      const uint64_t dal = tc::make_smem_desc(smem_u32(a_lo) + kb * 128u * 128u + kin);
+      const uint64_t dbh = tc::make_smem_desc(smem_u32(b_hi) + kb * (uint32_t)N * 128u + kin);
+      const uint64_t dbl = tc::make_smem_desc(smem_u32(b_lo) + kb * (uint32_t)N * 128u + kin);
+      tc::mma_f16_ss(tmem, dah, dbh, idesc, acc);
+      acc = 1;
+      if (mode == 0) {
+        tc::mma_f16_ss(tmem, dah, dbl, idesc, 1);
+        tc::mma_f16_ss(tmem, dal, dbh, idesc, 1);
+      }
+    }
+    tc::mma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc::fence_after_thread_sync();
+  // read back: thread = row (TMEM lane)
+  const int row = warp * 32 + lane;
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    float v[16];
+    tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+    tc::tmem_ld_wait();
+    for (int j = 0; j < 16; ++j) out[(size_t)row * N + c0 + j] = v[j];
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 256);
+}
+
+}  // namespace
+}  // namespace mf
+
+using namespace mf;
+
+extern "C" int mf_tc_probe_gemm(const float* d_a, const float* d_w, float* d_out, int32_t k, int32_t n, int32_t mode,
+                                void* stream) {
+  MF_REQUIRE(d_a && d_w && d_out, "mf_tc_probe_gemm: null argument");
+  MF_REQUIRE(k >= 16 && k % 16 == 0 && k <= 256, "mf_tc_probe_gemm: K=%d must be a multiple of 16 in 16..256", k);
+  MF_REQUIRE(n >= 16 && n % 16 == 0 && n <= 256, "mf_tc_probe_gemm: N=%d must be a multiple of 16 in 16..256", n);
+  MF_REQUIRE(mode >= 0 && mode <= 2, "mf_tc_probe_gemm: bad mode");
+  const int kp = (k + 63) / 64 * 64;
+  const size_t smem = (size_t)2 * 128 * kp * 2 + (size_t)2 * n * kp * 2 + 1024;
+  MF_REQUIRE(smem <= 227 * 1024, "mf_tc_probe_gemm: operands do not fit shared memory");
+  MF_CUDA_CHECK(cudaFuncSetAttribute(tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tc_probe_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(d_a, d_w, d_out, k, n, mode);
+  return post_launch("tc_probe_kernel");
+}

@@ -246,7 +246,8 @@ class NormalizingFlow:
         xb = xb.contiguous()
         cb = cb.to(dtype).contiguous() if cb is not None else None
         N, D = xb.shape
-        desc, blob = m.packed(xb.device, dtype)
+        gemm = m.effective_gemm(dtype)
+        desc, blob = m.packed(xb.device, dtype, gemm=gemm)
         z = torch.empty_like(xb)
         ladj = torch.empty(N, dtype=dtype, device=xb.device)
         need_lp = want_logprob and not post
@@ -255,7 +256,7 @@ class NormalizingFlow:
         if debug:
             bins = torch.empty((len(core), N, D), dtype=torch.int8, device=xb.device)
             inside = torch.empty((len(core), N, D), dtype=torch.uint8, device=xb.device)
-        _cabi.flow_log_prob(desc, blob, xb, cb, logprob, z, ladj, bins, inside, m.gemm)
+        _cabi.flow_log_prob(desc, blob, xb, cb, logprob, z, ladj, bins, inside, gemm)
         z = z.reshape(*batch, D)
         ladj = ladj.reshape(batch)
         if ladj_pre is not None:
@@ -285,9 +286,10 @@ class NormalizingFlow:
         zb, cb, batch = self._rows(z)
         zb = zb.contiguous()
         cb = cb.to(dtype).contiguous() if cb is not None else None
-        desc, blob = m.packed(zb.device, dtype, identity_base=True)
+        gemm = m.effective_gemm(dtype, sampling=True)
+        desc, blob = m.packed(zb.device, dtype, identity_base=True, gemm=gemm)
         x = torch.empty_like(zb)
-        _cabi.flow_sample(desc, blob, zb, cb, x, m.gemm)
+        _cabi.flow_sample(desc, blob, zb, cb, x, gemm)
         x = x.reshape(*batch, m.features)
         for t in reversed(pre):
             x = t.inv(x)
@@ -369,7 +371,7 @@ class MAF(nn.Module):
             args = base_args if base_args is not None else [torch.zeros(features), torch.ones(features)]
             self.base = Unconditional(base, *args)  # the fork registers base_args as parameters
         self.gemm = {"exact": GEMM_EXACT, "tc_3xf16": GEMM_TC_3XF16, "tc_bf16": GEMM_TC_BF16}[gemm]
-        self._blob_cache = None
+        self._blob_cache = {}
         self._desc_cache = {}
         self._register_load_state_dict_pre_hook(self._rename_legacy_keys)
         if dtype is not None:
@@ -436,15 +438,23 @@ class MAF(nn.Module):
                 d.base_a[f], d.base_b[f] = float(a[f]), float(b[f])
         return d
 
-    def packed(self, device, dtype, identity_base=False):
+    def effective_gemm(self, dtype, sampling=False):
+        """Tensor-core modes cover fp32 log_prob; fp64 flows and sampling run the exact CUDA-core kernel."""
+        if dtype != torch.float32 or sampling:
+            return GEMM_EXACT
+        return self.gemm
+
+    def packed(self, device, dtype, identity_base=False, gemm=None):
         """(desc, blob): the kernel-side copy of the weights, rebuilt when any parameter changed."""
+        gemm = self.gemm if gemm is None else gemm
         core = self.core_transforms()
         params = []
         for t in core:
             for lin in t.hyper.linears():
                 params += [lin.weight, lin.bias, lin.mask]
-        key = (str(device), dtype, self.gemm, tuple((p.data_ptr(), p._version) for p in params))
-        if self._blob_cache is None or self._blob_cache[0] != key:
+        key = (str(device), dtype, tuple((p.data_ptr(), p._version) for p in params))
+        cached = self._blob_cache.get(gemm)
+        if cached is None or cached[0] != key:
             for p in params:
                 if p.device != device:
                     raise _cabi.MemflowB200Error(f"flow parameters live on {p.device}, data on {device}")
@@ -452,16 +462,17 @@ class MAF(nn.Module):
             ws = [p.detach().to(dtype).contiguous() for p in params[0::3]]
             bs = [p.detach().to(dtype).contiguous() for p in params[1::3]]
             ms = [p.detach().to(torch.uint8).contiguous() for p in params[2::3]]
-            nbytes = _cabi.flow_blob_bytes(desc, dtype, self.gemm)
+            nbytes = _cabi.flow_blob_bytes(desc, dtype, gemm)
             blob = torch.empty(nbytes, dtype=torch.uint8, device=device)
-            _cabi.flow_pack_weights(desc, ws, bs, ms, dtype, self.gemm, blob)
-            self._blob_cache = (key, blob)
+            _cabi.flow_pack_weights(desc, ws, bs, ms, dtype, gemm, blob)
+            cached = (key, blob)
+            self._blob_cache[gemm] = cached
         base_key = tuple((t.data_ptr(), t._version) for t in self.base.tensors())
         dent = self._desc_cache.get(identity_base)
         if dent is None or dent[0] != base_key:
             dent = (base_key, self.make_desc(identity_base))
             self._desc_cache[identity_base] = dent
-        return dent[1], self._blob_cache[1]
+        return dent[1], cached[1]
 
 
 class NSF(MAF):

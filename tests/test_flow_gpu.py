@@ -239,3 +239,64 @@ def test_one_dimensional_normalisation(cuda):
         p = flow(c.expand(xs.shape[0], -1)).log_prob(xs).exp()
     integral = torch.trapezoid(p, xs[:, 0]).item()
     assert abs(integral - 1) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-core paths (tcgen05): same oracle, same fp32 gate for the 3xFP16 split mode
+TC_CONFIGS = ["TF-A", "TF-B", "NCSF", "UniformNCSF", "PSNSF", "no-context"]
+
+
+@pytest.mark.parametrize("name", TC_CONFIGS)
+@pytest.mark.parametrize("mode", ["default", "stress"])
+@pytest.mark.parametrize("N", [3000, 129])
+def test_tc_3xf16_log_prob_parity(cuda, name, mode, N):
+    flow = build(name, cuda, torch.float32, mode=mode)
+    flow.gemm = flows.modules.GEMM_TC_3XF16
+    x, c = inputs(flow, N, 11, cuda, torch.float32)
+    with torch.no_grad():
+        lp, z, ladj, bins, inside = flow(c).log_prob_debug(x)
+    torch.cuda.synchronize()
+    spec = spec_from_module(flow)
+    xn = x.double().cpu().numpy()
+    cn = c.double().cpu().numpy() if c is not None else None
+    z_ref, ladj_ref, dbg = fo.flow_forward(spec, xn, cn, return_debug=True)
+    lp_ref = fo.base_log_prob(spec, z_ref) + ladj_ref
+    z32, ladj32 = fo.flow_forward(spec, xn, cn, dtype=np.float32)
+    lp32 = (fo.base_log_prob(spec, z32) + ladj32).astype(np.float64)
+    lp, z = lp.double().cpu().numpy(), z.double().cpu().numpy()
+    fin = np.isfinite(lp_ref)
+    assert np.array_equal(np.isfinite(lp), fin)
+    err = np.abs(lp[fin] - lp_ref[fin]) / scale_lp(lp_ref[fin])
+    print(f"TC 3xf16 {name} {mode} N={N}:")
+    fp32_gate(err, np.abs(lp32[fin] - lp_ref[fin]) / scale_lp(lp_ref[fin]), "log_prob")
+    zerr = (np.abs(z - z_ref) / np.maximum(1.0, np.abs(z_ref))).max(-1)
+    fp32_gate(zerr, (np.abs(z32 - z_ref) / np.maximum(1.0, np.abs(z_ref))).max(-1), "z")
+    k_ref = np.stack([d[0] for d in dbg]); m_ref = np.stack([d[1] for d in dbg])
+    mism = (bins.cpu().numpy() != k_ref) | (inside.cpu().numpy().astype(bool) != m_ref)
+    print(f"    bin/mask mismatches: {mism.sum()} of {mism.size}")
+    assert mism.mean() < 1e-3
+
+
+@pytest.mark.parametrize("name", ["TF-A", "TF-B"])
+def test_tc_bf16_log_prob_close(cuda, name):
+    """Throughput mode: bf16 operands (8-bit mantissa) -- agreement at the 1e-2 level, reported."""
+    flow = build(name, cuda, torch.float32, mode="default")
+    x, c = inputs(flow, 3000, 11, cuda, torch.float32)
+    with torch.no_grad():
+        ref = flow(c).log_prob(x)
+        flow.gemm = flows.modules.GEMM_TC_BF16
+        lp = flow(c).log_prob(x)
+    fin = torch.isfinite(ref)
+    assert torch.equal(torch.isfinite(lp), fin)
+    err = ((lp[fin] - ref[fin]).abs() / ref[fin].abs().clamp_min(1.0))
+    print(f"TC bf16 {name}: log_prob err median {err.median().item():.1e} max {err.max().item():.1e}")
+    assert err.median().item() < 5e-3 and err.max().item() < 0.2
+
+
+def test_tc_unsupported_shape_fails_loudly(cuda):
+    from memflow_msci_project_b200._cabi import MemflowB200Error
+    flow = build("UF", cuda, torch.float32)  # hidden width 512 > 128
+    flow.gemm = flows.modules.GEMM_TC_3XF16
+    x, c = inputs(flow, 64, 1, cuda, torch.float32)
+    with pytest.raises(MemflowB200Error), torch.no_grad():
+        flow(c).log_prob(x)
