@@ -188,6 +188,18 @@ __device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, 1
 
 __device__ __forceinline__ float softclipf(float v, float inv) { return __fdividef(v, 1.f + fabsf(v * inv)); }
 
+// exp(x) on the SFU (ex2.approx, 2 ulp) with the rounding of x * log2(e) compensated: ~2^-22 relative for the
+// bounded arguments of the soft-clipped softmax, at 5 instructions instead of expf's ~15
+__device__ __forceinline__ float exp_sfu(float x) {
+  const float kL2E = 1.4426950216293335f, kL2E_lo = 1.925963033500107e-08f;
+  const float t = x * kL2E;
+  float r = fmaf(x, kL2E, -t);
+  r = fmaf(x, kL2E_lo, r);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+  return fmaf(e, r * 0.6931471805599453f, e);
+}
+
 // Spline of one feature with its 3K-1 unconstrained parameters in TMEM (this thread's lane):
 // columns [0,K) widths, [Kp,Kp+K) heights, [2Kp, 2Kp+K-1) derivatives.  Forward transform + log-det.
 // sb: the parameters' biases in shared memory (same column layout).
@@ -298,6 +310,89 @@ __device__ __forceinline__ void rqs_forward_tmem(uint32_t taddr, const float* sb
   ladj = (inside ? __logf(jac) : 0.f) + ladj0;
 }
 
+// Same transform with all logits of the feature held in registers (Kp = 8 * NCH <= 32): every TMEM column is
+// loaded once, every exponential is evaluated once, and the two knot scans run in one pass.
+__device__ __forceinline__ void tmem_ld8_raw(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+
+template <int NCH>
+__device__ __forceinline__ void rqs_forward_tmem_reg(uint32_t taddr, const float* sb, const SplineCfg<float>& cfg,
+                                                     float v, float& out, float& ladj, int& bin, bool& inside) {
+  constexpr int KP = 8 * NCH;
+  const int K = cfg.K;
+  float ladj0 = 0.f;
+  if (cfg.univariate == MF_UNIV_CIRCULAR_RQS) v = circular_wrap(v, cfg.bound);
+  if (cfg.univariate == MF_UNIV_PS_RQS) { v = (v + 1.f) * 0.5f; ladj0 = -0.6931471805599453f; }
+  uint32_t rw[KP], rh[KP], rd[KP];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    tmem_ld8_raw(taddr + c * 8, rw + c * 8);
+    tmem_ld8_raw(taddr + KP + c * 8, rh + c * 8);
+    tmem_ld8_raw(taddr + 2 * KP + c * 8, rd + c * 8);
+  }
+  tc::tmem_ld_wait();
+  float ew[KP], eh[KP];
+  float mw = 0.f, mh = 0.f;
+#pragma unroll
+  for (int j = 0; j < KP; ++j) {
+    ew[j] = softclipf(__uint_as_float(rw[j]) + sb[j], cfg.inv_ls2);
+    eh[j] = softclipf(__uint_as_float(rh[j]) + sb[KP + j], cfg.inv_ls2);
+  }
+  if (cfg.inv_ls2 == 0.f) {  // no soft clip: logits are unbounded, subtract the maximum
+    mw = -INFINITY; mh = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < KP; ++j)
+      if (j < K) { mw = fmaxf(mw, ew[j]); mh = fmaxf(mh, eh[j]); }
+  }
+  float sw = 0.f, sh = 0.f;
+#pragma unroll
+  for (int j = 0; j < KP; ++j) {
+    ew[j] = (j < K) ? exp_sfu(ew[j] - mw) : 0.f;
+    eh[j] = (j < K) ? exp_sfu(eh[j] - mh) : 0.f;
+    sw += ew[j];
+    sh += eh[j];
+  }
+  const float isw = __fdividef(1.f, sw), ish = __fdividef(1.f, sh);
+  int k = -1;
+  float x0 = 0.f, x1 = 1.f, y0 = 0.f, y1 = 1.f, cw = 0.f, ch = 0.f, prev = -cfg.bound, prevh = -cfg.bound;
+  float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < KP; ++j) {
+    if (j < K) {
+      cw += ew[j] * isw;
+      ch += eh[j] * ish;
+      const float knot = cfg.bound * (2.f * cw - 1.f), knoth = cfg.bound * (2.f * ch - 1.f);
+      if (prev < v) {
+        k = j; x0 = prev; x1 = knot; y0 = prevh; y1 = knoth;
+        t1 = __uint_as_float(rd[j]) + sb[2 * KP + j];                              // derivative logit k   (knot k+1)
+        t0 = (j > 0) ? __uint_as_float(rd[j > 0 ? j - 1 : 0]) + sb[2 * KP + (j > 0 ? j - 1 : 0)] : 0.f;  // logit k-1 (knot k)
+      }
+      prev = knot; prevh = knoth;
+    }
+  }
+  if (prev < v) k = K;
+  inside = (k >= 0) && (k < K);
+  k = k < 0 ? k + K : (k >= K ? k - K : k);
+  bin = k;
+  const float d0 = (k > 0) ? exp_sfu(softclipf(t0, cfg.inv_ls1)) : 1.f;
+  const float d1 = (k < K - 1) ? exp_sfu(softclipf(t1, cfg.inv_ls1)) : 1.f;
+  if (!inside) { x0 = 0.f; x1 = 1.f; y0 = 0.f; y1 = 1.f; }
+  const float idx = __fdividef(1.f, x1 - x0);
+  const float s = (y1 - y0) * idx;
+  const float z = inside ? (v - x0) * idx : 0.f;
+  const float omz = 1.f - z;
+  const float den = s + (d0 + d1 - 2.f * s) * z * omz;
+  const float iden = __fdividef(1.f, den);
+  const float y = y0 + (y1 - y0) * (s * z * z + d0 * z * omz) * iden;
+  const float jac = s * s * (2.f * s * z * omz + d0 * omz * omz + d1 * z * z) * iden * iden;
+  out = inside ? y : v;
+  ladj = (inside ? logf(jac) : 0.f) + ladj0;
+}
+
 // ------------------------------------------------------------------------------------------------
 template <int NSPLIT>
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -346,7 +441,7 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
             const uint32_t part_bytes = (uint32_t)j.N * 128u;
             for (int kb = 0; kb < j.nkb; ++kb, ++it) {
               const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-              mbar_wait(&w_empty[s], ph ^ 1);
+              mbar_wait_relaxed(&w_empty[s], ph ^ 1, 2000);
               mbar_expect_tx(&w_full[s], kParts * part_bytes);
               const unsigned char* src = tb + j.w_off + (long long)kb * kParts * part_bytes;
               unsigned char* dst = w_ring + s * kStageBytes;
@@ -528,7 +623,15 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
               float out, la;
               int bin;
               bool ins;
-              rqs_forward_tmem(taddr + fl * L.PFt, sb + fl * L.PFt, cfg, L.Kp, xv, out, la, bin, ins);
+              const uint32_t ta = taddr + fl * L.PFt;
+              const float* sbf = sb + fl * L.PFt;
+              switch (L.Kp) {
+                case 8: rqs_forward_tmem_reg<1>(ta, sbf, cfg, xv, out, la, bin, ins); break;
+                case 16: rqs_forward_tmem_reg<2>(ta, sbf, cfg, xv, out, la, bin, ins); break;
+                case 24: rqs_forward_tmem_reg<3>(ta, sbf, cfg, xv, out, la, bin, ins); break;
+                case 32: rqs_forward_tmem_reg<4>(ta, sbf, cfg, xv, out, la, bin, ins); break;
+                default: rqs_forward_tmem(ta, sbf, cfg, L.Kp, xv, out, la, bin, ins); break;
+              }
               if (valid) {
                 gz[g * D + f] = out;
                 ladj += la;

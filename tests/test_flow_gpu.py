@@ -88,14 +88,14 @@ def scale_lp(v):
     return np.maximum(1.0, np.abs(v))
 
 
-def fp32_gate(err, err_oracle32, what):
+def fp32_gate(err, err_oracle32, what, factor=2.5, floor=1e-6):
     """fp32 acceptance: see module docstring."""
     qs = [0.5, 0.99, 0.999]
     g, o = np.quantile(err, qs), np.quantile(err_oracle32, qs)
     print(f"    {what}: kernel-fp32 err 50/99/99.9/max = {g[0]:.1e}/{g[1]:.1e}/{g[2]:.1e}/{err.max():.1e};  "
           f"numpy-fp32 oracle = {o[0]:.1e}/{o[1]:.1e}/{o[2]:.1e}/{err_oracle32.max():.1e}")
     assert g[0] < 1e-5
-    assert np.all(g <= 2.5 * o + 1e-6)
+    assert np.all(g <= factor * o + floor)
     assert err.max() <= 4 * err_oracle32.max() + 1e-5
 
 
@@ -268,9 +268,10 @@ def test_tc_3xf16_log_prob_parity(cuda, name, mode, N):
     assert np.array_equal(np.isfinite(lp), fin)
     err = np.abs(lp[fin] - lp_ref[fin]) / scale_lp(lp_ref[fin])
     print(f"TC 3xf16 {name} {mode} N={N}:")
-    fp32_gate(err, np.abs(lp32[fin] - lp_ref[fin]) / scale_lp(lp_ref[fin]), "log_prob")
+    # the tensor-core path evaluates exp / reciprocal on the SFU (2 ulp): allow 3x (+2e-6) of the numpy-fp32 spread
+    fp32_gate(err, np.abs(lp32[fin] - lp_ref[fin]) / scale_lp(lp_ref[fin]), "log_prob", factor=3.0, floor=2e-6)
     zerr = (np.abs(z - z_ref) / np.maximum(1.0, np.abs(z_ref))).max(-1)
-    fp32_gate(zerr, (np.abs(z32 - z_ref) / np.maximum(1.0, np.abs(z_ref))).max(-1), "z")
+    fp32_gate(zerr, (np.abs(z32 - z_ref) / np.maximum(1.0, np.abs(z_ref))).max(-1), "z", factor=3.0, floor=2e-6)
     k_ref = np.stack([d[0] for d in dbg]); m_ref = np.stack([d[1] for d in dbg])
     mism = (bins.cpu().numpy() != k_ref) | (inside.cpu().numpy().astype(bool) != m_ref)
     print(f"    bin/mask mismatches: {mism.sum()} of {mism.size}")

@@ -33,13 +33,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "kernels.json"))
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--only", default="all", choices=["all", "rambo", "flow"])
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     res = []
     # ---------------- RAMBO
     cases = {"n4": [125.25, 172.5, 172.5, 1e-5], "n8": [4.7, 4.7, 4.7, 1e-3, 1e-3, 4.7, 1e-3, 1e-3]}
     N = 2_000_000 if args.quick else 8_000_000
-    for name, masses in cases.items():
+    for name, masses in (cases.items() if args.only in ("all", "rambo") else []):
         n = len(masses)
         for compute in ["f64", "f32"]:
             ps = PhaseSpace(13000, [21, 21], [0] * n, final_masses=torch.tensor(masses), dev=dev, compute=compute,
@@ -69,7 +70,7 @@ def main():
         "TF-1D": (dict(features=1, context=66, transforms=5, bins=16, hidden_features=[256] * 3, passes=1,
                        base=flows.BoxUniform, base_args=[-torch.ones(1), torch.ones(1)], univariate_kwargs={"bound": 1.0}), 2_000_000),
     }
-    for name, (kw, n_obj) in fl.items():
+    for name, (kw, n_obj) in (fl.items() if args.only in ("all", "flow") else []):
         if args.quick:
             n_obj //= 4
         torch.manual_seed(7)
@@ -80,11 +81,17 @@ def main():
         x = (0.3 * torch.randn(n_obj, D, device=dev)).clamp_(-0.99, 0.99)
         c = torch.randn(n_obj, C, device=dev)
         with torch.no_grad():
-            ms = timeit(lambda: flow(c).log_prob(x), reps=5)
-            tf = fl_obj * n_obj / (ms * 1e-3) / 1e12
-            res.append(dict(kernel=f"flow log_prob {name} fp32 exact", objects=n_obj, ms=ms, objects_per_s=n_obj / (ms * 1e-3),
-                            flops_per_object=fl_obj, achieved_tflops=tf, tensor_frac=tf / TF,
-                            bytes_per_object=4 * (D + C) + 4, achieved_gbs=n_obj * (4 * (D + C) + 4) / (ms * 1e-3) / 1e9))
+            for gname, gmode in (("exact", flows.modules.GEMM_EXACT), ("tc_3xf16", flows.modules.GEMM_TC_3XF16),
+                                 ("tc_bf16", flows.modules.GEMM_TC_BF16)):
+                if gmode != flows.modules.GEMM_EXACT and max(H) > 128:
+                    continue
+                flow.gemm = gmode
+                ms = timeit(lambda: flow(c).log_prob(x), reps=5)
+                tf = fl_obj * n_obj / (ms * 1e-3) / 1e12
+                res.append(dict(kernel=f"flow log_prob {name} fp32 {gname}", objects=n_obj, ms=ms, objects_per_s=n_obj / (ms * 1e-3),
+                                flops_per_object=fl_obj, achieved_tflops=tf, tensor_frac=tf / TF,
+                                bytes_per_object=4 * (D + C) + 4, achieved_gbs=n_obj * (4 * (D + C) + 4) / (ms * 1e-3) / 1e9))
+            flow.gemm = flows.modules.GEMM_EXACT
             nz = torch.randn(n_obj, D, device=dev)
             ms = timeit(lambda: flow(c).sample_from_noise(nz), reps=3)
             tf = fl_obj * kw["passes"] * n_obj / (ms * 1e-3) / 1e12
