@@ -39,6 +39,14 @@ WORKLOAD = ("ttH 1M events/GPU: RAMBO n=4 forward+Jacobian + TF-A transfer-flow 
             "(D=3,C=65,T=5,K=16,[128]x4) on 10 objects/event + per-event reduce")
 
 
+GEMM_DESC = {"exact": "fp32 FMA on CUDA cores (flow_kernel)",
+             "tc_3xf16": "tcgen05, fp16 hi/lo split operands, 3 MMAs per product, fp32 accumulate (fp32-class accuracy)",
+             "tc_bf16": "tcgen05, bf16 operands, fp32 accumulate (throughput mode, ~1e-3 log_prob error)"}
+KERNEL_NAME = {"exact": "flow_kernel<float,8> (fused MAF log_prob, CUDA cores)",
+               "tc_3xf16": "flow_tc_kernel<3> (fused MAF log_prob, tcgen05 3xFP16)",
+               "tc_bf16": "flow_tc_kernel<1> (fused MAF log_prob, tcgen05 bf16)"}
+
+
 def flops_per_object():
     D, C, H, L, K, T = 3, 65, 128, 4, 16, 5
     return T * 2 * ((D + C) * H + (L - 1) * H * H + H * D * (3 * K - 1))
@@ -105,12 +113,12 @@ def synth_inputs(events, seed, torch, pin=False):
     return out
 
 
-def build_flow(torch, device):
+def build_flow(torch, device, gemm="exact"):
     from memflow_msci_project_b200 import flows
     torch.manual_seed(7)
     flow = flows.NSF(features=3, context=65, transforms=5, bins=16, hidden_features=[128] * 4, randperm=False,
                      base=flows.BoxUniform, base_args=[-torch.ones(3), torch.ones(3)],
-                     univariate_kwargs={"bound": 1.0}, passes=3)
+                     univariate_kwargs={"bound": 1.0}, passes=3, gemm=gemm)
     return flow.to(device)
 
 
@@ -179,7 +187,7 @@ def run_ours(args):
     r, x, ctx, mask = [t.to(dev) for t in host]
     ps = PhaseSpace(SQRT_S, [21, 21], [25, 6, -6, 21], final_masses=torch.tensor(MASSES), dev=dev,
                     check_inputs=False)
-    flow = build_flow(torch, dev)
+    flow = build_flow(torch, dev, args.gemm)
 
     def step_device():
         with torch.no_grad():
@@ -252,15 +260,17 @@ def run_ours(args):
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "events_per_gpu": events, "objects_per_event": P_OBJ,
-                           "rambo_compute": "f64", "flow_gemm": "exact-fp32-cuda-core",
+                           "rambo_compute": "f64", "flow_gemm": GEMM_DESC[args.gemm],
                            "l2": "inputs (2.8 GB/step) exceed the 126 MB L2, no flush needed"},
                 "gpu_launches": int(launches_per_step * args.steps),
                 "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(events * 4)},
-                "roofline": {"bound": "tensor", "kernel": "flow_kernel<float,8> (fused MAF log_prob)",
+                "roofline": {"bound": "tensor", "kernel": KERNEL_NAME[args.gemm],
                              "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                              "traffic": traffic, "peak_source": peak_src, "kernel_ms": ms_flow,
-                             "algorithmic_flops_per_object": flops_per_object()},
+                             "algorithmic_flops_per_object": flops_per_object(),
+                             "note": "achieved = ALGORITHMIC dense FLOPs / kernel time; the 3xFP16 mode issues 3 MMAs per "
+                                     "algorithmic product, so tensor-pipe work is 3x the algorithmic figure"},
                 "clocks": clocks}
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
@@ -281,6 +291,8 @@ def main():
     ap.add_argument("--events", type=int, default=1_000_000, help="events per GPU per step")
     ap.add_argument("--ref-events", type=int, default=40_000, help="events per step of the CPU port leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gemm", default="tc_3xf16", choices=["exact", "tc_3xf16", "tc_bf16"],
+                    help="conditioner GEMM arithmetic of the flow kernel (default: tensor cores at fp32-class accuracy)")
     args = ap.parse_args()
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     if args.impl == "reference":

@@ -558,15 +558,27 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
           const int kfill = L.in0_ksteps * 16;
           for (int f = 0; f < D; ++f) put1(row, f, valid ? gz[g * D + f] : 0.f);
           for (int k = D + C; k < kfill; ++k) put1(row, k, 0.f);
-          // context: coalesced over the flat [rows x C] range of this tile
+          // context: coalesced over the flat [rows x C] range of this tile, eight loads in flight per thread
           int r = 0, c = gt;
           while (C > 0 && c >= C) { c -= C; ++r; }
           const int dr = C > 0 ? 128 / C : 0, dc = C > 0 ? 128 % C : 0;
-          for (int idx = gt; idx < 128 * C; idx += 128) {
-            const float v = (r < rows) ? gc[tile0 * C + idx] : 0.f;
-            put1(r, D + c, v);
-            r += dr; c += dc;
-            if (c >= C) { c -= C; ++r; }
+          const float* gct = gc + tile0 * C;
+          const int total = 128 * C, valid_elems = rows * C;
+          for (int idx0 = gt; idx0 < total; idx0 += 8 * 128) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int idx = idx0 + u * 128;
+              v[u] = (idx < valid_elems) ? __ldg(gct + idx) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              if (idx0 + u * 128 < total) {
+                put1(r, D + c, v[u]);
+                r += dr; c += dc;
+                if (c >= C) { c -= C; ++r; }
+              }
+            }
           }
           fence_proxy_async_smem();
           mbar_arrive(&a_ready[t]);
@@ -584,30 +596,38 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
           const uint32_t taddr = tmem + lane_off + (uint32_t)(t * 256 + buf * 128);
           if (!j.last) {
             // hidden layer: TMEM -> +bias -> ReLU -> operand planes of the next layer (in place)
-            for (int c0 = 0; c0 < j.N; c0 += 16) {
-              float v[16];
-              tc::tmem_ld16(taddr + c0, v);
+            for (int c00 = 0; c00 < j.N; c00 += 32) {
+              float vv[32];
+              tc::tmem_ld16(taddr + c00, vv);
+              if (c00 + 16 < j.N) tc::tmem_ld16(taddr + c00 + 16, vv + 16);
               tc::tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 16; i += 4) {
-                const float4 b4 = *reinterpret_cast<const float4*>(sb + c0 + i);
-                v[i] = fmaxf(v[i] + b4.x, 0.f); v[i + 1] = fmaxf(v[i + 1] + b4.y, 0.f);
-                v[i + 2] = fmaxf(v[i + 2] + b4.z, 0.f); v[i + 3] = fmaxf(v[i + 3] + b4.w, 0.f);
-              }
+              for (int half = 0; half < 2; ++half) {
+                const int c0 = c00 + half * 16;
+                if (c0 < j.N) {
+                  float* v = vv + half * 16;
 #pragma unroll
-              for (int h8 = 0; h8 < 2; ++h8) {  // two 16-byte chunks of 8 columns
-                const uint32_t off = tc::sw128_offset(row, c0 + h8 * 8, 128);
-                if (NSPLIT == 3) {
-                  uint32_t hi[4], lo[4];
+                  for (int i = 0; i < 16; i += 4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(sb + c0 + i);
+                    v[i] = fmaxf(v[i] + b4.x, 0.f); v[i + 1] = fmaxf(v[i + 1] + b4.y, 0.f);
+                    v[i + 2] = fmaxf(v[i + 2] + b4.z, 0.f); v[i + 3] = fmaxf(v[i + 3] + b4.w, 0.f);
+                  }
 #pragma unroll
-                  for (int i = 0; i < 4; ++i) tc::split_f16(v[h8 * 8 + 2 * i], v[h8 * 8 + 2 * i + 1], hi[i], lo[i]);
-                  *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                  *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                } else {
-                  uint32_t pk[4];
+                  for (int h8 = 0; h8 < 2; ++h8) {  // two 16-byte chunks of 8 columns
+                    const uint32_t off = tc::sw128_offset(row, c0 + h8 * 8, 128);
+                    if (NSPLIT == 3) {
+                      uint32_t hi[4], lo[4];
 #pragma unroll
-                  for (int i = 0; i < 4; ++i) pk[i] = tc::pack_bf16(v[h8 * 8 + 2 * i], v[h8 * 8 + 2 * i + 1]);
-                  *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                      for (int i = 0; i < 4; ++i) tc::split_f16(v[h8 * 8 + 2 * i], v[h8 * 8 + 2 * i + 1], hi[i], lo[i]);
+                      *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                      *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    } else {
+                      uint32_t pk[4];
+#pragma unroll
+                      for (int i = 0; i < 4; ++i) pk[i] = tc::pack_bf16(v[h8 * 8 + 2 * i], v[h8 * 8 + 2 * i + 1]);
+                      *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                  }
                 }
               }
             }
