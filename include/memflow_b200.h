@@ -251,6 +251,17 @@ int mf_event_reduce(const void* d_logprob, const uint8_t* d_mask, const void* d_
 int mf_tc_probe_gemm(const float* d_a, const float* d_w, float* d_out, int32_t k, int32_t n, int32_t mode,
                      void* stream);
 
+/*
+ * Standalone zuko MonotonicRQSTransform on materialised parameters (a17): forward + log|dy/dx| or inverse of n
+ * independent scalars.
+ *   d_params [n, 3K-1]  (K widths | K heights | K-1 derivatives), unconstrained hyper-network outputs
+ *   d_x [n] -> d_y [n], d_ladj [n] (NULL for the inverse), d_bins [n] int8 / d_inside [n] uint8 (may be NULL)
+ *   univariate: MF_UNIV_* (circular shift / PS pre-map applied around the spline like in the flows)
+ */
+int mf_rqs_transform(const void* d_params, const void* d_x, int64_t n, int32_t bins, int32_t univariate, double bound,
+                     double slope, int32_t inverse, void* d_y, void* d_ladj, int8_t* d_bins, uint8_t* d_inside,
+                     int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -164,3 +164,13 @@ def tc_probe_gemm(a, w, mode):
                                     ctypes.c_int32(mode), _stream(a.device))
     check(rc, "mf_tc_probe_gemm")
     return out
+
+
+def rqs_transform(params, x, bins, univariate, bound, slope, inverse, y, ladj, bins_out=None, inside=None):
+    """zuko MonotonicRQSTransform on packed parameters [n, 3K-1] (mf_rqs_transform)."""
+    with torch.cuda.device(x.device):
+        rc = lib().mf_rqs_transform(_ptr(params), _ptr(x), ctypes.c_int64(x.numel()), ctypes.c_int32(bins),
+                                    ctypes.c_int32(univariate), ctypes.c_double(bound), ctypes.c_double(slope or 0.0),
+                                    ctypes.c_int32(1 if inverse else 0), _ptr(y), _ptr(ladj), _ptr(bins_out), _ptr(inside),
+                                    ctypes.c_int(_dtype_code(x.dtype)), _stream(x.device))
+    check(rc, "mf_rqs_transform")

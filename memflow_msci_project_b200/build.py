@@ -14,13 +14,18 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(OUT_DIR, "libmemflow_b200.so")
-SOURCES = ["abi.cu", "rambo.cu", "flow.cu", "reduce.cu", "tc_probe.cu", "flow_tc.cu"]
+SOURCES = ["abi.cu", "rambo.cu", "flow.cu", "reduce.cu", "tc_probe.cu", "flow_tc.cu", "rqs.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
     "-ccbin", "/usr/bin/g++",
 ]
+
+
+# rambo.cu: --use_fast_math only changes FLOAT arithmetic (approximate division / sqrt / transcendentals),
+# i.e. the fp32 throughput mode; the fp64 parity mode is unaffected.
+EXTRA_FLAGS = {"rambo.cu": ["--use_fast_math"]}
 
 
 def _stale(target, deps):
@@ -44,7 +49,7 @@ def build(force=False, verbose=False):
 
     def compile_one(job):
         s, o = job
-        cmd = [NVCC] + FLAGS + ["-c", s, "-o", o]
+        cmd = [NVCC] + FLAGS + EXTRA_FLAGS.get(os.path.basename(s), []) + ["-c", s, "-o", o]
         res = subprocess.run(cmd, capture_output=True, text=True)
         log = os.path.join(OUT_DIR, os.path.basename(s) + ".ptxas.log")
         with open(log, "w") as f:

@@ -21,6 +21,7 @@
 #include <algorithm>
 
 #include "flow_common.cuh"
+#include "spline_reg.cuh"
 #include "tc_common.cuh"
 
 namespace mf {
@@ -186,20 +187,6 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
-__device__ __forceinline__ float softclipf(float v, float inv) { return __fdividef(v, 1.f + fabsf(v * inv)); }
-
-// exp(x) on the SFU (ex2.approx, 2 ulp) with the rounding of x * log2(e) compensated: ~2^-22 relative for the
-// bounded arguments of the soft-clipped softmax, at 5 instructions instead of expf's ~15
-__device__ __forceinline__ float exp_sfu(float x) {
-  const float kL2E = 1.4426950216293335f, kL2E_lo = 1.925963033500107e-08f;
-  const float t = x * kL2E;
-  float r = fmaf(x, kL2E, -t);
-  r = fmaf(x, kL2E_lo, r);
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
-  return fmaf(e, r * 0.6931471805599453f, e);
-}
-
 // Spline of one feature with its 3K-1 unconstrained parameters in TMEM (this thread's lane):
 // columns [0,K) widths, [Kp,Kp+K) heights, [2Kp, 2Kp+K-1) derivatives.  Forward transform + log-det.
 // sb: the parameters' biases in shared memory (same column layout).
@@ -323,10 +310,6 @@ template <int NCH>
 __device__ __forceinline__ void rqs_forward_tmem_reg(uint32_t taddr, const float* sb, const SplineCfg<float>& cfg,
                                                      float v, float& out, float& ladj, int& bin, bool& inside) {
   constexpr int KP = 8 * NCH;
-  const int K = cfg.K;
-  float ladj0 = 0.f;
-  if (cfg.univariate == MF_UNIV_CIRCULAR_RQS) v = circular_wrap(v, cfg.bound);
-  if (cfg.univariate == MF_UNIV_PS_RQS) { v = (v + 1.f) * 0.5f; ladj0 = -0.6931471805599453f; }
   uint32_t rw[KP], rh[KP], rd[KP];
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
@@ -335,62 +318,14 @@ __device__ __forceinline__ void rqs_forward_tmem_reg(uint32_t taddr, const float
     tmem_ld8_raw(taddr + 2 * KP + c * 8, rd + c * 8);
   }
   tc::tmem_ld_wait();
-  float ew[KP], eh[KP];
-  float mw = 0.f, mh = 0.f;
+  float lw[KP], lh[KP], ld[KP];
 #pragma unroll
-  for (int j = 0; j < KP; ++j) {
-    ew[j] = softclipf(__uint_as_float(rw[j]) + sb[j], cfg.inv_ls2);
-    eh[j] = softclipf(__uint_as_float(rh[j]) + sb[KP + j], cfg.inv_ls2);
+  for (int j = 0; j < KP; ++j) {  // accumulator + bias
+    lw[j] = __uint_as_float(rw[j]) + sb[j];
+    lh[j] = __uint_as_float(rh[j]) + sb[KP + j];
+    ld[j] = __uint_as_float(rd[j]) + sb[2 * KP + j];
   }
-  if (cfg.inv_ls2 == 0.f) {  // no soft clip: logits are unbounded, subtract the maximum
-    mw = -INFINITY; mh = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < KP; ++j)
-      if (j < K) { mw = fmaxf(mw, ew[j]); mh = fmaxf(mh, eh[j]); }
-  }
-  float sw = 0.f, sh = 0.f;
-#pragma unroll
-  for (int j = 0; j < KP; ++j) {
-    ew[j] = (j < K) ? exp_sfu(ew[j] - mw) : 0.f;
-    eh[j] = (j < K) ? exp_sfu(eh[j] - mh) : 0.f;
-    sw += ew[j];
-    sh += eh[j];
-  }
-  const float isw = __fdividef(1.f, sw), ish = __fdividef(1.f, sh);
-  int k = -1;
-  float x0 = 0.f, x1 = 1.f, y0 = 0.f, y1 = 1.f, cw = 0.f, ch = 0.f, prev = -cfg.bound, prevh = -cfg.bound;
-  float t0 = 0.f, t1 = 0.f;
-#pragma unroll
-  for (int j = 0; j < KP; ++j) {
-    if (j < K) {
-      cw += ew[j] * isw;
-      ch += eh[j] * ish;
-      const float knot = cfg.bound * (2.f * cw - 1.f), knoth = cfg.bound * (2.f * ch - 1.f);
-      if (prev < v) {
-        k = j; x0 = prev; x1 = knot; y0 = prevh; y1 = knoth;
-        t1 = __uint_as_float(rd[j]) + sb[2 * KP + j];                              // derivative logit k   (knot k+1)
-        t0 = (j > 0) ? __uint_as_float(rd[j > 0 ? j - 1 : 0]) + sb[2 * KP + (j > 0 ? j - 1 : 0)] : 0.f;  // logit k-1 (knot k)
-      }
-      prev = knot; prevh = knoth;
-    }
-  }
-  if (prev < v) k = K;
-  inside = (k >= 0) && (k < K);
-  k = k < 0 ? k + K : (k >= K ? k - K : k);
-  bin = k;
-  const float d0 = (k > 0) ? exp_sfu(softclipf(t0, cfg.inv_ls1)) : 1.f;
-  const float d1 = (k < K - 1) ? exp_sfu(softclipf(t1, cfg.inv_ls1)) : 1.f;
-  if (!inside) { x0 = 0.f; x1 = 1.f; y0 = 0.f; y1 = 1.f; }
-  const float idx = __fdividef(1.f, x1 - x0);
-  const float s = (y1 - y0) * idx;
-  const float z = inside ? (v - x0) * idx : 0.f;
-  const float omz = 1.f - z;
-  const float den = s + (d0 + d1 - 2.f * s) * z * omz;
-  const float iden = __fdividef(1.f, den);
-  const float y = y0 + (y1 - y0) * (s * z * z + d0 * z * omz) * iden;
-  const float jac = s * s * (2.f * s * z * omz + d0 * omz * omz + d1 * z * z) * iden * iden;
-  out = inside ? y : v;
-  ladj = (inside ? logf(jac) : 0.f) + ladj0;
+  rqs_eval_reg<NCH>(lw, lh, ld, cfg, false, v, out, ladj, bin, inside);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -29,9 +29,35 @@ constexpr int kEPB = 128;  // events per CTA (one per thread)
 
 template <typename T>
 struct Mth;
+// fp64 sqrt / reciprocal for the parity mode: fp32 SFU seed + Newton steps in fp64 (faithfully rounded,
+// ~1 ulp) instead of the IEEE sequences with their slow-path calls.  Arguments outside the fp32 exponent
+// range (never produced by physical kinematics) take the library routine.
+__device__ __forceinline__ double fast_sqrt(double x) {
+  const float xf = (float)x;
+  if (!(xf > 1e-30f && xf < 1e30f)) return sqrt(x);  // 0, negative (NaN like the reference), NaN, huge
+  double y = (double)rsqrtf(xf);
+  y = y * fma(-0.5 * x, y * y, 1.5);
+  double sq = x * y;
+  return fma(fma(-sq, sq, x), 0.5 * y, sq);
+}
+__device__ __forceinline__ double fast_rcp(double x) {
+  const float xf = (float)x;
+  if (!(fabsf(xf) > 1e-30f && fabsf(xf) < 1e30f)) return 1.0 / x;
+  double y = (double)__fdividef(1.f, xf);
+  y = y * fma(-x, y, 2.0);
+  y = y * fma(-x, y, 2.0);
+  return y;
+}
+__device__ __forceinline__ double fast_div(double a, double b) {
+  const double y = fast_rcp(b);
+  const double q = a * y;
+  return fma(fma(-q, b, a), y, q);
+}
+__device__ __forceinline__ float fast_div(float a, float b) { return a / b; }
+
 template <>
 struct Mth<double> {
-  static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+  static __device__ __forceinline__ double sqrt_(double x) { return fast_sqrt(x); }
   static __device__ __forceinline__ double exp_(double x) { return exp(x); }
   static __device__ __forceinline__ double log_(double x) { return log(x); }
   static __device__ __forceinline__ double pow_(double x, double y) { return pow(x, y); }
@@ -58,30 +84,50 @@ __device__ __forceinline__ T ipow(T x, int e) {
 // Root u in [0,1] of v = (e+1) u^e - e u^(e+1)   (massless_map, rambo_generator.py:142-143;
 // solved there by bisect_vec_batch, :400-446).  Bracketed Newton from the asymptotic seeds
 //   u ~ (v/(e+1))^(1/e)  (v -> 0),   1-u ~ sqrt(2(1-v)/(e(e+1)))  (v -> 1).
+__device__ __forceinline__ float solve_massless_u_f32(float v, int e) {
+  const float fe = (float)e;
+  const float vc = 2.f * ipow((fe - 1.f) / fe, e);  // value at the inflection point u = (e-1)/e
+  float u;
+  if (v < vc)
+    u = (e == 2) ? sqrtf(v * (1.f / 3.f)) : powf(v / (fe + 1.f), 1.f / fe);
+  else
+    u = 1.f - sqrtf(2.f * (1.f - v) / (fe * (fe + 1.f)));
+  float lo = 0.f, hi = 1.f;
+  const int iters = e <= 8 ? 4 : 12;
+  for (int it = 0; it < iters; ++it) {
+    const float ue1 = ipow(u, e - 1);
+    const float g = ue1 * u * ((fe + 1.f) - fe * u) - v;
+    const float gp = fe * (fe + 1.f) * ue1 * (1.f - u);
+    if (g < 0.f) lo = u;
+    if (g > 0.f) hi = u;
+    const float un = u - g / gp;
+    u = (un >= lo && un <= hi) ? un : 0.5f * (lo + hi);
+  }
+  return u;
+}
+
 template <typename T>
 __device__ __forceinline__ T solve_massless_u(T v, int e) {
   if (!(v > T(0))) return T(0);  // the bisection walks to the left/right end for v outside (0,1)
   if (!(v < T(1))) return T(1);
   if (e == 1) {                  // v = 2u - u^2
     T s = Mth<T>::sqrt_(T(1) - v);
-    return v / (T(1) + s);
+    return fast_div(v, T(1) + s);
   }
+  float uf = solve_massless_u_f32((float)v, e);
+  if (sizeof(T) == 4) return (T)uf;
+  // fp64: polish the fp32 root with bracketed Newton steps (quadratic: 1e-4 -> 1e-8 -> 1e-16)
   const T fe = T(e);
-  const T vc = T(2) * ipow((fe - T(1)) / fe, e);  // value at the inflection point u = (e-1)/e
-  T u;
-  if (v < vc)
-    u = Mth<T>::pow_(v / (fe + T(1)), T(1) / fe);
-  else
-    u = T(1) - Mth<T>::sqrt_(T(2) * (T(1) - v) / (fe * (fe + T(1))));
-  T lo = T(0), hi = T(1);
-  const int iters = (sizeof(T) == 4) ? (e <= 8 ? 4 : 12) : (e <= 8 ? 6 : 16);
+  uf = fminf(fmaxf(uf, 1e-30f), 1.f);
+  T u = (T)uf, lo = T(0), hi = T(1);
+  const int iters = e <= 8 ? 3 : 6;
   for (int it = 0; it < iters; ++it) {
     T ue1 = ipow(u, e - 1);
     T g = ue1 * u * ((fe + T(1)) - fe * u) - v;
     T gp = fe * (fe + T(1)) * ue1 * (T(1) - u);
     if (g < T(0)) lo = u;
     if (g > T(0)) hi = u;
-    T un = u - g / gp;
+    T un = u - fast_div(g, gp);
     u = (un >= lo && un <= hi) ? un : T(0.5) * (lo + hi);
   }
   return u;
@@ -92,6 +138,8 @@ struct RamboAux {
   double e_thr;      // sqrt_s * exp(-q/2): E_cm at u_b = 1 as the (fp32-valued) q defines it
   double thr_gap;    // e_thr - sum_mass
   double dS[MF_MAX_FINAL];  // tail_sum_fwd[i] - tail_sum_fwd[i+1] - mass[i]  (fp32 cumsum residue)
+  double inv_A, inv_c2;     // 1/x_A, 1/x_c2
+  double vol_scale;         // vol_coef / vol_fact
   int cuts_on;
   int perm[MF_MAX_FINAL];
 };
@@ -176,7 +224,7 @@ __device__ __forceinline__ void rambo_forward_event(const mf_rambo_desc& d, cons
   if (ua != ua || ub != ub) flags |= MF_FLAG_NAN_INPUT;  // rambo_generator.py:191-199
   TC x1, x2, E_cm, K0, wgt_x;
   if constexpr (!kF32) {
-    TC mlogx1 = ((TC)d.x_c1 + M::sqrt_((TC)d.x_c1sq + (TC(-2) * ua) / (TC)d.x_A)) / (TC)d.x_c2;
+    TC mlogx1 = ((TC)d.x_c1 + M::sqrt_((TC)d.x_c1sq + (TC(-2) * ua) * (TC)aux.inv_A)) * (TC)aux.inv_c2;
     TC mlogx2 = (-mlogx1 + (TC)d.x_q) * ub;
     x1 = M::exp_(-mlogx1);
     x2 = M::exp_(-mlogx2);
@@ -243,25 +291,25 @@ __device__ __forceinline__ void rambo_forward_event(const mf_rambo_desc& d, cons
         b = (Mi[i] - Mn + m) * (Mi[i] + Mn - m);
       }
       const TC sab = M::sqrt_(a * b);
-      const TC invM = TC(1) / Mi[i];
+      const TC invM = fast_div(TC(1), Mi[i]);
       qi[i] = TC(0.5) * sab * invM;
       if (i < n - 2) {
         // rho(M_i,M_{i+1},m_i) / rho(K_i,K_{i+1},0) * M_{i+1}/K_{i+1}
         TC omu2 = (TC(1) - U[i]) * (TC(1) + U[i]);  // (K_i^2 - K_{i+1}^2)/K_i^2
-        w *= (double)(sab * invM * invM * Mn / (omu2 * K[i + 1]));
+        w *= (double)fast_div(sab * invM * invM * Mn, omu2 * K[i + 1]);
       }
     }
   }
   {
     // 8 rho(M_{n-2}, m_{n-1}, m_{n-2}) with the fp32-rounded squares of the reference (:489-493)
     const TC Msq = Mi[n - 2] * Mi[n - 2];
-    TC t = M::sqrt_((Msq - (TC)d.last_plus_sq) * (Msq - (TC)d.last_minus_sq)) / Msq;
+    TC t = fast_div(M::sqrt_((Msq - (TC)d.last_plus_sq) * (Msq - (TC)d.last_minus_sq)), Msq);
     w *= (double)t;
-    TC km = K[0] / Mi[0];
+    TC km = fast_div(K[0], Mi[0]);
     w *= (double)ipow(km, 2 * n - 4);
     // Vol(E_cm, n), :111-140
     double E2 = (double)E_cm * (double)E_cm;
-    w *= d.vol_coef * ipow(E2, n - 2) / d.vol_fact;
+    w *= aux.vol_scale * ipow(E2, n - 2);
   }
   logw_out = want_logw ? (TC)log(w) : TC(0);
   if (d.quirks & MF_QUIRK_F32_VOLUME) {
@@ -289,7 +337,7 @@ __device__ __forceinline__ void rambo_forward_event(const mf_rambo_desc& d, cons
       // boost_t(p, Q_vec/Q_E) (phasespace/utils.py:88-118)
       TC Mq = Mi[i];
       TC bp = Qx * px + Qy * py + Qz * pz;
-      TC inv = TC(1) / (Mq * (QE + Mq));
+      TC inv = fast_div(TC(1), Mq * (QE + Mq));
       TC f = bp * inv + Ep * (QE + Mq) * inv;  // gamma2*bp*/... + gamma*E, per unit of Q_vec
       px += f * Qx; py += f * Qy; pz += f * Qz;
       TC E = M::sqrt_(px * px + py * py + pz * pz + msq);  // set_square_t, :339
@@ -607,6 +655,9 @@ int fill_aux(const mf_rambo_desc* d, const int32_t* perm, RamboAux* aux) {
   MF_REQUIRE(n >= 3 && n <= MF_MAX_FINAL, "n_final=%d outside 3..%d", n, MF_MAX_FINAL);
   aux->e_thr = d->sqrt_s * exp(-0.5 * d->x_q);
   aux->thr_gap = aux->e_thr - d->sum_mass;
+  aux->inv_A = 1.0 / d->x_A;
+  aux->inv_c2 = 1.0 / d->x_c2;
+  aux->vol_scale = d->vol_coef / d->vol_fact;
   for (int i = 0; i < MF_MAX_FINAL; ++i) {
     aux->dS[i] = 0.0;
     aux->perm[i] = i;

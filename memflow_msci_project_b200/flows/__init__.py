@@ -2,9 +2,10 @@
 from .modules import (MAF, NCSF, NSF, BoxUniform, DiagNormal, MaskedAutoregressiveTransform, MaskedLinear,
                       MaskedMLP, NormalizingFlow, SimpleAffineTransform, Unconditional,
                       UnconditionalDistribution)
+from .transforms import MonotonicRQSTransform
 from .custom import NCSF_gaussian, Custom_spline_flow_ps, PSNSF, UniformNCSF, UniformNSF
 
 __all__ = ["MAF", "NSF", "NCSF", "BoxUniform", "DiagNormal", "MaskedAutoregressiveTransform", "MaskedLinear",
            "MaskedMLP", "NormalizingFlow", "SimpleAffineTransform", "Unconditional",
            "UnconditionalDistribution", "NCSF_gaussian", "Custom_spline_flow_ps", "PSNSF", "UniformNCSF",
-           "UniformNSF"]
+           "UniformNSF", "MonotonicRQSTransform"]

@@ -301,3 +301,34 @@ def test_tc_unsupported_shape_fails_loudly(cuda):
     x, c = inputs(flow, 64, 1, cuda, torch.float32)
     with pytest.raises(MemflowB200Error), torch.no_grad():
         flow(c).log_prob(x)
+
+
+# ------------------------------------------------------------------------------------------------
+# standalone spline on materialised parameters (mf_rqs_transform)
+@pytest.mark.parametrize("K", [4, 16, 30, 55])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("N", [1000, 256 * 40 + 7])
+def test_standalone_rqs_transform(cuda, K, dtype, N):
+    g = torch.Generator().manual_seed(K * 7 + N)
+    w = 2.0 * torch.randn(N, K, generator=g)
+    h = 2.0 * torch.randn(N, K, generator=g)
+    d = 2.0 * torch.randn(N, K - 1, generator=g)
+    bound = 1.5
+    x = (0.6 * bound * torch.randn(N, generator=g)).clamp(-1.3 * bound, 1.3 * bound)  # some outside [-bound, bound]
+    t = flows.MonotonicRQSTransform(w.to(cuda, dtype), h.to(cuda, dtype), d.to(cuda, dtype), bound=bound)
+    y, ladj, bins, inside = t.call_debug(x.to(cuda, dtype))
+    knots = fo.rqs_knots(w.double().numpy(), h.double().numpy(), d.double().numpy(), bound, 1e-3)
+    y_ref, ladj_ref, k_ref, m_ref = fo.rqs_forward(x.double().numpy(), *knots)
+    tol = 1e-10 if dtype == torch.float64 else 2e-4   # fp32: narrow bins amplify knot rounding, see module docstring
+    assert np.abs(y.double().cpu().numpy() - y_ref).max() < tol
+    assert np.abs(ladj.double().cpu().numpy() - ladj_ref).max() < (1e-9 if dtype == torch.float64 else 5e-2)
+    mism = (bins.cpu().numpy() != k_ref) | (inside.cpu().numpy() != m_ref)
+    assert mism.sum() == 0 if dtype == torch.float64 else mism.mean() < 1e-3
+    assert (~m_ref).sum() > 0 and np.array_equal(y.double().cpu().numpy()[~m_ref], x.double().numpy()[~m_ref])  # identity outside
+    # inverse round trip
+    xb = t.inv(y)
+    rt = (xb.double().cpu() - x.double()).abs()
+    if dtype == torch.float64:
+        assert rt.max().item() < 1e-9
+    else:  # logits ~ N(0, 2^2): bins as narrow as 1e-4 amplify fp32 rounding in the worst element
+        assert rt.median().item() < 1e-6 and rt.quantile(0.999).item() < 5e-4 and rt.max().item() < 2e-2

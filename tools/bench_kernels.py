@@ -33,7 +33,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "kernels.json"))
     ap.add_argument("--quick", action="store_true")
-    ap.add_argument("--only", default="all", choices=["all", "rambo", "flow"])
+    ap.add_argument("--only", default="all", choices=["all", "rambo", "flow", "rqs"])
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     res = []
@@ -98,6 +98,20 @@ def main():
             res.append(dict(kernel=f"flow sample {name} fp32 exact (passes={kw['passes']})", objects=n_obj, ms=ms,
                             objects_per_s=n_obj / (ms * 1e-3), achieved_tflops=tf, tensor_frac=tf / TF))
         del x, c, flow
+    # ---------------- standalone spline on materialised parameters (HBM-bound)
+    if args.only in ("all", "rqs", "flow"):
+        for K in (16, 30):
+            n_el = 4_000_000 if args.quick else 16_000_000
+            P = 3 * K - 1
+            phi = torch.randn(n_el, P, device=dev)
+            xx = (0.5 * torch.randn(n_el, device=dev)).clamp_(-0.99, 0.99)
+            t = flows.MonotonicRQSTransform.from_packed(phi, K, bound=1.0)
+            ms = timeit(lambda: t.call_and_ladj(xx), reps=5)
+            bytes_el = 4 * P + 4 + 8
+            gbs = n_el * bytes_el / (ms * 1e-3) / 1e9
+            res.append(dict(kernel=f"rqs_transform standalone K={K} fp32 (fwd+ladj)", elements=n_el, ms=ms, events_per_s=n_el / (ms * 1e-3),
+                            bytes_per_event=bytes_el, achieved_gbs=gbs, hbm_frac=gbs / HBM))
+            del phi, xx, t
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     json.dump(dict(peaks=dict(hbm_gbs=HBM, bf16_tflops_sustained=TF), results=res), open(args.out, "w"), indent=1)
     for r in res:
