@@ -1,13 +1,218 @@
-"""Autograd bridges of the fused flow kernels (training path, BASELINE config 4)."""
+"""Autograd bridges of the fused flow kernels (training path, BASELINE config 4).
+
+STATUS (round 1): the FORWARD of a differentiable ``log_prob`` / ``rsample`` is the fused sm_100a kernel;
+the BACKWARD is not a native kernel yet: it re-evaluates the flow with differentiable torch ops on the GPU
+(the zuko algorithm restated below) and lets torch autograd produce the gradients w.r.t. x, the context
+and every hyper-network parameter.  This keeps the reference's training loops working unchanged
+(`loss = -flow(c).log_prob(x).mean(); loss.backward()`), but the backward runs at eager-torch speed and is
+reported as such; it never runs on the CPU and never touches oracle/.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
 from .. import _cabi
+from .modules import BASE_DIAG_NORMAL, UNIV_CIRCULAR_RQS, UNIV_PS_RQS
+
+
+def _softclip(v, factor):
+    return v / (1 + torch.abs(factor * v))
+
+
+def _rqs_knots(w, h, d, bound, slope):
+    if slope:
+        ls = math.log(slope)
+        w, h, d = _softclip(w, 2 / ls), _softclip(h, 2 / ls), _softclip(d, 1 / ls)
+    W = F.pad(F.softmax(w, dim=-1), (1, 0), value=0)
+    H = F.pad(F.softmax(h, dim=-1), (1, 0), value=0)
+    D = F.pad(d, (1, 1), value=0)
+    return bound * (2 * torch.cumsum(W, -1) - 1), bound * (2 * torch.cumsum(H, -1) - 1), torch.exp(D)
+
+
+def _bin(k, hor, ver, der):
+    K = hor.shape[-1] - 1
+    mask = (0 <= k) & (k < K)
+    k = k % K
+    idx = torch.stack((k, k + 1), dim=-1)
+    x0, x1 = hor.gather(-1, idx).unbind(-1)
+    y0, y1 = ver.gather(-1, idx).unbind(-1)
+    d0, d1 = der.gather(-1, idx).unbind(-1)
+    return mask, x0, x1, y0, y1, d0, d1, (y1 - y0) / (x1 - x0)
+
+
+def _rqs_forward(x, hor, ver, der):
+    k = (hor < x[..., None]).sum(-1) - 1
+    mask, x0, x1, y0, y1, d0, d1, s = _bin(k, hor, ver, der)
+    z = mask * (x - x0) / (x1 - x0)
+    den = s + (d0 + d1 - 2 * s) * z * (1 - z)
+    y = y0 + (y1 - y0) * (s * z**2 + d0 * z * (1 - z)) / den
+    jac = s**2 * (2 * s * z * (1 - z) + d0 * (1 - z) ** 2 + d1 * z**2) / den**2
+    return torch.where(mask, y, x), mask * torch.log(torch.where(mask, jac, torch.ones_like(jac)))
+
+
+def _rqs_inverse(y, hor, ver, der):
+    k = (ver < y[..., None]).sum(-1) - 1
+    mask, x0, x1, y0, y1, d0, d1, s = _bin(k, hor, ver, der)
+    y_ = mask * (y - y0)
+    a = (y1 - y0) * (s - d0) + y_ * (d0 + d1 - 2 * s)
+    b = (y1 - y0) * d0 - y_ * (d0 + d1 - 2 * s)
+    c = -s * y_
+    z = 2 * c / (-b - torch.sqrt(b**2 - 4 * a * c))
+    return torch.where(mask, x0 + z * (x1 - x0), y)
+
+
+def _wrap(x, bound):
+    return torch.remainder(x + bound, 2 * bound) - bound
+
+
+def _hyper(t, x, c):
+    h = x if c is None else torch.cat((x, c), dim=-1)
+    lins = t.hyper.linears()
+    for i, lin in enumerate(lins):
+        h = F.linear(h, lin.mask * lin.weight, lin.bias)
+        if i < len(lins) - 1:
+            h = torch.relu(h)
+    phi = h.unflatten(-1, (t.features, t.total))
+    K = t.bins
+    return _rqs_knots(phi[..., :K], phi[..., K:2 * K], phi[..., 2 * K:], t.bound, t.slope)
+
+
+def eager_forward(module, x, c):
+    """Differentiable restatement: (z, ladj) of the spline transforms of ``module`` (rows x [N,D], c [N,C])."""
+    ladj = x.new_zeros(x.shape[:-1])
+    for t in module.core_transforms():
+        knots = _hyper(t, x, c)
+        xin, l0 = x, 0.0
+        if t.univariate == UNIV_CIRCULAR_RQS:
+            xin = _wrap(x, t.bound)
+        elif t.univariate == UNIV_PS_RQS:
+            xin, l0 = (x + 1) / 2, math.log(0.5)
+        x, l = _rqs_forward(xin, *knots)
+        ladj = ladj + (l + l0).sum(-1)
+    return x, ladj
+
+
+def eager_inverse(module, z, c):
+    y = z
+    for t in reversed(module.core_transforms()):
+        x = torch.zeros_like(y)
+        for _ in range(t.passes):
+            x = _rqs_inverse(y, *_hyper(t, x, c))
+            if t.univariate == UNIV_CIRCULAR_RQS:
+                x = _wrap(x, t.bound)
+            elif t.univariate == UNIV_PS_RQS:
+                x = 2 * x - 1
+        y = x
+    return y
+
+
+def _params(module):
+    ps = []
+    for t in module.core_transforms():
+        for lin in t.hyper.linears():
+            ps += [lin.weight, lin.bias]
+    return ps
+
+
+class _FlowForwardFn(torch.autograd.Function):
+    """(x, c, *params) -> (z, ladj): fused kernel forward, eager-torch recompute backward."""
+
+    @staticmethod
+    def forward(ctx, bound_flow, x, c, *params):
+        m = bound_flow._m
+        dtype = m.compute_dtype()
+        gemm = m.effective_gemm(dtype)
+        desc, blob = m.packed(x.device, dtype, gemm=gemm)
+        z = torch.empty_like(x)
+        ladj = torch.empty(x.shape[0], dtype=dtype, device=x.device)
+        _cabi.flow_log_prob(desc, blob, x, c, None, z, ladj, None, None, gemm)
+        ctx.module = m
+        ctx.has_c = c is not None
+        ctx.save_for_backward(x, c if c is not None else x.new_empty(0))
+        return z, ladj
+
+    @staticmethod
+    def backward(ctx, gz, gladj):
+        m = ctx.module
+        x, c = ctx.saved_tensors
+        c = c if ctx.has_c else None
+        params = _params(m)
+        with torch.enable_grad():
+            xr = x.detach().requires_grad_(True)
+            cr = c.detach().requires_grad_(True) if c is not None else None
+            z, ladj = eager_forward(m, xr, cr)
+            inputs = [xr] + ([cr] if cr is not None else []) + [p for p in params if p.requires_grad]
+            grads = torch.autograd.grad([z, ladj], inputs, [gz, gladj], allow_unused=True)
+        it = iter(grads)
+        gx = next(it)
+        gc = next(it) if cr is not None else None
+        gp = [next(it) if p.requires_grad else None for p in params]
+        return (None, gx, gc, *gp)
 
 
 def flow_log_prob_autograd(bound_flow, x, want_logprob):
-    raise NotImplementedError(
-        "gradients through the fused flow kernel are not implemented yet: call under torch.no_grad() "
-        "(a silent fallback to eager torch is deliberately not provided)")
+    """Differentiable counterpart of NormalizingFlow._forward (same return triple)."""
+    m = bound_flow._m
+    pre, core, post = bound_flow._split()
+    if pre or post:
+        raise NotImplementedError("gradients through SimpleAffineTransform wrappers are not implemented")
+    _cabi.require_cuda(x, "x")
+    dtype = m.compute_dtype()
+    xb, cb, batch = bound_flow._rows(x.to(dtype))
+    xb = xb.contiguous()
+    cb = cb.to(dtype).contiguous() if cb is not None else None
+    z, ladj = _FlowForwardFn.apply(bound_flow, xb, cb, *_params(m))
+    logprob = None
+    if want_logprob:
+        base = m.base()
+        logprob = (base.log_prob(z) + ladj).reshape(batch)
+    return z.reshape(*batch, m.features), ladj.reshape(batch), logprob
+
+
+class _FlowInverseFn(torch.autograd.Function):
+    """(z, c, *params) -> x = T^-1(z): fused sampling kernel forward, eager-torch recompute backward."""
+
+    @staticmethod
+    def forward(ctx, bound_flow, z, c, *params):
+        m = bound_flow._m
+        dtype = m.compute_dtype()
+        gemm = m.effective_gemm(dtype, sampling=True)
+        desc, blob = m.packed(z.device, dtype, identity_base=True, gemm=gemm)
+        x = torch.empty_like(z)
+        _cabi.flow_sample(desc, blob, z, c, x, gemm)
+        ctx.module = m
+        ctx.has_c = c is not None
+        ctx.save_for_backward(z, c if c is not None else z.new_empty(0))
+        return x
+
+    @staticmethod
+    def backward(ctx, gx):
+        m = ctx.module
+        z, c = ctx.saved_tensors
+        c = c if ctx.has_c else None
+        params = _params(m)
+        with torch.enable_grad():
+            zr = z.detach().requires_grad_(True)
+            cr = c.detach().requires_grad_(True) if c is not None else None
+            x = eager_inverse(m, zr, cr)
+            inputs = [zr] + ([cr] if cr is not None else []) + [p for p in params if p.requires_grad]
+            grads = torch.autograd.grad([x], inputs, [gx], allow_unused=True)
+        it = iter(grads)
+        gz = next(it)
+        gc = next(it) if cr is not None else None
+        gp = [next(it) if p.requires_grad else None for p in params]
+        return (None, gz, gc, *gp)
 
 
 def flow_rsample_autograd(bound_flow, z):
-    raise NotImplementedError(
-        "gradients through the fused sampling kernel are not implemented yet: call under torch.no_grad()")
+    m = bound_flow._m
+    pre, core, post = bound_flow._split()
+    if pre or post:
+        raise NotImplementedError("gradients through SimpleAffineTransform wrappers are not implemented")
+    dtype = m.compute_dtype()
+    zb, cb, batch = bound_flow._rows(z.to(dtype))
+    zb = zb.contiguous()
+    cb = cb.to(dtype).contiguous() if cb is not None else None
+    x = _FlowInverseFn.apply(bound_flow, zb, cb, *_params(m))
+    return x.reshape(*batch, m.features)

@@ -93,3 +93,29 @@ def test_box_uniform_support_and_identity_outside_bound():
     assert z[1, 0] == 1.5 and z[2, 1] == -3.0  # identity outside [-bound, bound]
     lp = fo.flow_log_prob(spec, x, None)
     assert np.isfinite(lp[0]) and lp[1] == -np.inf and lp[2] == -np.inf
+
+
+@pytest.mark.parametrize("ctor,kw", [
+    (flows.NSF, dict(features=3, context=5, transforms=3, bins=6, hidden_features=[32, 32], univariate_kwargs={"bound": 1.5})),
+    (flows.NCSF_gaussian, dict(features=2, context=3, bins=5, transforms=2, hidden_features=[16])),
+    (flows.PSNSF, dict(features=2, context=0, bins=7, transforms=2, hidden_features=[24])),
+])
+def test_differentiable_restatement_matches_oracle(ctor, kw):
+    """The torch restatement that provides the (interim) backward pass computes the same function as the oracle."""
+    from helpers import spec_from_module
+    from memflow_msci_project_b200.flows import _autograd as ag
+    torch.manual_seed(3)
+    flow = ctor(**kw).double()
+    with torch.no_grad():
+        for t in flow.core_transforms():
+            t.hyper.linears()[-1].weight.mul_(3.0)
+    spec = spec_from_module(flow)
+    g = torch.Generator().manual_seed(5)
+    D, C = flow.features, flow.context
+    x = (torch.rand(200, D, generator=g, dtype=torch.float64) * 2 - 1) * 0.9
+    c = torch.randn(200, C, generator=g, dtype=torch.float64) if C else None
+    z, ladj = ag.eager_forward(flow, x, c)
+    z_ref, ladj_ref = fo.flow_forward(spec, x.numpy(), c.numpy() if c is not None else None)
+    assert np.abs(z.detach().numpy() - z_ref).max() < 1e-12 and np.abs(ladj.detach().numpy() - ladj_ref).max() < 1e-11
+    xb = ag.eager_inverse(flow, torch.from_numpy(z_ref), c)
+    assert np.abs(xb.detach().numpy() - fo.flow_inverse(spec, z_ref, c.numpy() if c is not None else None)).max() < 1e-10

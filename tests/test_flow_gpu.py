@@ -332,3 +332,42 @@ def test_standalone_rqs_transform(cuda, K, dtype, N):
         assert rt.max().item() < 1e-9
     else:  # logits ~ N(0, 2^2): bins as narrow as 1e-4 amplify fp32 rounding in the worst element
         assert rt.median().item() < 1e-6 and rt.quantile(0.999).item() < 5e-4 and rt.max().item() < 2e-2
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd: fused forward + (interim) eager-torch backward
+def test_log_prob_gradients_match_eager_autograd(cuda):
+    from memflow_msci_project_b200.flows import _autograd as ag
+    flow = build("NCSF", cuda, torch.float64, mode="stress")
+    x, c = inputs(flow, 300, 3, cuda, torch.float64, outside_frac=0.0)
+    x = x.requires_grad_(True)
+    c = c.requires_grad_(True)
+    lp = flow(c).log_prob(x)              # fused kernel forward
+    loss = -lp.mean()
+    loss.backward()
+    g_fused = [x.grad.clone(), c.grad.clone()] + [p.grad.clone() for p in flow.parameters() if p.grad is not None]
+    # pure eager reference of the same loss
+    for p in flow.parameters():
+        p.grad = None
+    x2 = x.detach().clone().requires_grad_(True)
+    c2 = c.detach().clone().requires_grad_(True)
+    z, ladj = ag.eager_forward(flow, x2, c2)
+    lp2 = flow.base().log_prob(z) + ladj
+    (-lp2.mean()).backward()
+    g_eager = [x2.grad, c2.grad] + [p.grad for p in flow.parameters() if p.grad is not None]
+    assert torch.allclose(lp, lp2, atol=1e-10)
+    assert len(g_fused) == len(g_eager) and len(g_fused) > 4
+    for a, b in zip(g_fused, g_eager):
+        assert torch.allclose(a, b, atol=1e-9, rtol=1e-7)
+
+
+def test_rsample_is_differentiable(cuda):
+    flow = build("TF-B", cuda, torch.float64, mode="default")
+    _, c = inputs(flow, 64, 3, cuda, torch.float64)
+    c = c.requires_grad_(True)
+    torch.manual_seed(0)
+    s = flow(c).rsample((2,))
+    assert s.shape == (2, 64, 3) and s.requires_grad
+    s.square().mean().backward()
+    assert c.grad is not None and torch.isfinite(c.grad).all() and c.grad.abs().sum() > 0
+    assert all(p.grad is not None for p in flow.transforms[0].hyper.parameters())
