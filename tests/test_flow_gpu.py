@@ -371,3 +371,23 @@ def test_rsample_is_differentiable(cuda):
     s.square().mean().backward()
     assert c.grad is not None and torch.isfinite(c.grad).all() and c.grad.abs().sum() > 0
     assert all(p.grad is not None for p in flow.transforms[0].hyper.parameters())
+
+
+def test_host_pipeline_matches_single_shot(cuda):
+    """Chunked, overlapped host pipeline == one-shot device evaluation, bit for bit."""
+    from memflow_msci_project_b200.likelihood import HostPipeline, event_log_prob
+    from memflow_msci_project_b200.phasespace.phasespace import PhaseSpace
+    flow = build("TF-A", cuda, torch.float32, mode="default")
+    ps = PhaseSpace(13000, [21, 21], [25, 6, -6, 21], dev=cuda, check_inputs=False)
+    B, P = 1000, 4
+    g = torch.Generator().manual_seed(1)
+    r = torch.rand(B, 10, generator=g).clamp_(1e-6, 1 - 1e-6).pin_memory()
+    x = (0.3 * torch.randn(B, P, 3, generator=g)).pin_memory()
+    c = torch.randn(B, P, 65, generator=g).pin_memory()
+    m = (torch.rand(B, P, generator=g) < 0.8).to(torch.uint8).pin_memory()
+    pipe = HostPipeline(ps, flow, B, P, 3, 65, 10, cuda, chunks=3)
+    out = pipe.run(r, x, c, m)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = event_log_prob(ps, flow, r.to(cuda), x.to(cuda), c.to(cuda), m.to(cuda))[0]
+    assert torch.equal(out, ref.cpu())
