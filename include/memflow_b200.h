@@ -224,7 +224,8 @@ int mf_flow_pack_weights(const mf_flow_desc* desc, const void* const* d_weights,
  */
 int mf_flow_log_prob(const mf_flow_desc* desc, const void* d_blob, const void* d_x,
                      const void* d_ctx, int64_t n, void* d_logprob, void* d_z, void* d_ladj,
-                     int8_t* d_bins, uint8_t* d_inside, int dtype, int gemm, void* stream);
+                     int8_t* d_bins, uint8_t* d_inside, int dtype, int gemm, void* d_workspace,
+                     int64_t workspace_bytes, void* stream);
 
 /*
  * flow(c).sample() / .rsample()  (a16): x = T^-1(z), z = base sample built from caller-supplied
@@ -233,7 +234,16 @@ int mf_flow_log_prob(const mf_flow_desc* desc, const void* d_blob, const void* d
  *   d_noise [N,D] -> d_x [N,D];  d_ctx [N,C]
  */
 int mf_flow_sample(const mf_flow_desc* desc, const void* d_blob, const void* d_noise,
-                   const void* d_ctx, int64_t n, void* d_x, int dtype, int gemm, void* stream);
+                   const void* d_ctx, int64_t n, void* d_x, int dtype, int gemm, void* d_workspace,
+                   int64_t workspace_bytes, void* stream);
+
+/*
+ * Scratch the two calls above need for (desc, n, dtype, gemm); op 0 = log_prob, 1 = sample.  The caller
+ * allocates it (the ABI never allocates) and may reuse it across calls on one stream.  0 = none needed.
+ */
+#define MF_FLOW_OP_LOG_PROB 0
+#define MF_FLOW_OP_SAMPLE 1
+int64_t mf_flow_workspace_bytes(const mf_flow_desc* desc, int64_t n, int dtype, int gemm, int op);
 
 /*
  * Per-event likelihood tail: out[e] = sum_p logprob[e,p] * mask[e,p] - logw[e]

@@ -129,21 +129,34 @@ def flow_pack_weights(desc, weights, biases, masks, dtype, gemm, blob):
     check(rc, "mf_flow_pack_weights")
 
 
+def _flow_workspace(desc, n, dtype, gemm, op, device):
+    L = lib()
+    L.mf_flow_workspace_bytes.restype = ctypes.c_int64
+    nb = L.mf_flow_workspace_bytes(ctypes.byref(desc), ctypes.c_int64(n), ctypes.c_int(_dtype_code(dtype)),
+                                   ctypes.c_int(gemm), ctypes.c_int(op))
+    if nb < 0:
+        check(-1, "mf_flow_workspace_bytes")
+    return torch.empty(int(nb), dtype=torch.uint8, device=device) if nb > 0 else None
+
+
 def flow_log_prob(desc, blob, x, ctx, logprob, z, ladj, bins, inside, gemm):
+    ws = _flow_workspace(desc, x.shape[0], x.dtype, gemm, 0, x.device)
     with torch.cuda.device(x.device):
         rc = lib().mf_flow_log_prob(ctypes.byref(desc), _ptr(blob), _ptr(x), _ptr(ctx),
                                     ctypes.c_int64(x.shape[0]), _ptr(logprob), _ptr(z), _ptr(ladj),
                                     _ptr(bins), _ptr(inside), ctypes.c_int(_dtype_code(x.dtype)),
-                                    ctypes.c_int(gemm), _stream(x.device))
+                                    ctypes.c_int(gemm), _ptr(ws), ctypes.c_int64(ws.numel() if ws is not None else 0),
+                                    _stream(x.device))
     check(rc, "mf_flow_log_prob")
 
 
 def flow_sample(desc, blob, noise, ctx, x, gemm):
+    ws = _flow_workspace(desc, noise.shape[0], noise.dtype, gemm, 1, noise.device)
     with torch.cuda.device(noise.device):
         rc = lib().mf_flow_sample(ctypes.byref(desc), _ptr(blob), _ptr(noise), _ptr(ctx),
                                   ctypes.c_int64(noise.shape[0]), _ptr(x),
-                                  ctypes.c_int(_dtype_code(noise.dtype)), ctypes.c_int(gemm),
-                                  _stream(noise.device))
+                                  ctypes.c_int(_dtype_code(noise.dtype)), ctypes.c_int(gemm), _ptr(ws),
+                                  ctypes.c_int64(ws.numel() if ws is not None else 0), _stream(noise.device))
     check(rc, "mf_flow_sample")
 
 

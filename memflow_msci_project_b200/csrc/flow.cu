@@ -458,25 +458,35 @@ static int flow_run(const mf_flow_desc* desc, const FlowKernelArgs& a, int dtype
 
 int mf_flow_log_prob(const mf_flow_desc* desc, const void* d_blob, const void* d_x, const void* d_ctx,
                      int64_t n, void* d_logprob, void* d_z, void* d_ladj, int8_t* d_bins,
-                     uint8_t* d_inside, int dtype, int gemm, void* stream) {
+                     uint8_t* d_inside, int dtype, int gemm, void* d_workspace, int64_t workspace_bytes,
+                     void* stream) {
   MF_REQUIRE(n >= 0, "mf_flow_log_prob: negative count");
   MF_REQUIRE(desc && d_blob && (d_x || n == 0), "mf_flow_log_prob: null argument");
   FlowKernelArgs a{};
   a.blob = d_blob; a.x = d_x; a.ctx = d_ctx; a.n = n;
   a.logprob = d_logprob; a.z = d_z; a.ladj = d_ladj; a.bins = d_bins; a.inside = d_inside;
+  a.work = d_workspace; a.work_bytes = workspace_bytes;
   a.mode = 0; a.passes = desc->passes; a.base = desc->base; a.univariate = desc->univariate;
   a.bound = desc->bound; a.slope = desc->slope;
   return flow_run(desc, a, dtype, gemm, stream);
 }
 
+int64_t mf_flow_workspace_bytes(const mf_flow_desc* desc, int64_t n, int dtype, int gemm, int op) {
+  if (check_flow_common(desc, dtype, gemm) != MF_OK || n < 0) return -1;
+  if (gemm == MF_GEMM_EXACT) return 0;
+  return flow_tc_workspace_bytes(*desc, n, gemm, op);
+}
+
 int mf_flow_sample(const mf_flow_desc* desc, const void* d_blob, const void* d_noise, const void* d_ctx,
-                   int64_t n, void* d_x, int dtype, int gemm, void* stream) {
+                   int64_t n, void* d_x, int dtype, int gemm, void* d_workspace, int64_t workspace_bytes,
+                   void* stream) {
   MF_REQUIRE(n >= 0, "mf_flow_sample: negative count");
   MF_REQUIRE(desc && d_blob && ((d_noise && d_x) || n == 0), "mf_flow_sample: null argument");
   MF_REQUIRE(desc->passes >= 1 && desc->passes <= desc->features, "passes=%d outside 1..features", desc->passes);
   FlowKernelArgs a{};
   a.blob = d_blob; a.x = d_noise; a.ctx = d_ctx; a.n = n;
   a.z = d_x;
+  a.work = d_workspace; a.work_bytes = workspace_bytes;
   a.mode = 1; a.passes = desc->passes; a.base = desc->base; a.univariate = desc->univariate;
   a.bound = desc->bound; a.slope = desc->slope;
   return flow_run(desc, a, dtype, gemm, stream);

@@ -88,6 +88,8 @@ struct FlowKernelArgs {
   void* ladj;
   int8_t* bins;
   uint8_t* inside;
+  void* work;         // caller-provided scratch (mf_flow_workspace_bytes)
+  long long work_bytes;
   int mode;           // 0 = log_prob / transform, 1 = sample
   int passes;
   int base;
@@ -106,6 +108,7 @@ int flow_tc_blob_bytes(const mf_flow_desc& d, int gemm, long long* bytes);
 int flow_tc_pack(const mf_flow_desc& d, const void* const* w, const void* const* b, const uint8_t* const* m,
                  int gemm, void* blob, long long blob_bytes, cudaStream_t st);
 int flow_tc_run(const mf_flow_desc& d, const FlowKernelArgs& a, const BaseParams& bp, int gemm, cudaStream_t st);
+long long flow_tc_workspace_bytes(const mf_flow_desc& d, long long n, int gemm, int op);
 
 #ifdef __CUDACC__
 template <typename T> struct FM;

@@ -308,7 +308,8 @@ __device__ __forceinline__ void tmem_ld8_raw(uint32_t taddr, uint32_t* r) {
 
 template <int NCH>
 __device__ __forceinline__ void rqs_forward_tmem_reg(uint32_t taddr, const float* sb, const SplineCfg<float>& cfg,
-                                                     float v, float& out, float& ladj, int& bin, bool& inside) {
+                                                     bool inverse, float v, float& out, float& ladj, int& bin,
+                                                     bool& inside) {
   constexpr int KP = 8 * NCH;
   uint32_t rw[KP], rh[KP], rd[KP];
 #pragma unroll
@@ -325,7 +326,7 @@ __device__ __forceinline__ void rqs_forward_tmem_reg(uint32_t taddr, const float
     lh[j] = __uint_as_float(rh[j]) + sb[KP + j];
     ld[j] = __uint_as_float(rd[j]) + sb[2 * KP + j];
   }
-  rqs_eval_reg<NCH>(lw, lh, ld, cfg, false, v, out, ladj, bin, inside);
+  rqs_eval_reg<NCH>(lw, lh, ld, cfg, inverse, v, out, ladj, bin, inside);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -347,6 +348,9 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
   const long long n = args.n;
   const long long n_tiles = (n + 127) / 128;
   const long long n_pairs = (n_tiles + 1) / 2;
+  const bool inverse = args.mode == 1;                 // sampling: transforms in reverse, `passes` sweeps each
+  const int sweeps = inverse ? args.passes : 1;
+  const int n_units = L.T * sweeps;                    // one unit = one hyper-network evaluation of a tile
   const unsigned char* blob = static_cast<const unsigned char*>(args.blob);
   const float* bias_all = reinterpret_cast<const float*>(blob + L.bias_off);
 
@@ -369,7 +373,8 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
     if (lane == 0) {
       uint32_t it = 0;
       for (long long p = blockIdx.x; p < n_pairs; p += gridDim.x) {
-        for (int tr = 0; tr < L.T; ++tr) {
+        for (int unit = 0; unit < n_units; ++unit) {
+          const int tr = inverse ? (L.T - 1 - unit / sweeps) : unit;
           const unsigned char* tb = blob + (long long)tr * L.t_stride;
           for (int ji = 0; ji < L.njobs; ++ji) {
             const TcJob& j = L.job[ji];
@@ -395,7 +400,7 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
       uint32_t aph[2] = {0, 0};     // a_ready phases
       for (long long p = blockIdx.x; p < n_pairs; p += gridDim.x) {
         const int ntile = (2 * p + 1 < n_tiles) ? 2 : 1;
-        for (int tr = 0; tr < L.T; ++tr) {
+        for (int unit = 0; unit < n_units; ++unit) {
           for (int ji = 0; ji < L.njobs; ++ji) {
             const TcJob& j = L.job[ji];
             const uint32_t idesc = tc::make_idesc_f16(NSPLIT == 3 ? 0 : 1, 128, j.N);
@@ -482,11 +487,23 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
       const int rows = (int)min((long long)128, n - tile0);
       const bool valid = row < rows;
       const long long g = tile0 + row;
-      // working copy of x lives in the z buffer (each thread touches only its own row)
+      // working copy of x lives in the output buffer (each thread touches only its own row); when sampling,
+      // gx holds the noise and the base sample a + b * noise is the starting point
       if (valid)
-        for (int f = 0; f < D; ++f) gz[g * D + f] = gx[g * D + f];
+        for (int f = 0; f < D; ++f) {
+          float v0 = gx[g * D + f];
+          if (inverse)
+            v0 = (args.base == MF_BASE_DIAG_NORMAL) ? (float)bp.a[f] + (float)bp.b[f] * v0
+                                                   : (float)bp.a[f] + ((float)bp.b[f] - (float)bp.a[f]) * v0;
+          gz[g * D + f] = v0;
+        }
+      float* gy = static_cast<float*>(args.work);  // sampling: target y of the transform being inverted
       float ladj = 0.f;
-      for (int tr = 0; tr < L.T; ++tr) {
+      for (int unit = 0; unit < n_units; ++unit) {
+        const int tr = inverse ? (L.T - 1 - unit / sweeps) : unit;
+        if (inverse && (unit % sweeps) == 0 && valid) {  // y <- x, x <- 0  (AutoregressiveTransform._inverse)
+          for (int f = 0; f < D; ++f) { gy[g * D + f] = gz[g * D + f]; gz[g * D + f] = 0.f; }
+        }
         const float* bias_t = bias_all + (size_t)tr * L.bias_stride;
         // ---- stage (x | ctx | 0) as the layer-0 operand
         {
@@ -574,24 +591,24 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
             // last-layer chunk: splines of the chunk's features straight out of TMEM
             for (int fl = 0; fl < j.nfeat; ++fl) {
               const int f = j.feat0 + fl;
-              const float xv = valid ? gz[g * D + f] : 0.f;
+              const float xv = valid ? (inverse ? gy[g * D + f] : gz[g * D + f]) : 0.f;
               float out, la;
               int bin;
               bool ins;
               const uint32_t ta = taddr + fl * L.PFt;
               const float* sbf = sb + fl * L.PFt;
               switch (L.Kp) {
-                case 8: rqs_forward_tmem_reg<1>(ta, sbf, cfg, xv, out, la, bin, ins); break;
-                case 16: rqs_forward_tmem_reg<2>(ta, sbf, cfg, xv, out, la, bin, ins); break;
-                case 24: rqs_forward_tmem_reg<3>(ta, sbf, cfg, xv, out, la, bin, ins); break;
-                case 32: rqs_forward_tmem_reg<4>(ta, sbf, cfg, xv, out, la, bin, ins); break;
+                case 8: rqs_forward_tmem_reg<1>(ta, sbf, cfg, inverse, xv, out, la, bin, ins); break;
+                case 16: rqs_forward_tmem_reg<2>(ta, sbf, cfg, inverse, xv, out, la, bin, ins); break;
+                case 24: rqs_forward_tmem_reg<3>(ta, sbf, cfg, inverse, xv, out, la, bin, ins); break;
+                case 32: rqs_forward_tmem_reg<4>(ta, sbf, cfg, inverse, xv, out, la, bin, ins); break;
                 default: rqs_forward_tmem(ta, sbf, cfg, L.Kp, xv, out, la, bin, ins); break;
               }
               if (valid) {
                 gz[g * D + f] = out;
                 ladj += la;
-                if (args.bins) args.bins[((size_t)tr * n + g) * D + f] = (int8_t)bin;
-                if (args.inside) args.inside[((size_t)tr * n + g) * D + f] = ins ? 1 : 0;
+                if (!inverse && args.bins) args.bins[((size_t)tr * n + g) * D + f] = (int8_t)bin;
+                if (!inverse && args.inside) args.inside[((size_t)tr * n + g) * D + f] = ins ? 1 : 0;
               }
             }
             tc::fence_before_thread_sync();
@@ -599,7 +616,7 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
           }
         }
       }
-      if (valid) {
+      if (valid && !inverse) {
         if (args.ladj) static_cast<float*>(args.ladj)[g] = ladj;
         if (args.logprob) {
           float lp = 0.f;
@@ -651,12 +668,25 @@ int flow_tc_pack(const mf_flow_desc& d, const void* const* w, const void* const*
   return MF_OK;
 }
 
+long long flow_tc_workspace_bytes(const mf_flow_desc& d, long long n, int gemm, int op) {
+  (void)gemm;
+  if (op == MF_FLOW_OP_SAMPLE) return n * d.features * 4;  // y targets of the transform being inverted
+  return 0;
+}
+
 int flow_tc_run(const mf_flow_desc& d, const FlowKernelArgs& a, const BaseParams& bp, int gemm, cudaStream_t st) {
   TcLayout L;
   int rc = make_tc_layout(d, gemm, &L);
   if (rc != MF_OK) return rc;
-  MF_REQUIRE(a.mode == 0, "tensor-core path implements log_prob / transform only (sampling uses MF_GEMM_EXACT)");
-  MF_REQUIRE(a.z != nullptr, "tensor-core flow path needs the z output buffer (it is the working copy of x)");
+  MF_REQUIRE(a.z != nullptr, "tensor-core flow path needs the z / x output buffer (it is the working copy of x)");
+  if (a.mode == 1) {
+    if (L.Kp > 32) {
+      set_error("tensor-core sampling needs bins <= 32 (got %d); use MF_GEMM_EXACT", d.bins);
+      return MF_EUNSUPPORTED;
+    }
+    MF_REQUIRE(a.work != nullptr && a.work_bytes >= flow_tc_workspace_bytes(d, a.n, gemm, MF_FLOW_OP_SAMPLE),
+               "tensor-core sampling needs a workspace of mf_flow_workspace_bytes() bytes");
+  }
   const int parts = (L.nsplit == 3) ? 2 : 1;
   const size_t smem = (size_t)2 * parts * kABufBytes + (size_t)kStages * parts * kWPartBytes;
   const long long n_pairs = ((a.n + 127) / 128 + 1) / 2;

@@ -439,8 +439,11 @@ class MAF(nn.Module):
         return d
 
     def effective_gemm(self, dtype, sampling=False):
-        """Tensor-core modes cover fp32 log_prob; fp64 flows and sampling run the exact CUDA-core kernel."""
-        if dtype != torch.float32 or sampling:
+        """Tensor-core modes cover fp32; fp64 flows (and tensor-core sampling with more than 32 bins) run the
+        exact CUDA-core kernel."""
+        if dtype != torch.float32:
+            return GEMM_EXACT
+        if sampling and self.gemm != GEMM_EXACT and self.core_transforms()[0].bins > 32:
             return GEMM_EXACT
         return self.gemm
 

@@ -93,10 +93,15 @@ def main():
                                 bytes_per_object=4 * (D + C) + 4, achieved_gbs=n_obj * (4 * (D + C) + 4) / (ms * 1e-3) / 1e9))
             flow.gemm = flows.modules.GEMM_EXACT
             nz = torch.randn(n_obj, D, device=dev)
-            ms = timeit(lambda: flow(c).sample_from_noise(nz), reps=3)
-            tf = fl_obj * kw["passes"] * n_obj / (ms * 1e-3) / 1e12
-            res.append(dict(kernel=f"flow sample {name} fp32 exact (passes={kw['passes']})", objects=n_obj, ms=ms,
-                            objects_per_s=n_obj / (ms * 1e-3), achieved_tflops=tf, tensor_frac=tf / TF))
+            for gname, gmode in (("exact", flows.modules.GEMM_EXACT), ("tc_3xf16", flows.modules.GEMM_TC_3XF16)):
+                if gmode != flows.modules.GEMM_EXACT and (max(H) > 128 or K > 32):
+                    continue
+                flow.gemm = gmode
+                ms = timeit(lambda: flow(c).sample_from_noise(nz), reps=3)
+                tf = fl_obj * kw["passes"] * n_obj / (ms * 1e-3) / 1e12
+                res.append(dict(kernel=f"flow sample {name} fp32 {gname} (passes={kw['passes']})", objects=n_obj, ms=ms,
+                                objects_per_s=n_obj / (ms * 1e-3), achieved_tflops=tf, tensor_frac=tf / TF))
+            flow.gemm = flows.modules.GEMM_EXACT
         del x, c, flow
     # ---------------- standalone spline on materialised parameters (HBM-bound)
     if args.only in ("all", "rqs", "flow"):
