@@ -192,7 +192,8 @@ typedef struct mf_flow_desc {
   int32_t passes;     /* AutoregressiveTransform.passes (fixed-point sweeps of the inverse) */
   int32_t univariate; /* MF_UNIV_* */
   int32_t base;       /* MF_BASE_* */
-  int32_t reserved;
+  int32_t ctx_group;  /* consecutive x rows sharing ONE context row (context hoisted per event in the MEM
+                         sweep, BASELINE config 5); 0 or 1 = one context row per x row */
   double bound;       /* spline domain [-bound, bound] */
   double slope;       /* soft-clip slope of MonotonicRQSTransform (1e-3 in zuko >= 0.2); <= 0 disables */
   double base_a[MF_MAX_FEATURES];

@@ -217,7 +217,7 @@ flow_kernel(const __grid_constant__ FlowLayout L, const __grid_constant__ FlowKe
                                                   : (T)bp.a[c] + ((T)bp.b[c] - (T)bp.a[c]) * v;
           }
         } else if (c < D + C) {
-          v = gc[(tile0 + m) * C + (c - D)];
+          v = gc[((tile0 + m) / args.ctx_group) * C + (c - D)];
         }
       }
       in0[i] = v;
@@ -466,6 +466,7 @@ int mf_flow_log_prob(const mf_flow_desc* desc, const void* d_blob, const void* d
   a.blob = d_blob; a.x = d_x; a.ctx = d_ctx; a.n = n;
   a.logprob = d_logprob; a.z = d_z; a.ladj = d_ladj; a.bins = d_bins; a.inside = d_inside;
   a.work = d_workspace; a.work_bytes = workspace_bytes;
+  a.ctx_group = desc->ctx_group > 1 ? desc->ctx_group : 1;
   a.mode = 0; a.passes = desc->passes; a.base = desc->base; a.univariate = desc->univariate;
   a.bound = desc->bound; a.slope = desc->slope;
   return flow_run(desc, a, dtype, gemm, stream);
@@ -487,6 +488,7 @@ int mf_flow_sample(const mf_flow_desc* desc, const void* d_blob, const void* d_n
   a.blob = d_blob; a.x = d_noise; a.ctx = d_ctx; a.n = n;
   a.z = d_x;
   a.work = d_workspace; a.work_bytes = workspace_bytes;
+  a.ctx_group = desc->ctx_group > 1 ? desc->ctx_group : 1;
   a.mode = 1; a.passes = desc->passes; a.base = desc->base; a.univariate = desc->univariate;
   a.bound = desc->bound; a.slope = desc->slope;
   return flow_run(desc, a, dtype, gemm, stream);

@@ -90,6 +90,7 @@ struct FlowKernelArgs {
   uint8_t* inside;
   void* work;         // caller-provided scratch (mf_flow_workspace_bytes)
   long long work_bytes;
+  int ctx_group;      // x rows per context row (>= 1)
   int mode;           // 0 = log_prob / transform, 1 = sample
   int passes;
   int base;

@@ -679,6 +679,10 @@ int flow_tc_run(const mf_flow_desc& d, const FlowKernelArgs& a, const BaseParams
   int rc = make_tc_layout(d, gemm, &L);
   if (rc != MF_OK) return rc;
   MF_REQUIRE(a.z != nullptr, "tensor-core flow path needs the z / x output buffer (it is the working copy of x)");
+  if (a.ctx_group > 1) {
+    set_error("context grouping (ctx_group=%d) is implemented on the MF_GEMM_EXACT path only", a.ctx_group);
+    return MF_EUNSUPPORTED;
+  }
   if (a.mode == 1) {
     if (L.Kp > 32) {
       set_error("tensor-core sampling needs bins <= 32 (got %d); use MF_GEMM_EXACT", d.bins);

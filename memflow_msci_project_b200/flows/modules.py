@@ -37,7 +37,7 @@ class FlowDesc(ctypes.Structure):
         ("transforms", ctypes.c_int32), ("n_hidden", ctypes.c_int32),
         ("hidden", ctypes.c_int32 * MF_MAX_HIDDEN_LAYERS),
         ("passes", ctypes.c_int32), ("univariate", ctypes.c_int32), ("base", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("ctx_group", ctypes.c_int32),
         ("bound", ctypes.c_double), ("slope", ctypes.c_double),
         ("base_a", ctypes.c_double * MF_MAX_FEATURES), ("base_b", ctypes.c_double * MF_MAX_FEATURES),
     ]
@@ -186,9 +186,10 @@ class _Transform:
 class NormalizingFlow:
     """``flow(c)``: zuko.distributions.NormalizingFlow bound to a context (a14-a16)."""
 
-    def __init__(self, module, c):
+    def __init__(self, module, c, ctx_group=1):
         self._m = module
         self._c = c
+        self._ctx_group = int(ctx_group)
 
     # -- properties used by the reference
     @property
@@ -201,6 +202,13 @@ class NormalizingFlow:
         return d if self._c is None else d.expand(self._c.shape[:-1])
 
     # -- helpers
+    def _with_group(self, desc):
+        if self._ctx_group <= 1:
+            return desc
+        d = FlowDesc.from_buffer_copy(desc)
+        d.ctx_group = self._ctx_group
+        return d
+
     def _split(self):
         pre, core, post, seen = [], [], [], False
         for t in self._m.transforms:
@@ -223,6 +231,12 @@ class NormalizingFlow:
         c = self._c
         if c is None:
             return x.reshape(-1, D), None, x.shape[:-1]
+        if self._ctx_group > 1:
+            xb = x.reshape(-1, D)
+            cb = c.reshape(-1, c.shape[-1])
+            if cb.shape[0] * self._ctx_group != xb.shape[0]:
+                raise ValueError(f"ctx_group={self._ctx_group}: {cb.shape[0]} context rows do not cover {xb.shape[0]} x rows")
+            return xb, cb, x.shape[:-1]
         batch = torch.broadcast_shapes(x.shape[:-1], c.shape[:-1])
         xb = x.expand(*batch, D).reshape(-1, D)
         cb = c.expand(*batch, c.shape[-1]).reshape(-1, c.shape[-1])
@@ -247,7 +261,10 @@ class NormalizingFlow:
         cb = cb.to(dtype).contiguous() if cb is not None else None
         N, D = xb.shape
         gemm = m.effective_gemm(dtype)
+        if self._ctx_group > 1:
+            gemm = GEMM_EXACT  # context grouping lives on the CUDA-core path
         desc, blob = m.packed(xb.device, dtype, gemm=gemm)
+        desc = self._with_group(desc)
         z = torch.empty_like(xb)
         ladj = torch.empty(N, dtype=dtype, device=xb.device)
         need_lp = want_logprob and not post
@@ -287,7 +304,10 @@ class NormalizingFlow:
         zb = zb.contiguous()
         cb = cb.to(dtype).contiguous() if cb is not None else None
         gemm = m.effective_gemm(dtype, sampling=True)
+        if self._ctx_group > 1:
+            gemm = GEMM_EXACT
         desc, blob = m.packed(zb.device, dtype, identity_base=True, gemm=gemm)
+        desc = self._with_group(desc)
         x = torch.empty_like(zb)
         _cabi.flow_sample(desc, blob, zb, cb, x, gemm)
         x = x.reshape(*batch, m.features)
@@ -384,10 +404,12 @@ class MAF(nn.Module):
             if k.startswith(prefix + "transform.transforms."):
                 state_dict[prefix + k[len(prefix) + len("transform."):]] = state_dict.pop(k)
 
-    def forward(self, c=None):
+    def forward(self, c=None, ctx_group=1):
+        """``flow(c)``.  ``ctx_group=G`` (extension): ``c`` has one row per GROUP of G consecutive x rows -- the
+        per-event context of a MEM integration sweep is read in place instead of being repeated G times."""
         if c is not None and c.shape[-1] != self.context:
             raise ValueError(f"expected context with last dimension {self.context}, got {tuple(c.shape)}")
-        return NormalizingFlow(self, c)
+        return NormalizingFlow(self, c, ctx_group)
 
     # -- descriptors / packed weights ---------------------------------------------------------
     def core_transforms(self):

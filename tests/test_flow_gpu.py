@@ -423,3 +423,16 @@ def test_tc_3xf16_sample_parity(cuda, name, mode):
     flow.gemm = flows.modules.GEMM_EXACT
     xe = flow(c).sample_from_noise(noise)
     assert (xs - xe).abs().max().item() < 5e-3
+
+
+def test_context_group_equals_repeated_context(cuda):
+    """MEM-sweep hoist: one context row per event read in place == the same context repeated per point."""
+    flow = build("UF", cuda, torch.float32, mode="default")
+    E, G = 37, 50
+    g = torch.Generator().manual_seed(8)
+    x = (0.3 * torch.randn(E * G, 10, generator=g)).to(cuda)
+    c = torch.randn(E, 16, generator=g).to(cuda)
+    with torch.no_grad():
+        a = flow(c, ctx_group=G).log_prob(x)
+        b = flow(c.repeat_interleave(G, dim=0)).log_prob(x)
+    assert torch.equal(a, b)
