@@ -8,9 +8,14 @@
 //   warps 2-5     epilogue group of tile slot 0 (thread = object = TMEM lane)
 //   warps 6-9     epilogue group of tile slot 1
 // The two tile slots ping-pong: while the tensor core works on one tile's layer, the other tile's epilogue
-// (TMEM -> registers -> bias + ReLU -> operand conversion -> swizzled shared memory) runs on the CUDA cores.
-// Activations never leave the SM; the spline parameters of the last layer are consumed straight out of TMEM
-// by the thread that owns the object, so they never touch shared memory or HBM either.
+// (TMEM accumulator -> registers -> bias + ReLU -> fp16 hi/lo operand planes -> back into TMEM with tcgen05.st)
+// runs on the CUDA cores.  Hidden activations therefore never leave TMEM: layer l+1 takes its A operand straight
+// from TMEM (tcgen05.mma with a TMEM A operand), only the layer-0 operand (x | context) sits in shared memory,
+// where the context part is staged ONCE per tile and only the D columns of x are refreshed per transform.
+// The spline parameters of the last layer are consumed straight out of TMEM by the thread that owns the
+// object, so they never touch shared memory or HBM either.
+// TMEM map of tile slot t (256 columns): [0,128) fp32 accumulator, [128,192) hi plane, [192,256) lo plane
+// (64 columns = 128 packed 16-bit K elements).
 //
 // Numerics.  MF_GEMM_TC_3XF16: every fp32 operand value v is split into fp16 hi = rn(v), lo = rn(v - hi) and
 // each product is formed as hi*hi + hi*lo + lo*hi with fp32 accumulation: 22 significant bits, i.e. fp32-class
@@ -340,7 +345,7 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
   // [tile][part] activation operands, then the weight ring
   unsigned char* a_buf = smem;
   unsigned char* w_ring = smem + 2 * kParts * kABufBytes;
-  __shared__ __align__(8) uint64_t w_full[kStages], w_empty[kStages], a_ready[2], acc_full[2][2], acc_free[2][2];
+  __shared__ __align__(8) uint64_t w_full[kStages], w_empty[kStages], a_ready[2], acc_full[2], acc_free[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float sbias[2][2][128];  // [tile slot][job parity][column]
 
@@ -358,7 +363,8 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
     for (int s = 0; s < kStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&a_ready[t], 128);
-      for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[t][b], 1); mbar_init(&acc_free[t][b], 128); }
+      mbar_init(&acc_full[t], 1);
+      mbar_init(&acc_free[t], 128);
     }
     fence_mbar_init();
   }
@@ -406,10 +412,10 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
             const uint32_t idesc = tc::make_idesc_f16(NSPLIT == 3 ? 0 : 1, 128, j.N);
             for (int t = 0; t < ntile; ++t) {
               if (j.needs_a) { mbar_wait(&a_ready[t], aph[t]); aph[t] ^= 1; }
-              const uint32_t u = jobctr[t] >> 1, buf = jobctr[t] & 1;
-              if (u >= 1) mbar_wait(&acc_free[t][buf], (u - 1) & 1);
+              if (jobctr[t] >= 1) mbar_wait(&acc_free[t], (jobctr[t] - 1) & 1);  // accumulator drained
               tc::fence_after_thread_sync();
-              const uint32_t d_tmem = tmem + (uint32_t)(t * 256 + buf * 128);
+              const uint32_t d_tmem = tmem + (uint32_t)(t * 256);
+              const uint32_t a_tmem = d_tmem + 128;  // hi plane; lo plane 64 columns further
               const uint32_t a_base = smem_u32(a_buf + (size_t)t * kParts * kABufBytes);
               for (int kb = 0; kb < j.nkb; ++kb) {
                 const uint32_t s = (it + kb) % kStages, ph = ((it + kb) / kStages) & 1;
@@ -419,19 +425,28 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
                 const int ks_n = min(4, j.ksteps - kb * 4);
                 for (int ks = 0; ks < ks_n; ++ks) {
                   const uint32_t acc = (kb | ks) ? 1u : 0u;
-                  const uint64_t dah = tc::make_smem_desc(a_base + kb * (128u * 128u) + ks * 32u);
                   const uint64_t dbh = tc::make_smem_desc(w_base + ks * 32u);
-                  tc::mma_f16_ss(d_tmem, dah, dbh, idesc, acc);
-                  if (NSPLIT == 3) {
-                    const uint64_t dal = tc::make_smem_desc(a_base + kABufBytes + kb * (128u * 128u) + ks * 32u);
-                    const uint64_t dbl = tc::make_smem_desc(w_base + kWPartBytes + ks * 32u);
-                    tc::mma_f16_ss(d_tmem, dah, dbl, idesc, 1u);
-                    tc::mma_f16_ss(d_tmem, dal, dbh, idesc, 1u);
+                  const uint64_t dbl = tc::make_smem_desc(w_base + kWPartBytes + ks * 32u);
+                  if (ji == 0) {  // layer 0: (x | ctx) operand from shared memory
+                    const uint64_t dah = tc::make_smem_desc(a_base + kb * (128u * 128u) + ks * 32u);
+                    tc::mma_f16_ss(d_tmem, dah, dbh, idesc, acc);
+                    if (NSPLIT == 3) {
+                      const uint64_t dal = tc::make_smem_desc(a_base + kABufBytes + kb * (128u * 128u) + ks * 32u);
+                      tc::mma_f16_ss(d_tmem, dah, dbl, idesc, 1u);
+                      tc::mma_f16_ss(d_tmem, dal, dbh, idesc, 1u);
+                    }
+                  } else {        // hidden activations: operand planes in TMEM
+                    const uint32_t ah = a_tmem + (uint32_t)(kb * 4 + ks) * 8u;
+                    tc::mma_f16_ts(d_tmem, ah, dbh, idesc, acc);
+                    if (NSPLIT == 3) {
+                      tc::mma_f16_ts(d_tmem, ah, dbl, idesc, 1u);
+                      tc::mma_f16_ts(d_tmem, ah + 64u, dbh, idesc, 1u);
+                    }
                   }
                 }
                 if (t == ntile - 1) tc::mma_commit(&w_empty[s]);  // stage free once these MMAs retire
               }
-              tc::mma_commit(&acc_full[t][buf]);
+              tc::mma_commit(&acc_full[t]);
               jobctr[t]++;
             }
             it += j.nkb;
@@ -499,53 +514,55 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
         }
       float* gy = static_cast<float*>(args.work);  // sampling: target y of the transform being inverted
       float ladj = 0.f;
+      // ---- stage (ctx | 0) of the layer-0 operand once per tile; every MMA that read the previous tile's
+      //      operand has retired (this group waited on the last accumulator of that tile)
+      {
+        const int kfill = L.in0_ksteps * 16;
+        for (int k = D + C; k < kfill; ++k) put1(row, k, 0.f);
+        // context: coalesced over the flat [rows x C] range of this tile, eight loads in flight per thread
+        int r = 0, c = gt;
+        while (C > 0 && c >= C) { c -= C; ++r; }
+        const int dr = C > 0 ? 128 / C : 0, dc = C > 0 ? 128 % C : 0;
+        const float* gct = gc + tile0 * C;
+        const int total = 128 * C, valid_elems = rows * C;
+        for (int idx0 = gt; idx0 < total; idx0 += 8 * 128) {
+          float v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int idx = idx0 + u * 128;
+            v[u] = (idx < valid_elems) ? __ldg(gct + idx) : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            if (idx0 + u * 128 < total) {
+              put1(r, D + c, v[u]);
+              r += dr; c += dc;
+              if (c >= C) { c -= C; ++r; }
+            }
+          }
+        }
+      }
       for (int unit = 0; unit < n_units; ++unit) {
         const int tr = inverse ? (L.T - 1 - unit / sweeps) : unit;
         if (inverse && (unit % sweeps) == 0 && valid) {  // y <- x, x <- 0  (AutoregressiveTransform._inverse)
           for (int f = 0; f < D; ++f) { gy[g * D + f] = gz[g * D + f]; gz[g * D + f] = 0.f; }
         }
         const float* bias_t = bias_all + (size_t)tr * L.bias_stride;
-        // ---- stage (x | ctx | 0) as the layer-0 operand
-        {
-          const int kfill = L.in0_ksteps * 16;
-          for (int f = 0; f < D; ++f) put1(row, f, valid ? gz[g * D + f] : 0.f);
-          for (int k = D + C; k < kfill; ++k) put1(row, k, 0.f);
-          // context: coalesced over the flat [rows x C] range of this tile, eight loads in flight per thread
-          int r = 0, c = gt;
-          while (C > 0 && c >= C) { c -= C; ++r; }
-          const int dr = C > 0 ? 128 / C : 0, dc = C > 0 ? 128 % C : 0;
-          const float* gct = gc + tile0 * C;
-          const int total = 128 * C, valid_elems = rows * C;
-          for (int idx0 = gt; idx0 < total; idx0 += 8 * 128) {
-            float v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const int idx = idx0 + u * 128;
-              v[u] = (idx < valid_elems) ? __ldg(gct + idx) : 0.f;
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              if (idx0 + u * 128 < total) {
-                put1(r, D + c, v[u]);
-                r += dr; c += dc;
-                if (c >= C) { c -= C; ++r; }
-              }
-            }
-          }
-          fence_proxy_async_smem();
-          mbar_arrive(&a_ready[t]);
-        }
+        // ---- layer-0 operand: refresh the D columns of x (the context part was staged at the tile start)
+        for (int f = 0; f < D; ++f) put1(row, f, valid ? gz[g * D + f] : 0.f);
+        fence_proxy_async_smem();
+        mbar_arrive(&a_ready[t]);
         for (int ji = 0; ji < L.njobs; ++ji) {
           const TcJob& j = L.job[ji];
-          const uint32_t u = jobctr >> 1, buf = jobctr & 1;
+          const uint32_t jpar = jobctr & 1;
           ++jobctr;
           // this job's biases -> shared memory (double-buffered by job parity), overlapping the MMA
-          float* sb = sbias[t][buf];
+          float* sb = sbias[t][jpar];
           if (gt < j.N) sb[gt] = __ldg(bias_t + j.b_off + gt);
           group_bar(1 + t);
-          mbar_wait(&acc_full[t][buf], u & 1);
+          mbar_wait(&acc_full[t], jpar);
           tc::fence_after_thread_sync();
-          const uint32_t taddr = tmem + lane_off + (uint32_t)(t * 256 + buf * 128);
+          const uint32_t taddr = tmem + lane_off + (uint32_t)(t * 256);
           if (!j.last) {
             // hidden layer: TMEM -> +bias -> ReLU -> operand planes of the next layer (in place)
             for (int c00 = 0; c00 < j.N; c00 += 32) {
@@ -564,28 +581,25 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
                     v[i] = fmaxf(v[i] + b4.x, 0.f); v[i + 1] = fmaxf(v[i + 1] + b4.y, 0.f);
                     v[i + 2] = fmaxf(v[i + 2] + b4.z, 0.f); v[i + 3] = fmaxf(v[i + 3] + b4.w, 0.f);
                   }
+                  // 16 values -> 8 packed 16-bit pairs per plane -> operand planes in TMEM
+                  if (NSPLIT == 3) {
+                    uint32_t hi[8], lo[8];
 #pragma unroll
-                  for (int h8 = 0; h8 < 2; ++h8) {  // two 16-byte chunks of 8 columns
-                    const uint32_t off = tc::sw128_offset(row, c0 + h8 * 8, 128);
-                    if (NSPLIT == 3) {
-                      uint32_t hi[4], lo[4];
+                    for (int i = 0; i < 8; ++i) tc::split_f16(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+                    tc::tmem_st8(taddr + 128 + c0 / 2, hi);
+                    tc::tmem_st8(taddr + 192 + c0 / 2, lo);
+                  } else {
+                    uint32_t pk[8];
 #pragma unroll
-                      for (int i = 0; i < 4; ++i) tc::split_f16(v[h8 * 8 + 2 * i], v[h8 * 8 + 2 * i + 1], hi[i], lo[i]);
-                      *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                      *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                    } else {
-                      uint32_t pk[4];
-#pragma unroll
-                      for (int i = 0; i < 4; ++i) pk[i] = tc::pack_bf16(v[h8 * 8 + 2 * i], v[h8 * 8 + 2 * i + 1]);
-                      *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                    }
+                    for (int i = 0; i < 8; ++i) pk[i] = tc::pack_bf16(v[2 * i], v[2 * i + 1]);
+                    tc::tmem_st8(taddr + 128 + c0 / 2, pk);
                   }
                 }
               }
             }
+            tc::tmem_st_wait();
             tc::fence_before_thread_sync();
-            mbar_arrive(&acc_free[t][buf]);
-            fence_proxy_async_smem();
+            mbar_arrive(&acc_free[t]);
             mbar_arrive(&a_ready[t]);
           } else {
             // last-layer chunk: splines of the chunk's features straight out of TMEM
@@ -612,7 +626,7 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
               }
             }
             tc::fence_before_thread_sync();
-            mbar_arrive(&acc_free[t][buf]);
+            mbar_arrive(&acc_free[t]);
           }
         }
       }

@@ -3,6 +3,7 @@
 // TMEM read-back) in isolation:  out[128, N] = A[128, K] * W[N, K]^T  with fp32 inputs.
 //   mode 0: fp16 hi/lo split of both operands, 3 MMAs per k-step (hi*hi + hi*lo + lo*hi)
 //   mode 1: bf16 single MMA        mode 2: fp16 single MMA
+//   mode 3: fp16 hi/lo split with the A operand staged in TMEM (tcgen05.st) instead of shared memory
 #include "tc_common.cuh"
 
 namespace mf {
@@ -39,7 +40,7 @@ tc_probe_kernel(const float* __restrict__ A, const float* __restrict__ W, float*
   for (int i = tid; i < 128 * K; i += 128) put(a_hi, a_lo, 128, i / K, i % K, A[i]);
   for (int i = tid; i < N * K; i += 128) put(b_hi, b_lo, N, i / K, i % K, W[i]);
 
-  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 256);
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
     mbar_init(&bar, 1);
     fence_mbar_init();
@@ -50,7 +51,35 @@ tc_probe_kernel(const float* __restrict__ A, const float* __restrict__ W, float*
   tc::fence_after_thread_sync();
   const uint32_t tmem = tmem_base_s;
 
-  if (tid == 0) {
+  if (mode == 3) {
+    // A planes into TMEM: hi at columns [256, 256 + K/2), lo at [384, 384 + K/2); thread = row
+    const int row = warp * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    for (int k0 = 0; k0 < K; k0 += 16) {
+      uint32_t hi[8], lo[8];
+      for (int j = 0; j < 8; ++j) tc::split_f16(A[(size_t)row * K + k0 + 2 * j], A[(size_t)row * K + k0 + 2 * j + 1], hi[j], lo[j]);
+      tc::tmem_st8(tmem + lane_off + 256 + k0 / 2, hi);
+      tc::tmem_st8(tmem + lane_off + 384 + k0 / 2, lo);
+    }
+    tc::tmem_st_wait();
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    tc::fence_after_thread_sync();
+  }
+  if (tid == 0 && mode == 3) {
+    const uint32_t idesc = tc::make_idesc_f16(0, 128, N);
+    const int ksteps = K / 16;
+    for (int ks = 0; ks < ksteps; ++ks) {
+      const uint32_t kb = ks >> 2, kin = (ks & 3) * 32;
+      const uint64_t dbh = tc::make_smem_desc(smem_u32(b_hi) + kb * (uint32_t)N * 128u + kin);
+      const uint64_t dbl = tc::make_smem_desc(smem_u32(b_lo) + kb * (uint32_t)N * 128u + kin);
+      tc::mma_f16_ts(tmem, tmem + 256 + ks * 8, dbh, idesc, ks ? 1u : 0u);
+      tc::mma_f16_ts(tmem, tmem + 256 + ks * 8, dbl, idesc, 1u);
+      tc::mma_f16_ts(tmem, tmem + 384 + ks * 8, dbh, idesc, 1u);
+    }
+    tc::mma_commit(&bar);
+  }
+  if (tid == 0 && mode != 3) {
     const uint32_t idesc = tc::make_idesc_f16(mode == 1 ? 1 : 0, 128, N);
     const int ksteps = (K + 15) / 16;
     uint32_t acc = 0;
@@ -81,7 +110,7 @@ tc_probe_kernel(const float* __restrict__ A, const float* __restrict__ W, float*
   }
   tc::fence_before_thread_sync();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem, 256);
+  if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
 }  // namespace
@@ -94,7 +123,7 @@ extern "C" int mf_tc_probe_gemm(const float* d_a, const float* d_w, float* d_out
   MF_REQUIRE(d_a && d_w && d_out, "mf_tc_probe_gemm: null argument");
   MF_REQUIRE(k >= 16 && k % 16 == 0 && k <= 256, "mf_tc_probe_gemm: K=%d must be a multiple of 16 in 16..256", k);
   MF_REQUIRE(n >= 16 && n % 16 == 0 && n <= 256, "mf_tc_probe_gemm: N=%d must be a multiple of 16 in 16..256", n);
-  MF_REQUIRE(mode >= 0 && mode <= 2, "mf_tc_probe_gemm: bad mode");
+  MF_REQUIRE(mode >= 0 && mode <= 3, "mf_tc_probe_gemm: bad mode");
   const int kp = (k + 63) / 64 * 64;
   const size_t smem = (size_t)2 * 128 * kp * 2 + (size_t)2 * n * kp * 2 + 1024;
   MF_REQUIRE(smem <= 227 * 1024, "mf_tc_probe_gemm: operands do not fit shared memory");
