@@ -511,7 +511,10 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
             v0 = (args.base == MF_BASE_DIAG_NORMAL) ? (float)bp.a[f] + (float)bp.b[f] * v0
                                                    : (float)bp.a[f] + ((float)bp.b[f] - (float)bp.a[f]) * v0;
           gz[g * D + f] = v0;
+          put1(row, f, v0);  // x columns of the layer-0 operand
         }
+      if (!valid)
+        for (int f = 0; f < D; ++f) put1(row, f, 0.f);
       float* gy = static_cast<float*>(args.work);  // sampling: target y of the transform being inverted
       float ladj = 0.f;
       // ---- stage (ctx | 0) of the layer-0 operand once per tile; every MMA that read the previous tile's
@@ -544,12 +547,15 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
       }
       for (int unit = 0; unit < n_units; ++unit) {
         const int tr = inverse ? (L.T - 1 - unit / sweeps) : unit;
-        if (inverse && (unit % sweeps) == 0 && valid) {  // y <- x, x <- 0  (AutoregressiveTransform._inverse)
-          for (int f = 0; f < D; ++f) { gy[g * D + f] = gz[g * D + f]; gz[g * D + f] = 0.f; }
+        if (inverse && (unit % sweeps) == 0) {  // y <- x, x <- 0  (AutoregressiveTransform._inverse)
+          for (int f = 0; f < D; ++f) {
+            if (valid) { gy[g * D + f] = gz[g * D + f]; gz[g * D + f] = 0.f; }
+            put1(row, f, 0.f);
+          }
         }
         const float* bias_t = bias_all + (size_t)tr * L.bias_stride;
-        // ---- layer-0 operand: refresh the D columns of x (the context part was staged at the tile start)
-        for (int f = 0; f < D; ++f) put1(row, f, valid ? gz[g * D + f] : 0.f);
+        // ---- layer-0 operand: the context part was staged at the tile start, the D columns of x were written
+        //      by this thread when it produced them (tile start / spline output of the previous unit)
         fence_proxy_async_smem();
         mbar_arrive(&a_ready[t]);
         for (int ji = 0; ji < L.njobs; ++ji) {
@@ -559,6 +565,11 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
           // this job's biases -> shared memory (double-buffered by job parity), overlapping the MMA
           float* sb = sbias[t][jpar];
           if (gt < j.N) sb[gt] = __ldg(bias_t + j.b_off + gt);
+          // inputs of this chunk's splines, fetched before the accumulator wait (at most 5 features per chunk)
+          float xin[5];
+#pragma unroll
+          for (int fl = 0; fl < 5; ++fl)
+            xin[fl] = (j.last && fl < j.nfeat && valid) ? (inverse ? gy[g * D + j.feat0 + fl] : gz[g * D + j.feat0 + fl]) : 0.f;
           group_bar(1 + t);
           mbar_wait(&acc_full[t], jpar);
           tc::fence_after_thread_sync();
@@ -603,9 +614,11 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
             mbar_arrive(&a_ready[t]);
           } else {
             // last-layer chunk: splines of the chunk's features straight out of TMEM
-            for (int fl = 0; fl < j.nfeat; ++fl) {
+#pragma unroll
+            for (int fl = 0; fl < 5; ++fl) {
+              if (fl >= j.nfeat) break;
               const int f = j.feat0 + fl;
-              const float xv = valid ? (inverse ? gy[g * D + f] : gz[g * D + f]) : 0.f;
+              const float xv = xin[fl];
               float out, la;
               int bin;
               bool ins;
@@ -618,6 +631,7 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
                 case 32: rqs_forward_tmem_reg<4>(ta, sbf, cfg, inverse, xv, out, la, bin, ins); break;
                 default: rqs_forward_tmem(ta, sbf, cfg, L.Kp, xv, out, la, bin, ins); break;
               }
+              put1(row, f, valid ? out : 0.f);  // next unit's layer-0 operand (its last reader, job 0, has retired)
               if (valid) {
                 gz[g * D + f] = out;
                 ladj += la;
