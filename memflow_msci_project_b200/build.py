@@ -26,6 +26,8 @@ FLAGS = [
 # rambo.cu: --use_fast_math only changes FLOAT arithmetic (approximate division / sqrt / transcendentals),
 # i.e. the fp32 throughput mode; the fp64 parity mode is unaffected.
 EXTRA_FLAGS = {"rambo.cu": ["--use_fast_math"]}
+if os.environ.get("MF_TC_TRACE") == "1":  # cycle-level trace of the tensor-core flow kernel (tools/trace_tc.py)
+    EXTRA_FLAGS["flow_tc.cu"] = ["-DMF_TC_TRACE"]
 
 
 def _stale(target, deps):

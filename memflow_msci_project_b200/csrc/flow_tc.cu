@@ -1,12 +1,13 @@
 // flow_tc.cu -- fused conditional RQ-spline MAF log_prob with the conditioner GEMMs on tcgen05.
 //
-// One persistent CTA per SM works on PAIRS of 128-object tiles.  Warp roles (320 threads):
+// One persistent CTA per SM works on PAIRS of 128-object tiles.  Warp roles (352 threads):
 //   warp 0        weight loader: streams the packed, pre-swizzled weight K-blocks from L2 into a 3-stage
 //                 shared-memory ring with 1-D bulk async copies (TMA engine) completing on mbarriers
-//   warp 1        MMA issuer: one elected thread issues tcgen05.mma (M=128, N<=128, K=16, fp32 accumulate in
-//                 TMEM) for tile 0 and tile 1 back to back on the same weight stage, then tcgen05.commit
-//   warps 2-5     epilogue group of tile slot 0 (thread = object = TMEM lane)
-//   warps 6-9     epilogue group of tile slot 1
+//   warps 1, 2    MMA issuers of tile slot 0 / 1: one elected lane issues tcgen05.mma (M=128, N<=128, K=16,
+//                 fp32 accumulate in TMEM) and tcgen05.commit; both consume every weight stage (measured: one
+//                 issuer sustains ~1 MMA per 105 cycles, the tensor core needs 64 -> two issuers)
+//   warps 3-6     epilogue group of tile slot 0 (thread = object = TMEM lane)
+//   warps 7-10    epilogue group of tile slot 1
 // The two tile slots ping-pong: while the tensor core works on one tile's layer, the other tile's epilogue
 // (TMEM accumulator -> registers -> bias + ReLU -> fp16 hi/lo operand planes -> back into TMEM with tcgen05.st)
 // runs on the CUDA cores.  Hidden activations therefore never leave TMEM: layer l+1 takes its A operand straight
@@ -32,8 +33,23 @@
 namespace mf {
 namespace {
 
-constexpr int kTcThreads = 320;
-constexpr int kStages = 3;
+// Optional cycle-level trace of CTA 0 / first tile pair (build with -DMF_TC_TRACE): events are written as
+// (clock64, id) pairs into the `inside` debug buffer.  ids: 100+ji MMA sees a_ready, 200+ji MMA issued,
+// 300+ji epilogue sees acc_full, 400+ji epilogue done (tile slot 0 only).
+#ifdef MF_TC_TRACE
+#define MF_TRACE(cond, id)                                                          \
+  do {                                                                              \
+    if ((cond) && blockIdx.x == 0 && trace_n < 4000) {                              \
+      long long* tb_ = reinterpret_cast<long long*>(args.inside);                   \
+      tb_[2 * trace_n] = clock64(); tb_[2 * trace_n + 1] = (id); ++trace_n;         \
+    }                                                                               \
+  } while (0)
+#else
+#define MF_TRACE(cond, id) do { } while (0)
+#endif
+
+// weight ring depth: the 3xFP16 mode has room for 3 stages of 32 KB next to the operand buffers, bf16 for 8 of 16 KB
+__host__ __device__ constexpr int ring_stages(int nsplit) { return nsplit == 3 ? 3 : 8; }
 constexpr int kMaxJobs = 40;
 constexpr uint32_t kABufBytes = 128 * 128 * 2;  // one [128 x 128] 16-bit operand (two K-blocks)
 constexpr uint32_t kWPartBytes = 128 * 128;     // one [<=128 rows x 64] 16-bit weight K-block
@@ -190,7 +206,9 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void group_bar(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 // Spline of one feature with its 3K-1 unconstrained parameters in TMEM (this thread's lane):
 // columns [0,K) widths, [Kp,Kp+K) heights, [2Kp, 2Kp+K-1) derivatives.  Forward transform + log-det.
@@ -316,27 +334,46 @@ __device__ __forceinline__ void rqs_forward_tmem_reg(uint32_t taddr, const float
                                                      bool inverse, float v, float& out, float& ladj, int& bin,
                                                      bool& inside) {
   constexpr int KP = 8 * NCH;
-  uint32_t rw[KP], rh[KP], rd[KP];
+  float lw[KP], lh[KP];
+  {
+    uint32_t rw[KP], rh[KP];
 #pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    tmem_ld8_raw(taddr + c * 8, rw + c * 8);
-    tmem_ld8_raw(taddr + KP + c * 8, rh + c * 8);
-    tmem_ld8_raw(taddr + 2 * KP + c * 8, rd + c * 8);
-  }
-  tc::tmem_ld_wait();
-  float lw[KP], lh[KP], ld[KP];
+    for (int c = 0; c < NCH; ++c) {
+      tmem_ld8_raw(taddr + c * 8, rw + c * 8);
+      tmem_ld8_raw(taddr + KP + c * 8, rh + c * 8);
+    }
+    tc::tmem_ld_wait();
 #pragma unroll
-  for (int j = 0; j < KP; ++j) {  // accumulator + bias
-    lw[j] = __uint_as_float(rw[j]) + sb[j];
-    lh[j] = __uint_as_float(rh[j]) + sb[KP + j];
-    ld[j] = __uint_as_float(rd[j]) + sb[2 * KP + j];
+    for (int j = 0; j < KP; ++j) {  // accumulator + bias
+      lw[j] = __uint_as_float(rw[j]) + sb[j];
+      lh[j] = __uint_as_float(rh[j]) + sb[KP + j];
+    }
   }
-  rqs_eval_reg<NCH>(lw, lh, ld, cfg, inverse, v, out, ladj, bin, inside);
+  int k;
+  float x0, x1, y0, y1, ladj0, t0, t1;
+  rqs_scan_reg<NCH>(lw, lh, cfg, inverse, v, k, inside, x0, x1, y0, y1, ladj0);
+  {  // derivative logits are fetched only now (short register live ranges); the load is warp-uniform
+    uint32_t rd[KP];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) tmem_ld8_raw(taddr + 2 * KP + c * 8, rd + c * 8);
+    tc::tmem_ld_wait();
+    t0 = 0.f; t1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < KP; ++j) {
+      const float dj = __uint_as_float(rd[j]) + sb[2 * KP + j];
+      t0 = (j == k - 1) ? dj : t0;
+      t1 = (j == k) ? dj : t1;
+    }
+  }
+  bin = k;
+  rqs_finish(cfg, inverse, v, k, inside, x0, x1, y0, y1, t0, t1, ladj0, out, ladj);
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int NSPLIT>
-__global__ void __launch_bounds__(kTcThreads, 1)
+// EW = epilogue warp sets per tile slot: with EW = 2 two warps share every TMEM lane quarter and split the
+// columns of a hidden layer / the features of a spline chunk between them (16 epilogue warps per CTA).
+template <int NSPLIT, int EW>
+__global__ void __launch_bounds__((3 + 8 * EW) * 32, 1)
 flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowKernelArgs args,
                const __grid_constant__ BaseParams bp) {
   constexpr int kParts = (NSPLIT == 3) ? 2 : 1;           // operand planes (hi, lo)
@@ -345,6 +382,7 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
   // [tile][part] activation operands, then the weight ring
   unsigned char* a_buf = smem;
   unsigned char* w_ring = smem + 2 * kParts * kABufBytes;
+  constexpr int kStages = ring_stages(NSPLIT);
   __shared__ __align__(8) uint64_t w_full[kStages], w_empty[kStages], a_ready[2], acc_full[2], acc_free[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float sbias[2][2][128];  // [tile slot][job parity][column]
@@ -360,11 +398,11 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
   const float* bias_all = reinterpret_cast<const float*>(blob + L.bias_off);
 
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 2); }  // two MMA issuers release a stage
     for (int t = 0; t < 2; ++t) {
-      mbar_init(&a_ready[t], 128);
+      mbar_init(&a_ready[t], 128 * EW);
       mbar_init(&acc_full[t], 1);
-      mbar_init(&acc_free[t], 128);
+      mbar_init(&acc_free[t], 128 * EW);
     }
     fence_mbar_init();
   }
@@ -398,28 +436,36 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      uint32_t it = 0;             // weight stages consumed so far
-      uint32_t jobctr[2] = {0, 0};  // accumulator uses per tile slot
-      uint32_t aph[2] = {0, 0};     // a_ready phases
+  } else if (warp == 1 || warp == 2) {
+    // ===================== MMA issuers: one warp per tile slot =====================
+    // The whole warp walks the (warp-uniform) schedule and waits on the barriers; one elected lane issues the
+    // tcgen05 instructions.  Keeping the warp converged lets the compiler hold descriptors in uniform registers.
+    // Both issuers consume every weight stage; a stage is released once both have committed it.
+    {
+      const int t = warp - 1;
+      uint32_t it = 0;      // weight stages consumed so far
+      int trace_n = 1000 * t; (void)trace_n;
+      uint32_t jobctr = 0;  // accumulator uses of this tile slot
+      uint32_t aph = 0;     // a_ready phase
+      const uint32_t d_tmem = tmem + (uint32_t)(t * 256);
+      const uint32_t a_tmem = d_tmem + 128;  // hi plane; lo plane 64 columns further
+      const uint32_t a_base = smem_u32(a_buf + (size_t)t * kParts * kABufBytes);
       for (long long p = blockIdx.x; p < n_pairs; p += gridDim.x) {
-        const int ntile = (2 * p + 1 < n_tiles) ? 2 : 1;
+        const bool active = (2 * p + t) < n_tiles;  // odd tile count: slot 1 only releases the stages in the last pair
         for (int unit = 0; unit < n_units; ++unit) {
           for (int ji = 0; ji < L.njobs; ++ji) {
             const TcJob& j = L.job[ji];
             const uint32_t idesc = tc::make_idesc_f16(NSPLIT == 3 ? 0 : 1, 128, j.N);
-            for (int t = 0; t < ntile; ++t) {
-              if (j.needs_a) { mbar_wait(&a_ready[t], aph[t]); aph[t] ^= 1; }
-              if (jobctr[t] >= 1) mbar_wait(&acc_free[t], (jobctr[t] - 1) & 1);  // accumulator drained
+            if (active) {
+              if (j.needs_a) { mbar_wait(&a_ready[t], aph); aph ^= 1; }
+              if (jobctr >= 1) mbar_wait(&acc_free[t], (jobctr - 1) & 1);  // accumulator drained
+              MF_TRACE(lane == 0 && p == blockIdx.x && unit < 2, 100 + 10 * t + ji);
               tc::fence_after_thread_sync();
-              const uint32_t d_tmem = tmem + (uint32_t)(t * 256);
-              const uint32_t a_tmem = d_tmem + 128;  // hi plane; lo plane 64 columns further
-              const uint32_t a_base = smem_u32(a_buf + (size_t)t * kParts * kABufBytes);
-              for (int kb = 0; kb < j.nkb; ++kb) {
-                const uint32_t s = (it + kb) % kStages, ph = ((it + kb) / kStages) & 1;
-                mbar_wait(&w_full[s], ph);
+            }
+            for (int kb = 0; kb < j.nkb; ++kb, ++it) {
+              const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+              mbar_wait(&w_full[s], ph);
+              if (active) {
                 tc::fence_after_thread_sync();
                 const uint32_t w_base = smem_u32(w_ring + s * kStageBytes);
                 const int ks_n = min(4, j.ksteps - kb * 4);
@@ -429,37 +475,50 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
                   const uint64_t dbl = tc::make_smem_desc(w_base + kWPartBytes + ks * 32u);
                   if (ji == 0) {  // layer 0: (x | ctx) operand from shared memory
                     const uint64_t dah = tc::make_smem_desc(a_base + kb * (128u * 128u) + ks * 32u);
-                    tc::mma_f16_ss(d_tmem, dah, dbh, idesc, acc);
-                    if (NSPLIT == 3) {
-                      const uint64_t dal = tc::make_smem_desc(a_base + kABufBytes + kb * (128u * 128u) + ks * 32u);
-                      tc::mma_f16_ss(d_tmem, dah, dbl, idesc, 1u);
-                      tc::mma_f16_ss(d_tmem, dal, dbh, idesc, 1u);
+                    const uint64_t dal = tc::make_smem_desc(a_base + kABufBytes + kb * (128u * 128u) + ks * 32u);
+                    if (tc::elect_one()) {
+                      tc::mma_f16_ss(d_tmem, dah, dbh, idesc, acc);
+                      if (NSPLIT == 3) {
+                        tc::mma_f16_ss(d_tmem, dah, dbl, idesc, 1u);
+                        tc::mma_f16_ss(d_tmem, dal, dbh, idesc, 1u);
+                      }
                     }
                   } else {        // hidden activations: operand planes in TMEM
                     const uint32_t ah = a_tmem + (uint32_t)(kb * 4 + ks) * 8u;
-                    tc::mma_f16_ts(d_tmem, ah, dbh, idesc, acc);
-                    if (NSPLIT == 3) {
-                      tc::mma_f16_ts(d_tmem, ah, dbl, idesc, 1u);
-                      tc::mma_f16_ts(d_tmem, ah + 64u, dbh, idesc, 1u);
+                    if (tc::elect_one()) {
+                      tc::mma_f16_ts(d_tmem, ah, dbh, idesc, acc);
+                      if (NSPLIT == 3) {
+                        tc::mma_f16_ts(d_tmem, ah, dbl, idesc, 1u);
+                        tc::mma_f16_ts(d_tmem, ah + 64u, dbh, idesc, 1u);
+                      }
                     }
                   }
+                  __syncwarp();
                 }
-                if (t == ntile - 1) tc::mma_commit(&w_empty[s]);  // stage free once these MMAs retire
+                if (tc::elect_one()) tc::mma_commit(&w_empty[s]);  // this issuer is done with the stage
+              } else {
+                if (tc::elect_one()) mbar_arrive(&w_empty[s]);
               }
-              tc::mma_commit(&acc_full[t]);
-              jobctr[t]++;
+              __syncwarp();
             }
-            it += j.nkb;
+            if (active) {
+              if (tc::elect_one()) tc::mma_commit(&acc_full[t]);
+              __syncwarp();
+              MF_TRACE(lane == 0 && p == blockIdx.x && unit < 2, 200 + 10 * t + ji);
+              jobctr++;
+            }
           }
         }
       }
     }
   } else {
     // ===================== epilogue groups =====================
-    const int t = (warp - 2) >> 2;            // tile slot
-    const int q = warp & 3;                   // TMEM lane quarter this warp may access
+    const int eset = (warp - 3) >> 3;         // warp set inside the tile's epilogue group (0 .. EW-1)
+    const int t = ((warp - 3) & 7) >> 2;      // tile slot
+    const int q = warp & 3;                   // TMEM lane quarter this warp may access (4 consecutive warps cover all)
     const int row = q * 32 + lane;            // object inside the tile
-    const int gt = ((warp - 2) & 3) * 32 + lane;  // thread index inside the group (for cooperative loops)
+    const int gt = eset * 128 + ((warp - 3) & 3) * 32 + lane;  // thread index inside the group (cooperative loops)
+    constexpr int GT = 128 * EW;              // threads per epilogue group
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     unsigned char* a_hi = a_buf + (size_t)t * kParts * kABufBytes;
     unsigned char* a_lo = a_hi + kABufBytes;
@@ -472,6 +531,7 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
     cfg.inv_ls2 = args.slope > 0.0 ? (float)(2.0 / log(args.slope)) : 0.f;
     cfg.inv_ls1 = args.slope > 0.0 ? (float)(1.0 / log(args.slope)) : 0.f;
     uint32_t jobctr = 0;
+    int trace_n = 2000; (void)trace_n;
 
     auto put2 = [&](int r, int k, float v0, float v1) {  // two consecutive columns k, k+1 (k even)
       const uint32_t off = tc::sw128_offset(r, k, 128);
@@ -504,7 +564,7 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
       const long long g = tile0 + row;
       // working copy of x lives in the output buffer (each thread touches only its own row); when sampling,
       // gx holds the noise and the base sample a + b * noise is the starting point
-      if (valid)
+      if (valid && eset == 0)
         for (int f = 0; f < D; ++f) {
           float v0 = gx[g * D + f];
           if (inverse)
@@ -513,7 +573,7 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
           gz[g * D + f] = v0;
           put1(row, f, v0);  // x columns of the layer-0 operand
         }
-      if (!valid)
+      if (!valid && eset == 0)
         for (int f = 0; f < D; ++f) put1(row, f, 0.f);
       float* gy = static_cast<float*>(args.work);  // sampling: target y of the transform being inverted
       float ladj = 0.f;
@@ -521,23 +581,24 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
       //      operand has retired (this group waited on the last accumulator of that tile)
       {
         const int kfill = L.in0_ksteps * 16;
-        for (int k = D + C; k < kfill; ++k) put1(row, k, 0.f);
+        if (eset == 0)
+          for (int k = D + C; k < kfill; ++k) put1(row, k, 0.f);
         // context: coalesced over the flat [rows x C] range of this tile, eight loads in flight per thread
         int r = 0, c = gt;
         while (C > 0 && c >= C) { c -= C; ++r; }
-        const int dr = C > 0 ? 128 / C : 0, dc = C > 0 ? 128 % C : 0;
+        const int dr = C > 0 ? GT / C : 0, dc = C > 0 ? GT % C : 0;
         const float* gct = gc + tile0 * C;
         const int total = 128 * C, valid_elems = rows * C;
-        for (int idx0 = gt; idx0 < total; idx0 += 8 * 128) {
+        for (int idx0 = gt; idx0 < total; idx0 += 8 * GT) {
           float v[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            const int idx = idx0 + u * 128;
+            const int idx = idx0 + u * GT;
             v[u] = (idx < valid_elems) ? __ldg(gct + idx) : 0.f;
           }
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            if (idx0 + u * 128 < total) {
+            if (idx0 + u * GT < total) {
               put1(r, D + c, v[u]);
               r += dr; c += dc;
               if (c >= C) { c -= C; ++r; }
@@ -545,9 +606,15 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
           }
         }
       }
+      if (EW > 1) group_bar(1 + t, GT);  // x written by warp set 0 is read by the other set below
+      float bias_next;
+      {
+        const int tr0 = inverse ? (L.T - 1) : 0;
+        bias_next = (gt < L.job[0].N) ? __ldg(bias_all + (size_t)tr0 * L.bias_stride + L.job[0].b_off + gt) : 0.f;
+      }
       for (int unit = 0; unit < n_units; ++unit) {
         const int tr = inverse ? (L.T - 1 - unit / sweeps) : unit;
-        if (inverse && (unit % sweeps) == 0) {  // y <- x, x <- 0  (AutoregressiveTransform._inverse)
+        if (inverse && (unit % sweeps) == 0 && eset == 0) {  // y <- x, x <- 0  (AutoregressiveTransform._inverse)
           for (int f = 0; f < D; ++f) {
             if (valid) { gy[g * D + f] = gz[g * D + f]; gz[g * D + f] = 0.f; }
             put1(row, f, 0.f);
@@ -564,27 +631,41 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
           ++jobctr;
           // this job's biases -> shared memory (double-buffered by job parity), overlapping the MMA
           float* sb = sbias[t][jpar];
-          if (gt < j.N) sb[gt] = __ldg(bias_t + j.b_off + gt);
+          if (gt < j.N) sb[gt] = bias_next;  // fetched one job ahead (global latency off the critical path)
+          {
+            int ju = unit, jn = ji + 1;
+            if (jn == L.njobs) { jn = 0; ++ju; }
+            if (ju < n_units) {
+              const int trn = inverse ? (L.T - 1 - ju / sweeps) : ju;
+              const TcJob& nj = L.job[jn];
+              bias_next = (gt < nj.N) ? __ldg(bias_all + (size_t)trn * L.bias_stride + nj.b_off + gt) : 0.f;
+            }
+          }
+          group_bar(1 + t, GT);
           // inputs of this chunk's splines, fetched before the accumulator wait (at most 5 features per chunk)
           float xin[5];
 #pragma unroll
           for (int fl = 0; fl < 5; ++fl)
-            xin[fl] = (j.last && fl < j.nfeat && valid) ? (inverse ? gy[g * D + j.feat0 + fl] : gz[g * D + j.feat0 + fl]) : 0.f;
-          group_bar(1 + t);
+            xin[fl] = (j.last && fl < j.nfeat && (fl % EW) == eset && valid)
+                          ? (inverse ? gy[g * D + j.feat0 + fl] : gz[g * D + j.feat0 + fl]) : 0.f;
+          MF_TRACE(gt == 0 && t == 0 && p == blockIdx.x && unit < 2, 500 + ji);
           mbar_wait(&acc_full[t], jpar);
+          MF_TRACE(gt == 0 && t == 0 && p == blockIdx.x && unit < 2, 300 + ji);
           tc::fence_after_thread_sync();
           const uint32_t taddr = tmem + lane_off + (uint32_t)(t * 256);
           if (!j.last) {
             // hidden layer: TMEM -> +bias -> ReLU -> operand planes of the next layer (in place)
-            for (int c00 = 0; c00 < j.N; c00 += 32) {
+            const int csplit = (EW == 1) ? j.N : min(j.N, ((j.N / 2 + 31) / 32) * 32);
+            const int cbeg = eset == 0 ? 0 : csplit, cend = eset == 0 ? csplit : j.N;
+            for (int c00 = cbeg; c00 < cend; c00 += 32) {
               float vv[32];
               tc::tmem_ld16(taddr + c00, vv);
-              if (c00 + 16 < j.N) tc::tmem_ld16(taddr + c00 + 16, vv + 16);
+              if (c00 + 16 < cend) tc::tmem_ld16(taddr + c00 + 16, vv + 16);
               tc::tmem_ld_wait();
 #pragma unroll
               for (int half = 0; half < 2; ++half) {
                 const int c0 = c00 + half * 16;
-                if (c0 < j.N) {
+                if (c0 < cend) {
                   float* v = vv + half * 16;
 #pragma unroll
                   for (int i = 0; i < 16; i += 4) {
@@ -612,11 +693,13 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
             tc::fence_before_thread_sync();
             mbar_arrive(&acc_free[t]);
             mbar_arrive(&a_ready[t]);
+            MF_TRACE(gt == 0 && t == 0 && p == blockIdx.x && unit < 2, 400 + ji);
           } else {
             // last-layer chunk: splines of the chunk's features straight out of TMEM
 #pragma unroll
             for (int fl = 0; fl < 5; ++fl) {
               if (fl >= j.nfeat) break;
+              if ((fl % EW) != eset) continue;
               const int f = j.feat0 + fl;
               const float xv = xin[fl];
               float out, la;
@@ -641,10 +724,17 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
             }
             tc::fence_before_thread_sync();
             mbar_arrive(&acc_free[t]);
+            MF_TRACE(gt == 0 && t == 0 && p == blockIdx.x && unit < 2, 400 + ji);
           }
         }
       }
-      if (valid && !inverse) {
+      if (EW > 1 && !inverse) {  // the other warp set's share of ladj travels through the workspace
+        float* wl = static_cast<float*>(args.work);
+        if (eset == 1 && valid) wl[g] = ladj;
+        group_bar(1 + t, GT);
+        if (eset == 0 && valid) ladj += wl[g];
+      }
+      if (valid && !inverse && eset == 0) {
         if (args.ladj) static_cast<float*>(args.ladj)[g] = ladj;
         if (args.logprob) {
           float lp = 0.f;
@@ -696,10 +786,18 @@ int flow_tc_pack(const mf_flow_desc& d, const void* const* w, const void* const*
   return MF_OK;
 }
 
+int tc_epilogue_sets() {  // MF_TC_EW=2 selects the 16-epilogue-warp variant (measured: no gain, kept for A/B runs)
+  static const int ew = [] {
+    const char* e = getenv("MF_TC_EW");
+    return (e && e[0] == '2') ? 2 : 1;
+  }();
+  return ew;
+}
+
 long long flow_tc_workspace_bytes(const mf_flow_desc& d, long long n, int gemm, int op) {
   (void)gemm;
   if (op == MF_FLOW_OP_SAMPLE) return n * d.features * 4;  // y targets of the transform being inverted
-  return 0;
+  return n * 4;                                            // ladj share of the second epilogue warp set
 }
 
 int flow_tc_run(const mf_flow_desc& d, const FlowKernelArgs& a, const BaseParams& bp, int gemm, cudaStream_t st) {
@@ -720,19 +818,23 @@ int flow_tc_run(const mf_flow_desc& d, const FlowKernelArgs& a, const BaseParams
                "tensor-core sampling needs a workspace of mf_flow_workspace_bytes() bytes");
   }
   const int parts = (L.nsplit == 3) ? 2 : 1;
-  const size_t smem = (size_t)2 * parts * kABufBytes + (size_t)kStages * parts * kWPartBytes;
+  const size_t smem = (size_t)2 * parts * kABufBytes + (size_t)ring_stages(L.nsplit) * parts * kWPartBytes;
   const long long n_pairs = ((a.n + 127) / 128 + 1) / 2;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const unsigned grid = (unsigned)std::min<long long>(n_pairs, sms);
-  if (L.nsplit == 3) {
-    MF_CUDA_CHECK(cudaFuncSetAttribute(flow_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    flow_tc_kernel<3><<<grid, kTcThreads, smem, st>>>(L, a, bp);
-  } else {
-    MF_CUDA_CHECK(cudaFuncSetAttribute(flow_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    flow_tc_kernel<1><<<grid, kTcThreads, smem, st>>>(L, a, bp);
-  }
+  if (a.mode == 0)
+    MF_REQUIRE(a.work != nullptr && a.work_bytes >= a.n * 4, "tensor-core log_prob needs a workspace of mf_flow_workspace_bytes() bytes");
+  const int ew = tc_epilogue_sets();
+#define MF_TC_LAUNCH(NS, EWV)                                                                                   \
+  do {                                                                                                          \
+    MF_CUDA_CHECK(cudaFuncSetAttribute(flow_tc_kernel<NS, EWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    flow_tc_kernel<NS, EWV><<<grid, (3 + 8 * EWV) * 32, smem, st>>>(L, a, bp);                                  \
+  } while (0)
+  if (L.nsplit == 3) { if (ew == 2) MF_TC_LAUNCH(3, 2); else MF_TC_LAUNCH(3, 1); }
+  else               { if (ew == 2) MF_TC_LAUNCH(1, 2); else MF_TC_LAUNCH(1, 1); }
+#undef MF_TC_LAUNCH
   return post_launch("flow_tc_kernel");
 }
 

@@ -22,53 +22,51 @@ __device__ __forceinline__ float exp_sfu(float x) {
   return fmaf(e, r * 0.6931471805599453f, e);
 }
 
-// lw, lh: K width / height logits; ld: K-1 derivative logits (entries beyond are ignored).
+// Phase 1: knots and bin.  lw / lh hold the K width / height logits on entry and are overwritten (soft clip ->
+// softmax numerators).  v is pre-mapped (circular shift / PS map) in place for the forward direction.
 template <int NCH>
-__device__ __forceinline__ void rqs_eval_reg(const float* lw, const float* lh, const float* ld,
-                                             const SplineCfg<float>& cfg, bool inverse, float v, float& out,
-                                             float& ladj, int& bin, bool& inside) {
+__device__ __forceinline__ void rqs_scan_reg(float* lw, float* lh, const SplineCfg<float>& cfg, bool inverse, float& v,
+                                             int& k, bool& inside, float& x0, float& x1, float& y0, float& y1,
+                                             float& ladj0) {
   constexpr int KP = 8 * NCH;
   const int K = cfg.K;
-  float ladj0 = 0.f;
+  ladj0 = 0.f;
   if (!inverse) {
     if (cfg.univariate == MF_UNIV_CIRCULAR_RQS) v = circular_wrap(v, cfg.bound);
     if (cfg.univariate == MF_UNIV_PS_RQS) { v = (v + 1.f) * 0.5f; ladj0 = -0.6931471805599453f; }
   }
-  float ew[KP], eh[KP];
 #pragma unroll
   for (int j = 0; j < KP; ++j) {
-    ew[j] = softclipf(lw[j], cfg.inv_ls2);
-    eh[j] = softclipf(lh[j], cfg.inv_ls2);
+    lw[j] = softclipf(lw[j], cfg.inv_ls2);
+    lh[j] = softclipf(lh[j], cfg.inv_ls2);
   }
   float mw = 0.f, mh = 0.f;
   if (cfg.inv_ls2 == 0.f) {  // no soft clip: logits are unbounded, subtract the maximum
     mw = -INFINITY; mh = -INFINITY;
 #pragma unroll
     for (int j = 0; j < KP; ++j)
-      if (j < K) { mw = fmaxf(mw, ew[j]); mh = fmaxf(mh, eh[j]); }
+      if (j < K) { mw = fmaxf(mw, lw[j]); mh = fmaxf(mh, lh[j]); }
   }
   float sw = 0.f, sh = 0.f;
 #pragma unroll
   for (int j = 0; j < KP; ++j) {
-    ew[j] = (j < K) ? exp_sfu(ew[j] - mw) : 0.f;
-    eh[j] = (j < K) ? exp_sfu(eh[j] - mh) : 0.f;
-    sw += ew[j];
-    sh += eh[j];
+    lw[j] = (j < K) ? exp_sfu(lw[j] - mw) : 0.f;
+    lh[j] = (j < K) ? exp_sfu(lh[j] - mh) : 0.f;
+    sw += lw[j];
+    sh += lh[j];
   }
   const float isw = __fdividef(1.f, sw), ish = __fdividef(1.f, sh);
-  int k = -1;
-  float x0 = 0.f, x1 = 1.f, y0 = 0.f, y1 = 1.f, cw = 0.f, ch = 0.f, prevw = -cfg.bound, prevh = -cfg.bound;
-  float t0 = 0.f, t1 = 0.f;
+  k = -1;
+  x0 = 0.f; x1 = 1.f; y0 = 0.f; y1 = 1.f;
+  float cw = 0.f, ch = 0.f, prevw = -cfg.bound, prevh = -cfg.bound;
 #pragma unroll
   for (int j = 0; j < KP; ++j) {
     if (j < K) {
-      cw += ew[j] * isw;
-      ch += eh[j] * ish;
+      cw += lw[j] * isw;
+      ch += lh[j] * ish;
       const float knotw = cfg.bound * (2.f * cw - 1.f), knoth = cfg.bound * (2.f * ch - 1.f);
       if ((inverse ? prevh : prevw) < v) {  // k = #(knots < v) - 1 on the searched axis
         k = j; x0 = prevw; x1 = knotw; y0 = prevh; y1 = knoth;
-        t1 = ld[j];                      // derivative logit k   (knot k+1)
-        t0 = ld[j > 0 ? j - 1 : 0];      // derivative logit k-1 (knot k)
       }
       prevw = knotw; prevh = knoth;
     }
@@ -76,10 +74,16 @@ __device__ __forceinline__ void rqs_eval_reg(const float* lw, const float* lh, c
   if ((inverse ? prevh : prevw) < v) k = K;
   inside = (k >= 0) && (k < K);
   k = k < 0 ? k + K : (k >= K ? k - K : k);
-  bin = k;
+  if (!inside) { x0 = 0.f; x1 = 1.f; y0 = 0.f; y1 = 1.f; }
+}
+
+// Phase 2: the rational-quadratic map of bin k given the derivative logits t0 (knot k) and t1 (knot k+1).
+__device__ __forceinline__ void rqs_finish(const SplineCfg<float>& cfg, bool inverse, float v, int k, bool inside,
+                                           float x0, float x1, float y0, float y1, float t0, float t1, float ladj0,
+                                           float& out, float& ladj) {
+  const int K = cfg.K;
   const float d0 = (k > 0) ? exp_sfu(softclipf(t0, cfg.inv_ls1)) : 1.f;
   const float d1 = (k < K - 1) ? exp_sfu(softclipf(t1, cfg.inv_ls1)) : 1.f;
-  if (!inside) { x0 = 0.f; x1 = 1.f; y0 = 0.f; y1 = 1.f; }
   const float dx = x1 - x0, dy = y1 - y0;
   const float s = dy * __fdividef(1.f, dx);
   if (!inverse) {
@@ -104,6 +108,29 @@ __device__ __forceinline__ void rqs_eval_reg(const float* lw, const float* lh, c
     out = x;
     ladj = 0.f;
   }
+}
+
+// pick logits k-1 and k out of a register array without dynamic indexing
+template <int KP>
+__device__ __forceinline__ void select_pair(const float* ld, int k, float& t0, float& t1) {
+  t0 = 0.f; t1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < KP; ++j) {
+    t0 = (j == k - 1) ? ld[j] : t0;
+    t1 = (j == k) ? ld[j] : t1;
+  }
+}
+
+// lw, lh: K width / height logits (overwritten); ld: K-1 derivative logits (entries beyond are ignored).
+template <int NCH>
+__device__ __forceinline__ void rqs_eval_reg(float* lw, float* lh, const float* ld, const SplineCfg<float>& cfg,
+                                             bool inverse, float v, float& out, float& ladj, int& bin, bool& inside) {
+  int k;
+  float x0, x1, y0, y1, ladj0, t0, t1;
+  rqs_scan_reg<NCH>(lw, lh, cfg, inverse, v, k, inside, x0, x1, y0, y1, ladj0);
+  select_pair<8 * NCH>(ld, k, t0, t1);
+  bin = k;
+  rqs_finish(cfg, inverse, v, k, inside, x0, x1, y0, y1, t0, t1, ladj0, out, ladj);
 }
 
 }  // namespace mf

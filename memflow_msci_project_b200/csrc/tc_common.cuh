@@ -44,6 +44,19 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_f16(int fmt, int M, int 
          ((uint32_t)(M >> 4) << 24);
 }
 
+// true in exactly one lane of a fully converged warp (elect.sync)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                            uint32_t accumulate) {
   asm volatile(
