@@ -249,7 +249,7 @@ def run_ours(args):
     traffic = None
     tfile = os.path.join(ROOT, "profiles", "flow_kernel_traffic.json")
     if os.path.exists(tfile):
-        traffic = json.load(open(tfile)).get("dram_bytes_per_launch")
+        traffic = json.load(open(tfile)).get("dram_bytes_per_object", 0) * events * P_OBJ or None
 
     if rank == 0:
         h2d = sum(t.numel() * t.element_size() for t in host)
