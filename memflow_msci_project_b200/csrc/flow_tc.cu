@@ -48,11 +48,12 @@ namespace {
 #define MF_TRACE(cond, id) do { } while (0)
 #endif
 
-// weight ring depth: the 3xFP16 mode has room for 3 stages of 32 KB next to the operand buffers, bf16 for 8 of 16 KB
-__host__ __device__ constexpr int ring_stages(int nsplit) { return nsplit == 3 ? 3 : 8; }
+constexpr int kMaxStages = 8;                   // weight ring depth: as many as fit next to the layer-0 operands
 constexpr int kMaxJobs = 40;
-constexpr uint32_t kABufBytes = 128 * 128 * 2;  // one [128 x 128] 16-bit operand (two K-blocks)
 constexpr uint32_t kWPartBytes = 128 * 128;     // one [<=128 rows x 64] 16-bit weight K-block
+constexpr uint32_t kKBlockBytes = 128 * 128;    // one [128 x 64] 16-bit SWIZZLE_128B K-block of the layer-0 operand
+constexpr uint32_t kTailBytes = 128 * 32;       // one [128 x 16] 16-bit SWIZZLE_32B k-step of the layer-0 operand
+constexpr size_t kStaticSmem = 4096;            // barriers, bias slots (static __shared__), alignment slack
 
 struct TcJob {
   int N;        // MMA N (multiple of 16, <= 128)
@@ -74,6 +75,10 @@ struct TcLayout {
   int PFt;     // 3 * Kp
   int njobs;
   int in0_ksteps;
+  int in0_full;          // layer-0 operand: full 64-wide K-blocks (SWIZZLE_128B) ...
+  int in0_tail;          // ... followed by this many single k-steps in SWIZZLE_32B blocks
+  int in0_plane_bytes;   // bytes of one operand plane of one tile
+  int stages;            // weight ring depth
   long long t_stride;    // bytes per transform (weights)
   long long bias_off;    // byte offset of the fp32 bias region in the blob
   int bias_stride;       // floats per transform
@@ -115,6 +120,13 @@ int make_tc_layout(const mf_flow_desc& d, int gemm, TcLayout* L) {
     j.b_off = boff; boff += j.N;
   }
   L->in0_ksteps = L->job[0].ksteps;
+  L->in0_full = L->in0_ksteps / 4;
+  L->in0_tail = L->in0_ksteps % 4;
+  L->in0_plane_bytes = L->in0_full * (int)kKBlockBytes + L->in0_tail * (int)kTailBytes;
+  {
+    const size_t avail = 232448 - kStaticSmem - (size_t)2 * parts * L->in0_plane_bytes;
+    L->stages = (int)std::min<size_t>(kMaxStages, avail / ((size_t)parts * kWPartBytes));
+  }
   const int fpc = std::max(1, 128 / L->PFt);
   for (int f0 = 0; f0 < d.features; f0 += fpc) {
     MF_REQUIRE(nj < kMaxJobs, "too many last-layer chunks for the tensor-core path");
@@ -332,9 +344,10 @@ __device__ __forceinline__ void tmem_ld8_raw(uint32_t taddr, uint32_t* r) {
 template <int NCH>
 __device__ __forceinline__ void rqs_forward_tmem_reg(uint32_t taddr, const float* sb, const SplineCfg<float>& cfg,
                                                      bool inverse, float v, float& out, float& ladj, int& bin,
-                                                     bool& inside) {
+                                                     bool& inside, long long* ts = nullptr) {
   constexpr int KP = 8 * NCH;
   float lw[KP], lh[KP];
+  if (ts) ts[0] = clock64();
   {
     uint32_t rw[KP], rh[KP];
 #pragma unroll
@@ -343,6 +356,7 @@ __device__ __forceinline__ void rqs_forward_tmem_reg(uint32_t taddr, const float
       tmem_ld8_raw(taddr + KP + c * 8, rh + c * 8);
     }
     tc::tmem_ld_wait();
+    if (ts) ts[1] = clock64();
 #pragma unroll
     for (int j = 0; j < KP; ++j) {  // accumulator + bias
       lw[j] = __uint_as_float(rw[j]) + sb[j];
@@ -352,6 +366,7 @@ __device__ __forceinline__ void rqs_forward_tmem_reg(uint32_t taddr, const float
   int k;
   float x0, x1, y0, y1, ladj0, t0, t1;
   rqs_scan_reg<NCH>(lw, lh, cfg, inverse, v, k, inside, x0, x1, y0, y1, ladj0);
+  if (ts) ts[2] = clock64() + (long long)(x0 == 12345.f);
   {  // derivative logits are fetched only now (short register live ranges); the load is warp-uniform
     uint32_t rd[KP];
 #pragma unroll
@@ -366,7 +381,9 @@ __device__ __forceinline__ void rqs_forward_tmem_reg(uint32_t taddr, const float
     }
   }
   bin = k;
+  if (ts) ts[3] = clock64() + (long long)(t0 == 12345.f);
   rqs_finish(cfg, inverse, v, k, inside, x0, x1, y0, y1, t0, t1, ladj0, out, ladj);
+  if (ts) ts[4] = clock64() + (long long)(out == 12345.f);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -381,9 +398,11 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
   extern __shared__ __align__(1024) unsigned char smem[];
   // [tile][part] activation operands, then the weight ring
   unsigned char* a_buf = smem;
-  unsigned char* w_ring = smem + 2 * kParts * kABufBytes;
-  constexpr int kStages = ring_stages(NSPLIT);
-  __shared__ __align__(8) uint64_t w_full[kStages], w_empty[kStages], a_ready[2], acc_full[2], acc_free[2];
+  const uint32_t kPlane = (uint32_t)L.in0_plane_bytes;
+  const uint32_t kFullBytes = (uint32_t)L.in0_full * kKBlockBytes;  // tail k-steps start here inside a plane
+  unsigned char* w_ring = smem + 2 * kParts * kPlane;
+  const uint32_t kStages = (uint32_t)L.stages;
+  __shared__ __align__(8) uint64_t w_full[kMaxStages], w_empty[kMaxStages], a_ready[2], acc_full[2], acc_free[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float sbias[2][2][128];  // [tile slot][job parity][column]
 
@@ -398,7 +417,7 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
   const float* bias_all = reinterpret_cast<const float*>(blob + L.bias_off);
 
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 2); }  // two MMA issuers release a stage
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&a_ready[t], 128 * EW);
       mbar_init(&acc_full[t], 1);
@@ -436,81 +455,84 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
         }
       }
     }
-  } else if (warp == 1 || warp == 2) {
-    // ===================== MMA issuers: one warp per tile slot =====================
-    // The whole warp walks the (warp-uniform) schedule and waits on the barriers; one elected lane issues the
-    // tcgen05 instructions.  Keeping the warp converged lets the compiler hold descriptors in uniform registers.
-    // Both issuers consume every weight stage; a stage is released once both have committed it.
-    {
-      const int t = warp - 1;
-      uint32_t it = 0;      // weight stages consumed so far
-      int trace_n = 1000 * t; (void)trace_n;
-      uint32_t jobctr = 0;  // accumulator uses of this tile slot
-      uint32_t aph = 0;     // a_ready phase
-      const uint32_t d_tmem = tmem + (uint32_t)(t * 256);
-      const uint32_t a_tmem = d_tmem + 128;  // hi plane; lo plane 64 columns further
-      const uint32_t a_base = smem_u32(a_buf + (size_t)t * kParts * kABufBytes);
-      for (long long p = blockIdx.x; p < n_pairs; p += gridDim.x) {
-        const bool active = (2 * p + t) < n_tiles;  // odd tile count: slot 1 only releases the stages in the last pair
-        for (int unit = 0; unit < n_units; ++unit) {
-          for (int ji = 0; ji < L.njobs; ++ji) {
-            const TcJob& j = L.job[ji];
-            const uint32_t idesc = tc::make_idesc_f16(NSPLIT == 3 ? 0 : 1, 128, j.N);
-            if (active) {
-              if (j.needs_a) { mbar_wait(&a_ready[t], aph); aph ^= 1; }
-              if (jobctr >= 1) mbar_wait(&acc_free[t], (jobctr - 1) & 1);  // accumulator drained
-              MF_TRACE(lane == 0 && p == blockIdx.x && unit < 2, 100 + 10 * t + ji);
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // One warp walks the (warp-uniform) schedule and waits on the barriers; per K-block one elected lane issues
+    // the MMAs back to back.  The two tile slots take turns job by job (slot 0's job j, slot 1's job j, slot 0's
+    // job j+1, ...): while one slot's MMAs occupy the tensor pipe the other slot's epilogue drains its
+    // accumulator, so in steady state the pipe never waits for an epilogue that is shorter than an MMA phase.
+    uint32_t it = 0;                 // weight stages consumed so far
+    int trace_n = 0; (void)trace_n;
+    uint32_t jobctr[2] = {0, 0};     // accumulator uses per tile slot
+    uint32_t aph[2] = {0, 0};        // a_ready phases
+    for (long long p = blockIdx.x; p < n_pairs; p += gridDim.x) {
+      const int nact = (2 * p + 1 < n_tiles) ? 2 : 1;  // odd tile count: slot 1 idles in the last pair
+      for (int unit = 0; unit < n_units; ++unit) {
+        for (int ji = 0; ji < L.njobs; ++ji) {
+          const TcJob& j = L.job[ji];
+          const uint32_t idesc = tc::make_idesc_f16(NSPLIT == 3 ? 0 : 1, 128, j.N);
+          for (int t = 0; t < nact; ++t) {
+            const uint32_t d_tmem = tmem + (uint32_t)(t * 256);
+            const uint32_t a_tmem = d_tmem + 128;  // hi plane; lo plane 64 columns further
+            const uint32_t a_base = smem_u32(a_buf + (size_t)t * kParts * kPlane);
+            if (j.needs_a) { mbar_wait(&a_ready[t], aph[t]); aph[t] ^= 1; }
+            if (jobctr[t] >= 1) mbar_wait(&acc_free[t], (jobctr[t] - 1) & 1);  // accumulator drained
+            MF_TRACE(lane == 0, 100 + 10 * t + ji);
+            tc::fence_after_thread_sync();
+            for (int kb = 0; kb < j.nkb; ++kb) {
+              const uint32_t s = (it + kb) % kStages, ph = ((it + kb) / kStages) & 1;
+              if (t == 0) mbar_wait(&w_full[s], ph);
               tc::fence_after_thread_sync();
-            }
-            for (int kb = 0; kb < j.nkb; ++kb, ++it) {
-              const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-              mbar_wait(&w_full[s], ph);
-              if (active) {
-                tc::fence_after_thread_sync();
-                const uint32_t w_base = smem_u32(w_ring + s * kStageBytes);
-                const int ks_n = min(4, j.ksteps - kb * 4);
-                for (int ks = 0; ks < ks_n; ++ks) {
-                  const uint32_t acc = (kb | ks) ? 1u : 0u;
-                  const uint64_t dbh = tc::make_smem_desc(w_base + ks * 32u);
-                  const uint64_t dbl = tc::make_smem_desc(w_base + kWPartBytes + ks * 32u);
-                  if (ji == 0) {  // layer 0: (x | ctx) operand from shared memory
-                    const uint64_t dah = tc::make_smem_desc(a_base + kb * (128u * 128u) + ks * 32u);
-                    const uint64_t dal = tc::make_smem_desc(a_base + kABufBytes + kb * (128u * 128u) + ks * 32u);
-                    if (tc::elect_one()) {
-                      tc::mma_f16_ss(d_tmem, dah, dbh, idesc, acc);
+              const uint32_t w_base = smem_u32(w_ring + s * kStageBytes);
+              const int ks_n = min(4, j.ksteps - kb * 4);
+              // measured: 75 clk per 128x128x16 MMA issued like this against ~120 when every MMA sits in its own
+              // elect / branch / reconverge region
+              if (tc::elect_one()) {
+                const uint64_t dbh = tc::make_smem_desc(w_base);
+                const uint64_t dbl = tc::make_smem_desc(w_base + kWPartBytes);
+                if (ji == 0) {  // layer 0: (x | ctx) operand from shared memory
+                  const bool full = kb < L.in0_full;
+                  const uint64_t dah = full ? tc::make_smem_desc(a_base + kb * kKBlockBytes) : tc::make_smem_desc_sw32(a_base + kFullBytes);
+                  const uint64_t dal = full ? tc::make_smem_desc(a_base + kPlane + kb * kKBlockBytes)
+                                            : tc::make_smem_desc_sw32(a_base + kPlane + kFullBytes);
+                  const uint64_t astep = full ? 2u : (kTailBytes >> 4);  // descriptor address units of 16 bytes
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks) {
+                    if (ks < ks_n) {
+                      tc::mma_f16_ss(d_tmem, dah + ks * astep, dbh + ks * 2u, idesc, (kb | ks) ? 1u : 0u);
                       if (NSPLIT == 3) {
-                        tc::mma_f16_ss(d_tmem, dah, dbl, idesc, 1u);
-                        tc::mma_f16_ss(d_tmem, dal, dbh, idesc, 1u);
-                      }
-                    }
-                  } else {        // hidden activations: operand planes in TMEM
-                    const uint32_t ah = a_tmem + (uint32_t)(kb * 4 + ks) * 8u;
-                    if (tc::elect_one()) {
-                      tc::mma_f16_ts(d_tmem, ah, dbh, idesc, acc);
-                      if (NSPLIT == 3) {
-                        tc::mma_f16_ts(d_tmem, ah, dbl, idesc, 1u);
-                        tc::mma_f16_ts(d_tmem, ah + 64u, dbh, idesc, 1u);
+                        tc::mma_f16_ss(d_tmem, dah + ks * astep, dbl + ks * 2u, idesc, 1u);
+                        tc::mma_f16_ss(d_tmem, dal + ks * astep, dbh + ks * 2u, idesc, 1u);
                       }
                     }
                   }
-                  __syncwarp();
+                } else {        // hidden activations: operand planes in TMEM
+                  const uint32_t ah = a_tmem + (uint32_t)(kb * 4) * 8u;
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks) {
+                    if (ks < ks_n) {
+                      tc::mma_f16_ts(d_tmem, ah + ks * 8u, dbh + ks * 2u, idesc, (kb | ks) ? 1u : 0u);
+                      if (NSPLIT == 3) {
+                        tc::mma_f16_ts(d_tmem, ah + ks * 8u, dbl + ks * 2u, idesc, 1u);
+                        tc::mma_f16_ts(d_tmem, ah + 64u + ks * 8u, dbh + ks * 2u, idesc, 1u);
+                      }
+                    }
+                  }
                 }
-                if (tc::elect_one()) tc::mma_commit(&w_empty[s]);  // this issuer is done with the stage
-              } else {
-                if (tc::elect_one()) mbar_arrive(&w_empty[s]);
+                if (t == nact - 1) tc::mma_commit(&w_empty[s]);  // both slots are done with the stage
+                if (kb == j.nkb - 1) tc::mma_commit(&acc_full[t]);
               }
               __syncwarp();
             }
-            if (active) {
-              if (tc::elect_one()) tc::mma_commit(&acc_full[t]);
-              __syncwarp();
-              MF_TRACE(lane == 0 && p == blockIdx.x && unit < 2, 200 + 10 * t + ji);
-              jobctr++;
-            }
+            MF_TRACE(lane == 0, 200 + 10 * t + ji);
+            jobctr[t]++;
           }
+          it += j.nkb;
         }
       }
     }
+  } else if (warp == 2) {
+    // spare warp (keeps the epilogue warps aligned to the TMEM lane quarters: warp % 4)
   } else {
     // ===================== epilogue groups =====================
     const int eset = (warp - 3) >> 3;         // warp set inside the tile's epilogue group (0 .. EW-1)
@@ -520,8 +542,13 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
     const int gt = eset * 128 + ((warp - 3) & 3) * 32 + lane;  // thread index inside the group (cooperative loops)
     constexpr int GT = 128 * EW;              // threads per epilogue group
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    unsigned char* a_hi = a_buf + (size_t)t * kParts * kABufBytes;
-    unsigned char* a_lo = a_hi + kABufBytes;
+    unsigned char* a_hi = a_buf + (size_t)t * kParts * kPlane;
+    unsigned char* a_lo = a_hi + kPlane;
+    const int kfull_cols = L.in0_full * 64;
+    auto in0_offset = [&](int r, int k) -> uint32_t {
+      return k < kfull_cols ? tc::sw128_offset(r, k, 128)
+                            : kFullBytes + (uint32_t)((k - kfull_cols) >> 4) * kTailBytes + tc::sw32_offset(r, k & 15);
+    };
     const float* gx = static_cast<const float*>(args.x);
     const float* gc = static_cast<const float*>(args.ctx);
     float* gz = static_cast<float*>(args.z);
@@ -531,21 +558,10 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
     cfg.inv_ls2 = args.slope > 0.0 ? (float)(2.0 / log(args.slope)) : 0.f;
     cfg.inv_ls1 = args.slope > 0.0 ? (float)(1.0 / log(args.slope)) : 0.f;
     uint32_t jobctr = 0;
-    int trace_n = 2000; (void)trace_n;
+    int trace_n = 2000 + 1000 * t; (void)trace_n;
 
-    auto put2 = [&](int r, int k, float v0, float v1) {  // two consecutive columns k, k+1 (k even)
-      const uint32_t off = tc::sw128_offset(r, k, 128);
-      if (NSPLIT == 3) {
-        uint32_t hi, lo;
-        tc::split_f16(v0, v1, hi, lo);
-        *reinterpret_cast<uint32_t*>(a_hi + off) = hi;
-        *reinterpret_cast<uint32_t*>(a_lo + off) = lo;
-      } else {
-        *reinterpret_cast<uint32_t*>(a_hi + off) = tc::pack_bf16(v0, v1);
-      }
-    };
     auto put1 = [&](int r, int k, float v) {
-      const uint32_t off = tc::sw128_offset(r, k, 128);
+      const uint32_t off = in0_offset(r, k);
       if (NSPLIT == 3) {
         const __half h = __float2half_rn(v);
         *reinterpret_cast<__half*>(a_hi + off) = h;
@@ -648,9 +664,9 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
           for (int fl = 0; fl < 5; ++fl)
             xin[fl] = (j.last && fl < j.nfeat && (fl % EW) == eset && valid)
                           ? (inverse ? gy[g * D + j.feat0 + fl] : gz[g * D + j.feat0 + fl]) : 0.f;
-          MF_TRACE(gt == 0 && t == 0 && p == blockIdx.x && unit < 2, 500 + ji);
+          MF_TRACE(gt == 0, 500 + 300 * t + ji);
           mbar_wait(&acc_full[t], jpar);
-          MF_TRACE(gt == 0 && t == 0 && p == blockIdx.x && unit < 2, 300 + ji);
+          MF_TRACE(gt == 0, 300 + 300 * t + ji);
           tc::fence_after_thread_sync();
           const uint32_t taddr = tmem + lane_off + (uint32_t)(t * 256);
           if (!j.last) {
@@ -693,7 +709,7 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
             tc::fence_before_thread_sync();
             mbar_arrive(&acc_free[t]);
             mbar_arrive(&a_ready[t]);
-            MF_TRACE(gt == 0 && t == 0 && p == blockIdx.x && unit < 2, 400 + ji);
+            MF_TRACE(gt == 0, 400 + 300 * t + ji);
           } else {
             // last-layer chunk: splines of the chunk's features straight out of TMEM
 #pragma unroll
@@ -709,7 +725,18 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
               const float* sbf = sb + fl * L.PFt;
               switch (L.Kp) {
                 case 8: rqs_forward_tmem_reg<1>(ta, sbf, cfg, inverse, xv, out, la, bin, ins); break;
+#ifdef MF_TC_TRACE
+                case 16: {
+                  long long ts5[5];
+                  rqs_forward_tmem_reg<2>(ta, sbf, cfg, inverse, xv, out, la, bin, ins, ts5);
+                  if (gt == 0 && t == 0 && blockIdx.x == 0 && trace_n < 2900) {
+                    long long* tb_ = reinterpret_cast<long long*>(args.inside);
+                    for (int q5 = 0; q5 < 5; ++q5) { tb_[2 * trace_n] = ts5[q5]; tb_[2 * trace_n + 1] = 900 + q5; ++trace_n; }
+                  }
+                } break;
+#else
                 case 16: rqs_forward_tmem_reg<2>(ta, sbf, cfg, inverse, xv, out, la, bin, ins); break;
+#endif
                 case 24: rqs_forward_tmem_reg<3>(ta, sbf, cfg, inverse, xv, out, la, bin, ins); break;
                 case 32: rqs_forward_tmem_reg<4>(ta, sbf, cfg, inverse, xv, out, la, bin, ins); break;
                 default: rqs_forward_tmem(ta, sbf, cfg, L.Kp, xv, out, la, bin, ins); break;
@@ -724,7 +751,7 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
             }
             tc::fence_before_thread_sync();
             mbar_arrive(&acc_free[t]);
-            MF_TRACE(gt == 0 && t == 0 && p == blockIdx.x && unit < 2, 400 + ji);
+            MF_TRACE(gt == 0, 400 + 300 * t + ji);
           }
         }
       }
@@ -818,7 +845,8 @@ int flow_tc_run(const mf_flow_desc& d, const FlowKernelArgs& a, const BaseParams
                "tensor-core sampling needs a workspace of mf_flow_workspace_bytes() bytes");
   }
   const int parts = (L.nsplit == 3) ? 2 : 1;
-  const size_t smem = (size_t)2 * parts * kABufBytes + (size_t)ring_stages(L.nsplit) * parts * kWPartBytes;
+  MF_REQUIRE(L.stages >= 2, "layer-0 operand too large for the weight ring");
+  const size_t smem = (size_t)2 * parts * L.in0_plane_bytes + (size_t)L.stages * parts * kWPartBytes;
   const long long n_pairs = ((a.n + 127) / 128 + 1) / 2;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

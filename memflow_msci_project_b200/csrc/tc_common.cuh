@@ -26,7 +26,24 @@ __host__ __device__ __forceinline__ uint32_t sw128_offset(int r, int k, int R) {
          (uint32_t)(kk & 7) * 2u;
 }
 
+// 32-byte-swizzle K-major layout of ONE k-step (16 elements = 32 bytes per row): row r at r * 32, its two 16-byte
+// chunks swapped when bit 2 of r is set (Swizzle<1,4,3> on the byte address); 8-row groups 256 bytes apart.
+// Used for the tail k-steps of the layer-0 operand, where a full 128-byte K-block would waste shared memory.
+__host__ __device__ __forceinline__ uint32_t sw32_offset(int r, int k) {
+  return (uint32_t)r * 32u + (uint32_t)(((k >> 3) ^ ((r >> 2) & 1)) * 16) + (uint32_t)(k & 7) * 2u;
+}
+
 #ifdef __CUDACC__
+__device__ __forceinline__ uint64_t make_smem_desc_sw32(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(256 >> 4) << 32;  // stride byte offset: 8 rows * 32 bytes
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;           // layout type SWIZZLE_32B
+  return d;
+}
+
 // shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 bytes apart
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   uint64_t d = 0;

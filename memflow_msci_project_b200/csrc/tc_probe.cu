@@ -4,6 +4,8 @@
 //   mode 0: fp16 hi/lo split of both operands, 3 MMAs per k-step (hi*hi + hi*lo + lo*hi)
 //   mode 1: bf16 single MMA        mode 2: fp16 single MMA
 //   mode 3: fp16 hi/lo split with the A operand staged in TMEM (tcgen05.st) instead of shared memory
+//   mode 4: like mode 0, but the k-steps of A beyond the last full 64-wide K-block use 32-byte-swizzle blocks
+//   mode 100+: issue-rate timing (tc_issue_probe_kernel)
 #include "tc_common.cuh"
 
 namespace mf {
@@ -40,6 +42,19 @@ tc_probe_kernel(const float* __restrict__ A, const float* __restrict__ W, float*
   for (int i = tid; i < 128 * K; i += 128) put(a_hi, a_lo, 128, i / K, i % K, A[i]);
   for (int i = tid; i < N * K; i += 128) put(b_hi, b_lo, N, i / K, i % K, W[i]);
 
+  unsigned char* a_tail = b_lo + b_bytes;  // mode 4: [tail k-step][plane][128 x 32 B]
+  const int full_kb = K / 64, tail_steps = (K % 64) / 16;
+  if (mode == 4) {
+    for (int i = tid; i < 128 * tail_steps * 16; i += 128) {
+      const int r = i / (tail_steps * 16), kk = i % (tail_steps * 16);
+      const int ts = kk / 16, k = kk % 16;
+      const float v = A[(size_t)r * K + full_kb * 64 + kk];
+      const __half h = __float2half_rn(v);
+      unsigned char* blk = a_tail + (size_t)ts * 2 * 4096;
+      *reinterpret_cast<__half*>(blk + tc::sw32_offset(r, k)) = h;
+      *reinterpret_cast<__half*>(blk + 4096 + tc::sw32_offset(r, k)) = __float2half_rn(v - __half2float(h));
+    }
+  }
   if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
     mbar_init(&bar, 1);
@@ -79,7 +94,29 @@ tc_probe_kernel(const float* __restrict__ A, const float* __restrict__ W, float*
     }
     tc::mma_commit(&bar);
   }
-  if (tid == 0 && mode != 3) {
+  if (tid == 0 && mode == 4) {
+    const uint32_t idesc = tc::make_idesc_f16(0, 128, N);
+    const int ksteps = K / 16;
+    for (int ks = 0; ks < ksteps; ++ks) {
+      const uint32_t kb = ks >> 2, kin = (ks & 3) * 32;
+      uint64_t dah, dal;
+      if ((int)kb < full_kb) {
+        dah = tc::make_smem_desc(smem_u32(a_hi) + kb * 128u * 128u + kin);
+        dal = tc::make_smem_desc(smem_u32(a_lo) + kb * 128u * 128u + kin);
+      } else {
+        const int ts = ks - full_kb * 4;
+        dah = tc::make_smem_desc_sw32(smem_u32(a_tail) + ts * 8192u);
+        dal = tc::make_smem_desc_sw32(smem_u32(a_tail) + ts * 8192u + 4096u);
+      }
+      const uint64_t dbh = tc::make_smem_desc(smem_u32(b_hi) + kb * (uint32_t)N * 128u + kin);
+      const uint64_t dbl = tc::make_smem_desc(smem_u32(b_lo) + kb * (uint32_t)N * 128u + kin);
+      tc::mma_f16_ss(tmem, dah, dbh, idesc, ks ? 1u : 0u);
+      tc::mma_f16_ss(tmem, dah, dbl, idesc, 1u);
+      tc::mma_f16_ss(tmem, dal, dbh, idesc, 1u);
+    }
+    tc::mma_commit(&bar);
+  }
+  if (tid == 0 && mode != 3 && mode != 4) {
     const uint32_t idesc = tc::make_idesc_f16(mode == 1 ? 1 : 0, 128, N);
     const int ksteps = (K + 15) / 16;
     uint32_t acc = 0;
@@ -113,6 +150,69 @@ tc_probe_kernel(const float* __restrict__ A, const float* __restrict__ W, float*
   if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
+
+// Issue-rate probe: `issuers` warps each push `count` MMAs (M=128, N=n, K=16) at their own accumulator, operands
+// either both in shared memory (ts = 0) or A in TMEM (ts = 1).  out[2w] = cycles until warp w has issued everything,
+// out[2w+1] = cycles until its commit barrier fires.
+__global__ void __launch_bounds__(128, 1) tc_issue_probe_kernel(float* __restrict__ out, int count, int n, int ts, int issuers, int variant) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar[4];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (16384 + 32768) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(&bar[i], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
+  fence_proxy_async_smem();
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  const uint32_t tmem = tmem_base_s;
+  if (warp < issuers) {
+    const uint32_t idesc = tc::make_idesc_f16(0, 128, n);
+    const uint32_t a_s = smem_u32(smem), b_s = smem_u32(smem + 16384);
+    const uint32_t d_tmem = tmem + warp * 256, a_tmem = d_tmem + 128;
+    const long long t0 = clock64();
+    if (variant == 1) {  // the whole issue loop inside one elected thread, four k-steps unrolled
+      if (tc::elect_one()) {
+        uint64_t db[4], da[4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) { db[ks] = tc::make_smem_desc(b_s + ks * 32u); da[ks] = tc::make_smem_desc(a_s + ks * 32u); }
+        for (int i = 0; i < count; i += 4) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            if (ts) tc::mma_f16_ts(d_tmem, a_tmem + ks * 8u, db[ks], idesc, 1u);
+            else tc::mma_f16_ss(d_tmem, da[ks], db[ks], idesc, 1u);
+          }
+        }
+      }
+      __syncwarp();
+    } else
+    for (int i = 0; i < count; ++i) {
+      const uint32_t ks = i & 3;
+      const uint64_t db = tc::make_smem_desc(b_s + ks * 32u);
+      if (ts) {
+        if (tc::elect_one()) tc::mma_f16_ts(d_tmem, a_tmem + ks * 8u, db, idesc, 1u);
+      } else {
+        const uint64_t da = tc::make_smem_desc(a_s + ks * 32u);
+        if (tc::elect_one()) tc::mma_f16_ss(d_tmem, da, db, idesc, 1u);
+      }
+      __syncwarp();
+    }
+    if (tc::elect_one()) tc::mma_commit(&bar[warp]);
+    __syncwarp();
+    const long long t1 = clock64();
+    mbar_wait(&bar[warp], 0);
+    const long long t2 = clock64();
+    if ((tid & 31) == 0) { out[2 * warp] = (float)(t1 - t0); out[2 * warp + 1] = (float)(t2 - t0); }
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
 }  // namespace
 }  // namespace mf
 
@@ -123,9 +223,17 @@ extern "C" int mf_tc_probe_gemm(const float* d_a, const float* d_w, float* d_out
   MF_REQUIRE(d_a && d_w && d_out, "mf_tc_probe_gemm: null argument");
   MF_REQUIRE(k >= 16 && k % 16 == 0 && k <= 256, "mf_tc_probe_gemm: K=%d must be a multiple of 16 in 16..256", k);
   MF_REQUIRE(n >= 16 && n % 16 == 0 && n <= 256, "mf_tc_probe_gemm: N=%d must be a multiple of 16 in 16..256", n);
-  MF_REQUIRE(mode >= 0 && mode <= 3, "mf_tc_probe_gemm: bad mode");
+  if (mode >= 100) {  // timing: mode = 100 + 10 * (A in TMEM) + issuers; k = MMA count per issuer
+    const int variant = (mode - 100) / 20, ts = ((mode - 100) / 10) % 2, issuers = (mode - 100) % 10;
+    MF_REQUIRE(d_out && issuers >= 1 && issuers <= 2 && ts <= 1 && n <= 128 && n % 16 == 0, "mf_tc_probe_gemm: bad timing mode");
+    const size_t sm = 16384 + 32768;
+    MF_CUDA_CHECK(cudaFuncSetAttribute(tc_issue_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    tc_issue_probe_kernel<<<1, 128, sm, static_cast<cudaStream_t>(stream)>>>(d_out, k, n, ts, issuers, variant);
+    return post_launch("tc_issue_probe_kernel");
+  }
+  MF_REQUIRE(mode >= 0 && mode <= 4, "mf_tc_probe_gemm: bad mode");
   const int kp = (k + 63) / 64 * 64;
-  const size_t smem = (size_t)2 * 128 * kp * 2 + (size_t)2 * n * kp * 2 + 1024;
+  const size_t smem = (size_t)2 * 128 * kp * 2 + (size_t)2 * n * kp * 2 + 3 * 8192 + 1024;
   MF_REQUIRE(smem <= 227 * 1024, "mf_tc_probe_gemm: operands do not fit shared memory");
   MF_CUDA_CHECK(cudaFuncSetAttribute(tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   tc_probe_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(d_a, d_w, d_out, k, n, mode);

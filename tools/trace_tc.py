@@ -23,11 +23,18 @@ for _ in range(2):
     _cabi.flow_log_prob(desc, blob, x, c, lp, z, ladj, bins, inside, m.gemm)
 torch.cuda.synchronize()
 tr = inside.view(-1)[: 8000 * 8].view(torch.int64).cpu().view(-1, 2)
-ev = [(int(t), int(i)) for t, i in tr.tolist() if 100 <= i < 600 and t > 0]
+ev = [(int(t), int(i)) for t, i in tr.tolist() if 100 <= i < 1000 and t > 0]
 ev.sort()
 t0 = ev[0][0]
-names = {1: "MMA t0 ready ", 11: "MMA t1 ready ", 2: "MMA t0 issued", 21: "MMA t1 issued", 3: "EPI t0 acc_full", 4: "EPI t0 done", 5: "EPI t0 waits"}
-for t, i in ev[:90]:
-    kind, ji = (i // 100, i % 10) if i < 300 else (i // 100, i % 100)
-    tile = (i % 100) // 10 if i < 300 else 0
-    print(f"{t - t0:8d}  id={i:4d}")
+# ids: 1TJ issuer T sees operands for job J, 2TJ issuer T issued job J; slot 0 epilogue 5JJ waits / 3JJ sees the
+# accumulator / 4JJ done; slot 1 epilogue 8JJ / 6JJ / 7JJ.  Printed as two columns, one per tile slot.
+def slot(i):
+    if i < 300: return (i % 100) // 10
+    return 0 if (i < 600 or i >= 900) else 1
+def label(i):
+    if i < 300: return ("MMA ready  " if i < 200 else "MMA issued ") + str(i % 10)
+    if i >= 900: return "   spline " + ["start", "ld w/h done", "scan done", "deriv sel done", "finish done"][i - 900]
+    k = (i - 300 * slot(i)) // 100
+    return {3: "EPI accfull ", 4: "EPI done    ", 5: "EPI wait    "}[k] + str(i % 100)
+for t, i in ev[:1500]:
+    print(f"{t - t0:8d}  " + ("" if slot(i) == 0 else " " * 28) + label(i))
