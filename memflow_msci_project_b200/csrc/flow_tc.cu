@@ -659,11 +659,8 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
           }
           group_bar(1 + t, GT);
           // inputs of this chunk's splines, fetched before the accumulator wait (at most 5 features per chunk)
-          float xin[5];
-#pragma unroll
-          for (int fl = 0; fl < 5; ++fl)
-            xin[fl] = (j.last && fl < j.nfeat && (fl % EW) == eset && valid)
-                          ? (inverse ? gy[g * D + j.feat0 + fl] : gz[g * D + j.feat0 + fl]) : 0.f;
+          const float* xsrc = (inverse ? gy : gz) + g * D + j.feat0;
+          float xnext = (j.last && eset < j.nfeat && valid) ? xsrc[eset] : 0.f;
           MF_TRACE(gt == 0, 500 + 300 * t + ji);
           mbar_wait(&acc_full[t], jpar);
           MF_TRACE(gt == 0, 300 + 300 * t + ji);
@@ -712,12 +709,11 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
             MF_TRACE(gt == 0, 400 + 300 * t + ji);
           } else {
             // last-layer chunk: splines of the chunk's features straight out of TMEM
-#pragma unroll
-            for (int fl = 0; fl < 5; ++fl) {
-              if (fl >= j.nfeat) break;
-              if ((fl % EW) != eset) continue;
+#pragma unroll 1
+            for (int fl = eset; fl < j.nfeat; fl += EW) {  // one copy of the spline code (instruction cache)
               const int f = j.feat0 + fl;
-              const float xv = xin[fl];
+              const float xv = xnext;
+              if (fl + EW < j.nfeat && valid) xnext = xsrc[fl + EW];  // next feature's input, in flight during this spline
               float out, la;
               int bin;
               bool ins;

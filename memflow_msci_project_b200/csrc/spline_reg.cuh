@@ -50,26 +50,30 @@ __device__ __forceinline__ void rqs_scan_reg(float* lw, float* lh, const SplineC
   float sw = 0.f, sh = 0.f;
 #pragma unroll
   for (int j = 0; j < KP; ++j) {
-    lw[j] = (j < K) ? exp_sfu(lw[j] - mw) : 0.f;
-    lh[j] = (j < K) ? exp_sfu(lh[j] - mh) : 0.f;
+    // padding entries (j >= K) go through the same straight-line code with an argument that underflows to 0:
+    // a conditional around the inline-asm exp would be compiled as one branch per element
+    lw[j] = exp_sfu((j < K) ? lw[j] - mw : -200.f);
+    lh[j] = exp_sfu((j < K) ? lh[j] - mh : -200.f);
     sw += lw[j];
     sh += lh[j];
   }
   const float isw = __fdividef(1.f, sw), ish = __fdividef(1.f, sh);
   k = -1;
   x0 = 0.f; x1 = 1.f; y0 = 0.f; y1 = 1.f;
+  // branch-free scan (selects only): with a runtime K the padded entries add 0 to the running sums and are
+  // masked out of the bin search, so the loop stays one basic block the scheduler can interleave
   float cw = 0.f, ch = 0.f, prevw = -cfg.bound, prevh = -cfg.bound;
 #pragma unroll
   for (int j = 0; j < KP; ++j) {
-    if (j < K) {
-      cw += lw[j] * isw;
-      ch += lh[j] * ish;
-      const float knotw = cfg.bound * (2.f * cw - 1.f), knoth = cfg.bound * (2.f * ch - 1.f);
-      if ((inverse ? prevh : prevw) < v) {  // k = #(knots < v) - 1 on the searched axis
-        k = j; x0 = prevw; x1 = knotw; y0 = prevh; y1 = knoth;
-      }
-      prevw = knotw; prevh = knoth;
-    }
+    cw += lw[j] * isw;
+    ch += lh[j] * ish;
+    const float knotw = cfg.bound * (2.f * cw - 1.f), knoth = cfg.bound * (2.f * ch - 1.f);
+    const bool take = (j < K) & ((inverse ? prevh : prevw) < v);  // k = #(knots < v) - 1 on the searched axis
+    k = take ? j : k;
+    x0 = take ? prevw : x0; x1 = take ? knotw : x1;
+    y0 = take ? prevh : y0; y1 = take ? knoth : y1;
+    prevw = (j < K) ? knotw : prevw;
+    prevh = (j < K) ? knoth : prevh;
   }
   if ((inverse ? prevh : prevw) < v) k = K;
   inside = (k >= 0) && (k < K);
@@ -82,8 +86,9 @@ __device__ __forceinline__ void rqs_finish(const SplineCfg<float>& cfg, bool inv
                                            float x0, float x1, float y0, float y1, float t0, float t1, float ladj0,
                                            float& out, float& ladj) {
   const int K = cfg.K;
-  const float d0 = (k > 0) ? exp_sfu(softclipf(t0, cfg.inv_ls1)) : 1.f;
-  const float d1 = (k < K - 1) ? exp_sfu(softclipf(t1, cfg.inv_ls1)) : 1.f;
+  // boundary derivatives are 1 = exp(0): select the argument, not the result (keeps the inline-asm exp unconditional)
+  const float d0 = exp_sfu((k > 0) ? softclipf(t0, cfg.inv_ls1) : 0.f);
+  const float d1 = exp_sfu((k < K - 1) ? softclipf(t1, cfg.inv_ls1) : 0.f);
   const float dx = x1 - x0, dy = y1 - y0;
   const float s = dy * __fdividef(1.f, dx);
   if (!inverse) {

@@ -6,6 +6,7 @@
 //   mode 3: fp16 hi/lo split with the A operand staged in TMEM (tcgen05.st) instead of shared memory
 //   mode 4: like mode 0, but the k-steps of A beyond the last full 64-wide K-block use 32-byte-swizzle blocks
 //   mode 100+: issue-rate timing (tc_issue_probe_kernel)
+#include "spline_reg.cuh"
 #include "tc_common.cuh"
 
 namespace mf {
@@ -213,6 +214,41 @@ __global__ void __launch_bounds__(128, 1) tc_issue_probe_kernel(float* __restric
   if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
+
+// Spline-scan throughput probe: every thread runs `iters` register splines (K = 16) back to back on one SM;
+// out[0] = cycles per spline seen by warp 0.  variant 0: knot scan only, 1: scan + finish (full spline).
+__global__ void spline_probe_kernel(float* __restrict__ out, int iters, int variant, float seed) {
+  SplineCfg<float> cfg;
+  cfg.K = 16; cfg.univariate = MF_UNIV_RQS; cfg.bound = 1.f;
+  cfg.inv_ls2 = 2.f / logf(1e-3f); cfg.inv_ls1 = 1.f / logf(1e-3f);
+  const float tf = seed * (float)(threadIdx.x % 29) * 0.01f;
+#define MF_PB(j) (tf + (float)(((j) * 13) % 31 - 15) * 0.1f)
+  float v = 0.01f * (threadIdx.x % 64) - 0.3f, acc = 0.f;
+  const long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) {
+    float lw[16], lh[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { lw[j] = MF_PB(j) + acc; lh[j] = MF_PB(16 + j) - acc; }
+    int k; bool inside; float x0, x1, y0, y1, l0;
+    float vv = v;
+    rqs_scan_reg<2>(lw, lh, cfg, false, vv, k, inside, x0, x1, y0, y1, l0);
+    if (variant == 1) {
+      float t0_, t1_, o, la;
+      float ld[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) ld[j] = MF_PB(32 + j) + acc;
+      select_pair<16>(ld, k, t0_, t1_);
+      rqs_finish(cfg, false, vv, k, inside, x0, x1, y0, y1, t0_, t1_, l0, o, la);
+      acc = 1e-6f * (o + la);
+    } else {
+      acc = 1e-6f * (x0 + y1 + (float)k);
+    }
+  }
+  const long long t1 = clock64();
+  if (threadIdx.x == 0) out[0] = (float)(t1 - t0) / (float)iters;
+  if (acc == 12345.f) out[1] = acc;
+}
+
 }  // namespace
 }  // namespace mf
 
@@ -223,6 +259,12 @@ extern "C" int mf_tc_probe_gemm(const float* d_a, const float* d_w, float* d_out
   MF_REQUIRE(d_a && d_w && d_out, "mf_tc_probe_gemm: null argument");
   MF_REQUIRE(k >= 16 && k % 16 == 0 && k <= 256, "mf_tc_probe_gemm: K=%d must be a multiple of 16 in 16..256", k);
   MF_REQUIRE(n >= 16 && n % 16 == 0 && n <= 256, "mf_tc_probe_gemm: N=%d must be a multiple of 16 in 16..256", n);
+  if (mode >= 200) {  // spline throughput: mode = 200 + 10 * variant + warps per scheduler (1..4); k = iterations
+    const int variant = (mode - 200) / 10, wps = (mode - 200) % 10;
+    MF_REQUIRE(d_out && wps >= 1 && wps <= 8 && variant <= 1, "mf_tc_probe_gemm: bad spline probe mode");
+    spline_probe_kernel<<<1, 128 * wps, 0, static_cast<cudaStream_t>(stream)>>>(d_out, k, variant, 1.0f);
+    return post_launch("spline_probe_kernel");
+  }
   if (mode >= 100) {  // timing: mode = 100 + 10 * (A in TMEM) + issuers; k = MMA count per issuer
     const int variant = (mode - 100) / 20, ts = ((mode - 100) / 10) % 2, issuers = (mode - 100) % 10;
     MF_REQUIRE(d_out && issuers >= 1 && issuers <= 2 && ts <= 1 && n <= 128 && n % 16 == 0, "mf_tc_probe_gemm: bad timing mode");
