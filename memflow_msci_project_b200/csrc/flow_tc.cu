@@ -75,6 +75,7 @@ struct TcLayout {
   int PFt;     // 3 * Kp
   int njobs;
   int in0_ksteps;
+  int xcol0;             // layer-0 operand columns: context at [0, C), zeros, x at [xcol0, xcol0 + D), zeros
   int in0_full;          // layer-0 operand: full 64-wide K-blocks (SWIZZLE_128B) ...
   int in0_tail;          // ... followed by this many single k-steps in SWIZZLE_32B blocks
   int in0_plane_bytes;   // bytes of one operand plane of one tile
@@ -94,9 +95,10 @@ int make_tc_layout(const mf_flow_desc& d, int gemm, TcLayout* L) {
   L->nsplit = (gemm == MF_GEMM_TC_3XF16) ? 3 : 1;
   L->Kp = round_up(d.bins, 8);
   L->PFt = 3 * L->Kp;
-  if (d.features + d.context > 128 || L->PFt > 128 || d.bins < 2) {
-    set_error("tensor-core flow path needs D+C <= 128 and 3*roundup(bins,8) <= 128 (got D+C=%d, bins=%d)",
-              d.features + d.context, d.bins);
+  L->xcol0 = round_up(d.context, 8);
+  if (L->xcol0 + d.features > 128 || L->PFt > 128 || d.bins < 2) {
+    set_error("tensor-core flow path needs roundup(C,8)+D <= 128 and 3*roundup(bins,8) <= 128 (got D=%d, C=%d, bins=%d)",
+              d.features, d.context, d.bins);
     return MF_EUNSUPPORTED;
   }
   for (int l = 0; l < d.n_hidden; ++l)
@@ -113,7 +115,7 @@ int make_tc_layout(const mf_flow_desc& d, int gemm, TcLayout* L) {
     j.in_dim = (l == 0) ? d.features + d.context : d.hidden[l - 1];
     j.out_dim = d.hidden[l];
     j.N = round_up(j.out_dim, 16);
-    j.ksteps = round_up(j.in_dim, 16) / 16;
+    j.ksteps = round_up(l == 0 ? L->xcol0 + d.features : j.in_dim, 16) / 16;
     j.nkb = (j.ksteps + 3) / 4;
     j.needs_a = 1; j.last = 0; j.feat0 = 0; j.nfeat = 0; j.layer = l; j.row0 = 0;
     j.w_off = woff; woff += (long long)j.nkb * parts * j.N * 128;
@@ -180,8 +182,10 @@ __global__ void flow_tc_pack_kernel(TcLayout L, TcPackArgs<T> a, unsigned char* 
         }
       }
       float v = 0.f;
-      if (src_row >= 0 && k < j.in_dim) {
-        const long long s = (long long)src_row * j.in_dim + k;
+      int src_col = k;  // layer 0: operand column -> zuko input column (x | context)
+      if (ji == 0) src_col = (k < L.C) ? L.D + k : ((k >= L.xcol0 && k < L.xcol0 + L.D) ? k - L.xcol0 : -1);
+      if (src_row >= 0 && src_col >= 0 && src_col < j.in_dim) {
+        const long long s = (long long)src_row * j.in_dim + src_col;
         v = a.m[j.layer][s] ? (float)a.w[j.layer][s] : 0.f;
       }
       const int kb = k >> 6;
@@ -552,7 +556,7 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
     const float* gx = static_cast<const float*>(args.x);
     const float* gc = static_cast<const float*>(args.ctx);
     float* gz = static_cast<float*>(args.z);
-    const int D = L.D, C = L.C;
+    const int D = L.D, C = L.C, xcol0 = L.xcol0;
     SplineCfg<float> cfg;
     cfg.K = L.K; cfg.univariate = args.univariate; cfg.bound = (float)args.bound;
     cfg.inv_ls2 = args.slope > 0.0 ? (float)(2.0 / log(args.slope)) : 0.f;
@@ -580,60 +584,101 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
       const long long g = tile0 + row;
       // working copy of x lives in the output buffer (each thread touches only its own row); when sampling,
       // gx holds the noise and the base sample a + b * noise is the starting point
-      if (valid && eset == 0)
-        for (int f = 0; f < D; ++f) {
-          float v0 = gx[g * D + f];
-          if (inverse)
-            v0 = (args.base == MF_BASE_DIAG_NORMAL) ? (float)bp.a[f] + (float)bp.b[f] * v0
-                                                   : (float)bp.a[f] + ((float)bp.b[f] - (float)bp.a[f]) * v0;
-          gz[g * D + f] = v0;
-          put1(row, f, v0);  // x columns of the layer-0 operand
+      MF_TRACE(gt == 0, 950 + 10 * t);
+      if (eset == 0)
+        for (int f0 = 0; f0 < D; f0 += 8) {  // eight loads in flight
+          float xv[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) xv[u] = (valid && f0 + u < D) ? gx[g * D + f0 + u] : 0.f;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int f = f0 + u;
+            if (f < D) {
+              float v0 = xv[u];
+              if (inverse && valid)
+                v0 = (args.base == MF_BASE_DIAG_NORMAL) ? (float)bp.a[f] + (float)bp.b[f] * v0
+                                                       : (float)bp.a[f] + ((float)bp.b[f] - (float)bp.a[f]) * v0;
+              if (valid) gz[g * D + f] = v0;
+              put1(row, xcol0 + f, v0);  // x columns of the layer-0 operand
+            }
+          }
         }
-      if (!valid && eset == 0)
-        for (int f = 0; f < D; ++f) put1(row, f, 0.f);
       float* gy = static_cast<float*>(args.work);  // sampling: target y of the transform being inverted
       float ladj = 0.f;
+      MF_TRACE(gt == 0, 951 + 10 * t);
       // ---- stage (ctx | 0) of the layer-0 operand once per tile; every MMA that read the previous tile's
       //      operand has retired (this group waited on the last accumulator of that tile)
       {
         const int kfill = L.in0_ksteps * 16;
         if (eset == 0)
-          for (int k = D + C; k < kfill; ++k) put1(row, k, 0.f);
-        // context: coalesced over the flat [rows x C] range of this tile, eight loads in flight per thread
-        int r = 0, c = gt;
-        while (C > 0 && c >= C) { c -= C; ++r; }
-        const int dr = C > 0 ? GT / C : 0, dc = C > 0 ? GT % C : 0;
+          for (int k = xcol0 + D; k < kfill; ++k) put1(row, k, 0.f);
+        // context: one 16-byte operand chunk (8 columns of one row) per thread and step, four chunks in flight;
+        // consecutive threads take consecutive chunks, so a warp reads a contiguous stretch of global memory
+        const int nchunk = xcol0 >> 3;  // chunks per row (the last one zero-padded when C % 8 != 0)
+        const int total = 128 * nchunk;
         const float* gct = gc + tile0 * C;
-        const int total = 128 * C, valid_elems = rows * C;
-        for (int idx0 = gt; idx0 < total; idx0 += 8 * GT) {
-          float v[8];
+        for (int q0 = gt; q0 < total; q0 += 4 * GT) {
+          float v[4][8];
+          int rr[4], kc[4];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int idx = idx0 + u * GT;
-            v[u] = (idx < valid_elems) ? __ldg(gct + idx) : 0.f;
+          for (int u = 0; u < 4; ++u) {
+            const int q = q0 + u * GT;
+            rr[u] = q / nchunk;
+            kc[u] = q - rr[u] * nchunk;
+            const bool live = (q < total) && (rr[u] < rows);
+            const float* src = gct + (long long)rr[u] * C + kc[u] * 8;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[u][e] = (live && kc[u] * 8 + e < C) ? __ldg(src + e) : 0.f;
           }
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            if (idx0 + u * GT < total) {
-              put1(r, D + c, v[u]);
-              r += dr; c += dc;
-              if (c >= C) { c -= C; ++r; }
+          for (int u = 0; u < 4; ++u) {
+            if (q0 + u * GT < total) {
+              const int r = rr[u], c8 = kc[u];
+              const uint32_t off = (c8 * 8 < kfull_cols)
+                                       ? (uint32_t)(c8 >> 3) * kKBlockBytes + (uint32_t)r * 128u + (uint32_t)(((c8 & 7) ^ (r & 7)) << 4)
+                                       : kFullBytes + (uint32_t)((c8 * 8 - kfull_cols) >> 4) * kTailBytes + (uint32_t)r * 32u +
+                                             (uint32_t)(((c8 & 1) ^ ((r >> 2) & 1)) << 4);
+              uint4 hi, lo;
+              if (NSPLIT == 3) {
+                tc::split_f16(v[u][0], v[u][1], hi.x, lo.x); tc::split_f16(v[u][2], v[u][3], hi.y, lo.y);
+                tc::split_f16(v[u][4], v[u][5], hi.z, lo.z); tc::split_f16(v[u][6], v[u][7], hi.w, lo.w);
+                *reinterpret_cast<uint4*>(a_hi + off) = hi;
+                *reinterpret_cast<uint4*>(a_lo + off) = lo;
+              } else {
+                hi.x = tc::pack_bf16(v[u][0], v[u][1]); hi.y = tc::pack_bf16(v[u][2], v[u][3]);
+                hi.z = tc::pack_bf16(v[u][4], v[u][5]); hi.w = tc::pack_bf16(v[u][6], v[u][7]);
+                *reinterpret_cast<uint4*>(a_hi + off) = hi;
+              }
             }
           }
         }
       }
+      MF_TRACE(gt == 0, 952 + 10 * t);
+      {  // pull this slot's next tile (x rows and context rows) into L2 while this one is being processed
+        const long long nt0 = (tile + 2 * (long long)gridDim.x) * 128;
+        if (nt0 < n) {
+          const long long nrows = min((long long)128, n - nt0);
+          const char* px = reinterpret_cast<const char*>(gx + nt0 * D);
+          const char* pc = reinterpret_cast<const char*>(gc + nt0 * C);
+          const long long xb = nrows * D * 4, cb = nrows * C * 4;
+          for (long long o = (long long)gt * 128; o < xb; o += (long long)GT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(px + o));
+          for (long long o = (long long)gt * 128; o < cb; o += (long long)GT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + o));
+        }
+      }
       if (EW > 1) group_bar(1 + t, GT);  // x written by warp set 0 is read by the other set below
+      float lp_base = 0.f;               // base log-density, accumulated as the last transform's outputs appear
       float bias_next;
       {
         const int tr0 = inverse ? (L.T - 1) : 0;
         bias_next = (gt < L.job[0].N) ? __ldg(bias_all + (size_t)tr0 * L.bias_stride + L.job[0].b_off + gt) : 0.f;
       }
+      MF_TRACE(gt == 0, 953 + 10 * t);
       for (int unit = 0; unit < n_units; ++unit) {
         const int tr = inverse ? (L.T - 1 - unit / sweeps) : unit;
         if (inverse && (unit % sweeps) == 0 && eset == 0) {  // y <- x, x <- 0  (AutoregressiveTransform._inverse)
           for (int f = 0; f < D; ++f) {
             if (valid) { gy[g * D + f] = gz[g * D + f]; gz[g * D + f] = 0.f; }
-            put1(row, f, 0.f);
+            put1(row, xcol0 + f, 0.f);
           }
         }
         const float* bias_t = bias_all + (size_t)tr * L.bias_stride;
@@ -737,10 +782,12 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
                 case 32: rqs_forward_tmem_reg<4>(ta, sbf, cfg, inverse, xv, out, la, bin, ins); break;
                 default: rqs_forward_tmem(ta, sbf, cfg, L.Kp, xv, out, la, bin, ins); break;
               }
-              put1(row, f, valid ? out : 0.f);  // next unit's layer-0 operand (its last reader, job 0, has retired)
+              put1(row, xcol0 + f, valid ? out : 0.f);  // next unit's layer-0 operand (its last reader, job 0, has retired)
               if (valid) {
                 gz[g * D + f] = out;
                 ladj += la;
+                if (EW == 1 && !inverse && unit == n_units - 1)
+                  lp_base += base_log_prob_1<float>(args.base, out, (float)bp.a[f], (float)bp.b[f]);
                 if (!inverse && args.bins) args.bins[((size_t)tr * n + g) * D + f] = (int8_t)bin;
                 if (!inverse && args.inside) args.inside[((size_t)tr * n + g) * D + f] = ins ? 1 : 0;
               }
@@ -760,8 +807,9 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
       if (valid && !inverse && eset == 0) {
         if (args.ladj) static_cast<float*>(args.ladj)[g] = ladj;
         if (args.logprob) {
-          float lp = 0.f;
-          for (int f = 0; f < D; ++f) lp += base_log_prob_1<float>(args.base, gz[g * D + f], (float)bp.a[f], (float)bp.b[f]);
+          float lp = lp_base;
+          if (EW > 1)
+            for (int f = 0; f < D; ++f) lp += base_log_prob_1<float>(args.base, gz[g * D + f], (float)bp.a[f], (float)bp.b[f]);
           static_cast<float*>(args.logprob)[g] = lp + ladj;
         }
       }

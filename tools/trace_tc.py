@@ -30,9 +30,11 @@ t0 = ev[0][0]
 # accumulator / 4JJ done; slot 1 epilogue 8JJ / 6JJ / 7JJ.  Printed as two columns, one per tile slot.
 def slot(i):
     if i < 300: return (i % 100) // 10
+    if i >= 950: return (i - 950) // 10
     return 0 if (i < 600 or i >= 900) else 1
 def label(i):
     if i < 300: return ("MMA ready  " if i < 200 else "MMA issued ") + str(i % 10)
+    if i >= 950: return "   tile " + ["begin", "x staged", "ctx staged", "prefetch+bias done"][(i - 950) % 10]
     if i >= 900: return "   spline " + ["start", "ld w/h done", "scan done", "deriv sel done", "finish done"][i - 900]
     k = (i - 300 * slot(i)) // 100
     return {3: "EPI accfull ", 4: "EPI done    ", 5: "EPI wait    "}[k] + str(i % 100)
