@@ -83,6 +83,7 @@ class FlatInvertiblePhasespace(VirtualPhaseSpaceGenerator):
         self.compute = {"f64": _cabi.MF_COMPUTE_F64, "f32": _cabi.MF_COMPUTE_F32}[compute]
         self.reference_dtypes = reference_dtypes
         self.quirks = MF_QUIRK_F32_VOLUME if reference_quirks else 0
+        self.reference_quirks = bool(reference_quirks)  # also selects the autograd graph (phasespace/_autograd.py)
         self.check_inputs = check_inputs
         self._desc_cache = {}
 

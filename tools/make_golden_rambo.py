@@ -77,6 +77,20 @@ def main():
                                                  rap_maxcut=2.4)
             out["weight_cuts"] = wc.numpy()
             out["cuts"] = np.asarray([30.0, 0.4, 2.4])
+        # gradients of the reference's own autograd graph (requires_grad=True path, rambo_generator.py:175)
+        if n in (3, 4):
+            rg = r32[:128].double().clone().requires_grad_(True)
+            gm, gw_, gx1, gx2 = ps.get_momenta_from_ps(rg, requires_grad=True)
+            gen_ = torch.Generator().manual_seed(seed + 100)
+            cm = torch.randn(gm.shape, dtype=torch.float64, generator=gen_)
+            cw = torch.randn(gw_.shape, dtype=torch.float64, generator=gen_) / gw_.detach()
+            c1 = torch.randn(gx1.shape, dtype=torch.float64, generator=gen_)
+            c2 = torch.randn(gx2.shape, dtype=torch.float64, generator=gen_)
+            ((gm * cm).sum() + (gw_ * cw).sum() + (gx1 * c1).sum() + (gx2 * c2).sum()).backward()
+            np.savez_compressed(os.path.join(outdir, f"rambo_grad_{name}.npz"), masses=np.asarray(masses, dtype=np.float32),
+                                r=rg.detach().numpy(), cot_momenta=cm.numpy(), cot_weight=cw.numpy(), cot_x1=c1.numpy(),
+                                cot_x2=c2.numpy(), grad_r=rg.grad.numpy())
+            print(f"{name}: reference gradient fixture written, max |grad| per column {rg.grad.abs().max(0).values.numpy().round(2)}")
         # oracle cross-check
         desc = build_rambo_desc(mt, 13000)
         omom, ow, olw, ox1, ox2, ofl = orc.forward(desc, r32.double().numpy())
