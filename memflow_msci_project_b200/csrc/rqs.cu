@@ -29,9 +29,12 @@ __device__ __forceinline__ void rqs_row_reg(const float* p, const SplineCfg<floa
   float lw[KP], lh[KP], ld[KP];
 #pragma unroll
   for (int j = 0; j < KP; ++j) {
-    lw[j] = (j < K) ? p[j] : 0.f;
-    lh[j] = (j < K) ? p[K + j] : 0.f;
-    ld[j] = (j < K - 1) ? p[2 * K + j] : 0.f;
+    // clamped indices instead of guarded loads (a conditional load compiles to one branch per element); the
+    // duplicated entries beyond K are masked out inside the spline
+    const int jw = min(j, K - 1), jd = max(min(j, K - 2), 0);
+    lw[j] = p[jw];
+    lh[j] = p[K + jw];
+    ld[j] = p[2 * K + jd];
   }
   rqs_eval_reg<NCH>(lw, lh, ld, cfg, inverse, v, out, la, bin, ins);
 }
@@ -53,7 +56,7 @@ __device__ __forceinline__ void rqs_row<float>(float* p, const SplineCfg<float>&
 }
 
 template <typename T>
-__global__ void rqs_kernel(const T* __restrict__ g_par, const T* __restrict__ g_x, long long n, int K, int univariate,
+__global__ void __launch_bounds__(kRqsRows, 2) rqs_kernel(const T* __restrict__ g_par, const T* __restrict__ g_x, long long n, int K, int univariate,
                            double bound, double slope, int inverse, T* __restrict__ g_y, T* __restrict__ g_ladj,
                            int8_t* __restrict__ g_bins, uint8_t* __restrict__ g_inside, int use_tma) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -111,7 +114,7 @@ extern "C" int mf_rqs_transform(const void* d_params, const void* d_x, int64_t n
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int P = 3 * bins - 1;
   const size_t esz = dtype == MF_F32 ? 4 : 8;
-  int rows = kRqsRows;
+  int rows = dtype == MF_F32 ? 128 : kRqsRows;  // fp32: 128 rows x 128 registers -> four CTAs per SM (measured best)
   while (rows > 32 && (size_t)rows * P * esz > 56 * 1024) rows >>= 1;  // <= 56 KB per CTA: four CTAs per SM
   const size_t smem = (size_t)rows * P * esz;
   MF_REQUIRE(smem <= 220 * 1024, "mf_rqs_transform: bins too large for shared memory");
