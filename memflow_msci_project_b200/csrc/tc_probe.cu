@@ -162,7 +162,8 @@ __global__ void __launch_bounds__(128, 1) tc_issue_probe_kernel(float* __restric
   const int tid = threadIdx.x, warp = tid >> 5;
   for (int i = tid; i < (16384 + 32768) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
   if (tid == 0) {
-    for (int i = 0; i < 4; ++i) mbar_init(&bar[i], 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&bar[i], 1);
+    for (int i = 2; i < 4; ++i) mbar_init(&bar[i], 1000000);
     fence_mbar_init();
   }
   if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
@@ -176,6 +177,22 @@ __global__ void __launch_bounds__(128, 1) tc_issue_probe_kernel(float* __restric
     const uint32_t a_s = smem_u32(smem), b_s = smem_u32(smem + 16384);
     const uint32_t d_tmem = tmem + warp * 256, a_tmem = d_tmem + 128;
     const long long t0 = clock64();
+    if (variant == 2) {  // like variant 1, with a tcgen05.commit to a spare barrier after every 12 MMAs
+      if (tc::elect_one()) {
+        uint64_t db[4], da[4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) { db[ks] = tc::make_smem_desc(b_s + ks * 32u); da[ks] = tc::make_smem_desc(a_s + ks * 32u); }
+        for (int i = 0; i < count; i += 4) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            if (ts) tc::mma_f16_ts(d_tmem, a_tmem + ks * 8u, db[ks], idesc, 1u);
+            else tc::mma_f16_ss(d_tmem, da[ks], db[ks], idesc, 1u);
+          }
+          if ((i + 4) % 12 == 0) tc::mma_commit(&bar[2 + warp]);
+        }
+      }
+      __syncwarp();
+    } else
     if (variant == 1) {  // the whole issue loop inside one elected thread, four k-steps unrolled
       if (tc::elect_one()) {
         uint64_t db[4], da[4];
@@ -267,7 +284,7 @@ extern "C" int mf_tc_probe_gemm(const float* d_a, const float* d_w, float* d_out
   }
   if (mode >= 100) {  // timing: mode = 100 + 10 * (A in TMEM) + issuers; k = MMA count per issuer
     const int variant = (mode - 100) / 20, ts = ((mode - 100) / 10) % 2, issuers = (mode - 100) % 10;
-    MF_REQUIRE(d_out && issuers >= 1 && issuers <= 2 && ts <= 1 && n <= 128 && n % 16 == 0, "mf_tc_probe_gemm: bad timing mode");
+    MF_REQUIRE(d_out && issuers >= 1 && issuers <= 2 && ts <= 1 && variant <= 2 && n <= 128 && n % 16 == 0, "mf_tc_probe_gemm: bad timing mode");
     const size_t sm = 16384 + 32768;
     MF_CUDA_CHECK(cudaFuncSetAttribute(tc_issue_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     tc_issue_probe_kernel<<<1, 128, sm, static_cast<cudaStream_t>(stream)>>>(d_out, k, n, ts, issuers, variant);

@@ -14,4 +14,9 @@ timeout 100 python tools/profile_tc.py > gpurun_out/prof_tc_plain.log 2>&1 && \
 timeout 500 ncu --set full --clock-control none --import-source on -k regex:flow_tc_kernel -s 1 -c 1 -o gpurun_out/prof_tc python tools/profile_tc.py > gpurun_out/ncu_tc.log 2>&1
 timeout 100 python tools/profile_target.py rambo > gpurun_out/prof_rambo_plain.log 2>&1 && \
 timeout 500 ncu --set full --clock-control none --import-source on -k regex:"rambo_forward|rambo_inverse" -c 8 -o gpurun_out/prof_rambo python tools/profile_target.py rambo > gpurun_out/ncu_rambo.log 2>&1
+timeout 100 python tools/probe_issue.py > gpurun_out/probe_issue.txt 2>&1
+timeout 100 python tools/probe_issue_fixed.py >> gpurun_out/probe_issue.txt 2>&1
+timeout 100 python tools/probe_spline.py > gpurun_out/probe_spline.txt 2>&1
+timeout 400 python tools/bench_train.py --steps 3 --warmup 2 > gpurun_out/train.jsonl 2>&1
+timeout 300 python tools/bench_train.py --steps 3 --warmup 2 --no-sampling-loss >> gpurun_out/train.jsonl 2>&1
 ls -la gpurun_out | tail -20
