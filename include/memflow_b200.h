@@ -176,6 +176,7 @@ int mf_rambo_get_ps(const mf_rambo_desc* desc, const void* d_momenta, const void
 #define MF_GEMM_EXACT 0  /* CUDA-core FMA in the I/O dtype (fp32 or fp64): bit-for-bit class of torch fp32 */
 #define MF_GEMM_TC_3XF16 1 /* tcgen05, fp16 hi/lo split operands, 3 MMAs per product, fp32 accumulate */
 #define MF_GEMM_TC_BF16 2  /* tcgen05, bf16 operands, fp32 accumulate: throughput mode */
+#define MF_GEMM_MMA_3XF16 3 /* warp-level mma.sync, fp16 hi/lo split, 3 MMAs per product: hidden widths 129..512 (fp32) */
 
 /*
  * Static description of one flow = zuko.flows.NSF(features, context, transforms, bins,

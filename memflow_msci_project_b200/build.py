@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(OUT_DIR, "libmemflow_b200.so")
-SOURCES = ["abi.cu", "rambo.cu", "flow.cu", "reduce.cu", "tc_probe.cu", "flow_tc.cu", "rqs.cu"]
+SOURCES = ["abi.cu", "rambo.cu", "flow.cu", "reduce.cu", "tc_probe.cu", "flow_tc.cu", "rqs.cu", "flow_mma.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -28,6 +28,8 @@ FLAGS = [
 EXTRA_FLAGS = {"rambo.cu": ["--use_fast_math"]}
 if os.environ.get("MF_TC_TRACE") == "1":  # cycle-level trace of the tensor-core flow kernel (tools/trace_tc.py)
     EXTRA_FLAGS["flow_tc.cu"] = ["-DMF_TC_TRACE"]
+if os.environ.get("MF_MMA_NOSPLINE") == "1":  # timing experiment: wide-flow kernel without the spline arithmetic
+    EXTRA_FLAGS["flow_mma.cu"] = ["-DMF_MMA_NOSPLINE"]
 
 
 def _stale(target, deps):

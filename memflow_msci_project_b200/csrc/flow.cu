@@ -362,10 +362,13 @@ int launch_flow(const FlowLayout& L, const FlowKernelArgs& a, const BaseParams& 
   return MF_EUNSUPPORTED;
 }
 
+inline bool is_tcgen05(int gemm) { return gemm == MF_GEMM_TC_3XF16 || gemm == MF_GEMM_TC_BF16; }
+
 int check_flow_common(const mf_flow_desc* desc, int dtype, int gemm) {
   MF_REQUIRE(desc != nullptr, "null flow descriptor");
   MF_REQUIRE(dtype == MF_F32 || dtype == MF_F64, "unsupported dtype %d", dtype);
-  MF_REQUIRE(gemm == MF_GEMM_EXACT || gemm == MF_GEMM_TC_3XF16 || gemm == MF_GEMM_TC_BF16, "unknown gemm mode %d", gemm);
+  MF_REQUIRE(gemm == MF_GEMM_EXACT || gemm == MF_GEMM_TC_3XF16 || gemm == MF_GEMM_TC_BF16 || gemm == MF_GEMM_MMA_3XF16,
+             "unknown gemm mode %d", gemm);
   if (gemm != MF_GEMM_EXACT && dtype != MF_F32) {
     set_error("tensor-core gemm modes take fp32 tensors (fp64 flows use MF_GEMM_EXACT)");
     return MF_EUNSUPPORTED;
@@ -382,7 +385,7 @@ extern "C" {
 
 int64_t mf_flow_blob_bytes(const mf_flow_desc* desc, int dtype, int gemm) {
   if (check_flow_common(desc, dtype, gemm) != MF_OK) return -1;
-  if (gemm != MF_GEMM_EXACT) {
+  if (is_tcgen05(gemm)) {
     long long b = 0;
     return flow_tc_blob_bytes(*desc, gemm, &b) == MF_OK ? (int64_t)b : -1;
   }
@@ -397,7 +400,7 @@ int mf_flow_pack_weights(const mf_flow_desc* desc, const void* const* d_weights,
   int rc = check_flow_common(desc, dtype, gemm);
   if (rc != MF_OK) return rc;
   MF_REQUIRE(d_weights && d_biases && d_masks && d_blob, "mf_flow_pack_weights: null argument");
-  if (gemm != MF_GEMM_EXACT)
+  if (is_tcgen05(gemm))
     return flow_tc_pack(*desc, d_weights, d_biases, d_masks, gemm, d_blob, blob_bytes, static_cast<cudaStream_t>(stream));
   FlowLayout L;
   rc = make_flow_layout(*desc, &L);
@@ -439,7 +442,7 @@ static int flow_run(const mf_flow_desc* desc, const FlowKernelArgs& a, int dtype
   FlowLayout L;
   rc = make_flow_layout(*desc, &L);
   if (rc != MF_OK) return rc;
-  if (gemm != MF_GEMM_EXACT) {
+  if (is_tcgen05(gemm)) {
     MF_REQUIRE(desc->context == 0 || a.ctx != nullptr || a.n == 0, "context pointer is null but context=%d", desc->context);
     MF_REQUIRE(desc->bound > 0.0, "bound must be positive");
     if (a.n == 0) return MF_OK;
@@ -453,6 +456,7 @@ static int flow_run(const mf_flow_desc* desc, const FlowKernelArgs& a, int dtype
   BaseParams bp;
   for (int f = 0; f < MF_MAX_FEATURES; ++f) { bp.a[f] = desc->base_a[f]; bp.b[f] = desc->base_b[f]; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (gemm == MF_GEMM_MMA_3XF16) return flow_mma_run(L, a, bp, st);
   return dtype == MF_F32 ? launch_flow<float>(L, a, bp, st) : launch_flow<double>(L, a, bp, st);
 }
 
@@ -474,7 +478,7 @@ int mf_flow_log_prob(const mf_flow_desc* desc, const void* d_blob, const void* d
 
 int64_t mf_flow_workspace_bytes(const mf_flow_desc* desc, int64_t n, int dtype, int gemm, int op) {
   if (check_flow_common(desc, dtype, gemm) != MF_OK || n < 0) return -1;
-  if (gemm == MF_GEMM_EXACT) return 0;
+  if (!is_tcgen05(gemm)) return 0;
   return flow_tc_workspace_bytes(*desc, n, gemm, op);
 }
 

@@ -104,6 +104,12 @@ struct BaseParams {
 };
 
 
+// warp-level MMA path for wide hyper-networks (flow_mma.cu); uses the blob of the exact path
+struct FlowLayout;
+struct FlowKernelArgs;
+struct BaseParams;
+int flow_mma_run(const FlowLayout& L, const FlowKernelArgs& a, const BaseParams& bp, cudaStream_t st);
+
 // tcgen05 path (flow_tc.cu)
 int flow_tc_blob_bytes(const mf_flow_desc& d, int gemm, long long* bytes);
 int flow_tc_pack(const mf_flow_desc& d, const void* const* w, const void* const* b, const uint8_t* const* m,

@@ -266,6 +266,40 @@ __global__ void spline_probe_kernel(float* __restrict__ out, int iters, int vari
   if (acc == 12345.f) out[1] = acc;
 }
 
+
+// Legacy warp-level MMA rate probe: every warp issues `iters` x 8 independent mma.sync.m16n8k8 TF32 (fp32 accumulate).
+// out[0] = cycles per MMA per scheduler.  f16 = 1: m16n8k16 fp16 instead.
+__global__ void mma_sync_probe_kernel(float* __restrict__ out, int iters, int f16) {
+  float c[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { c[i][0] = c[i][1] = c[i][2] = c[i][3] = 0.f; }
+  uint32_t a[4] = {threadIdx.x, threadIdx.x * 3u, 7u, 11u}, b[2] = {threadIdx.x * 5u, 13u};
+  const long long t0 = clock64();
+  if (f16) {
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[i][0]), "+f"(c[i][1]), "+f"(c[i][2]), "+f"(c[i][3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+    }
+  } else {
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[i][0]), "+f"(c[i][1]), "+f"(c[i][2]), "+f"(c[i][3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+    }
+  }
+  const long long t1 = clock64();
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1] + c[i][2] + c[i][3];
+  if (threadIdx.x == 0) out[0] = (float)(t1 - t0) / (float)(iters * 8) / (float)(blockDim.x / 128);
+  if (s == 12345.f) out[1] = s;
+}
+
 }  // namespace
 }  // namespace mf
 
@@ -276,6 +310,12 @@ extern "C" int mf_tc_probe_gemm(const float* d_a, const float* d_w, float* d_out
   MF_REQUIRE(d_a && d_w && d_out, "mf_tc_probe_gemm: null argument");
   MF_REQUIRE(k >= 16 && k % 16 == 0 && k <= 256, "mf_tc_probe_gemm: K=%d must be a multiple of 16 in 16..256", k);
   MF_REQUIRE(n >= 16 && n % 16 == 0 && n <= 256, "mf_tc_probe_gemm: N=%d must be a multiple of 16 in 16..256", n);
+  if (mode >= 300) {  // legacy mma.sync rate: mode = 300 + warps per scheduler; k = iterations
+    const int wps = (mode - 300) % 10, f16 = (mode - 300) / 10;
+    MF_REQUIRE(d_out && wps >= 1 && wps <= 8 && f16 <= 1, "mf_tc_probe_gemm: bad mma.sync probe mode");
+    mma_sync_probe_kernel<<<1, 128 * wps, 0, static_cast<cudaStream_t>(stream)>>>(d_out, k, f16);
+    return post_launch("mma_sync_probe_kernel");
+  }
   if (mode >= 200) {  // spline throughput: mode = 200 + 10 * variant + warps per scheduler (1..4); k = iterations
     const int variant = (mode - 200) / 10, wps = (mode - 200) % 10;
     MF_REQUIRE(d_out && wps >= 1 && wps <= 8 && variant <= 1, "mf_tc_probe_gemm: bad spline probe mode");

@@ -26,7 +26,7 @@ MF_MAX_FEATURES = 64
 
 UNIV_RQS, UNIV_CIRCULAR_RQS, UNIV_PS_RQS = 0, 1, 2
 BASE_DIAG_NORMAL, BASE_BOX_UNIFORM = 0, 1
-GEMM_EXACT, GEMM_TC_3XF16, GEMM_TC_BF16 = 0, 1, 2
+GEMM_EXACT, GEMM_TC_3XF16, GEMM_TC_BF16, GEMM_MMA_3XF16 = 0, 1, 2, 3
 
 
 class FlowDesc(ctypes.Structure):
@@ -261,8 +261,8 @@ class NormalizingFlow:
         cb = cb.to(dtype).contiguous() if cb is not None else None
         N, D = xb.shape
         gemm = m.effective_gemm(dtype)
-        if self._ctx_group > 1:
-            gemm = GEMM_EXACT  # context grouping lives on the CUDA-core path
+        if self._ctx_group > 1 and gemm in (GEMM_TC_3XF16, GEMM_TC_BF16):
+            gemm = GEMM_EXACT  # context grouping is not implemented in the tcgen05 kernel
         desc, blob = m.packed(xb.device, dtype, gemm=gemm)
         desc = self._with_group(desc)
         z = torch.empty_like(xb)
@@ -304,7 +304,7 @@ class NormalizingFlow:
         zb = zb.contiguous()
         cb = cb.to(dtype).contiguous() if cb is not None else None
         gemm = m.effective_gemm(dtype, sampling=True)
-        if self._ctx_group > 1:
+        if self._ctx_group > 1 and gemm in (GEMM_TC_3XF16, GEMM_TC_BF16):
             gemm = GEMM_EXACT
         desc, blob = m.packed(zb.device, dtype, identity_base=True, gemm=gemm)
         desc = self._with_group(desc)
@@ -390,7 +390,7 @@ class MAF(nn.Module):
         else:
             args = base_args if base_args is not None else [torch.zeros(features), torch.ones(features)]
             self.base = Unconditional(base, *args)  # the fork registers base_args as parameters
-        self.gemm = {"exact": GEMM_EXACT, "tc_3xf16": GEMM_TC_3XF16, "tc_bf16": GEMM_TC_BF16}[gemm]
+        self.gemm = {"exact": GEMM_EXACT, "tc_3xf16": GEMM_TC_3XF16, "tc_bf16": GEMM_TC_BF16, "mma_3xf16": GEMM_MMA_3XF16}[gemm]
         self._blob_cache = {}
         self._desc_cache = {}
         self._register_load_state_dict_pre_hook(self._rename_legacy_keys)
@@ -465,7 +465,7 @@ class MAF(nn.Module):
         exact CUDA-core kernel."""
         if dtype != torch.float32:
             return GEMM_EXACT
-        if sampling and self.gemm != GEMM_EXACT and self.core_transforms()[0].bins > 32:
+        if sampling and self.gemm in (GEMM_TC_3XF16, GEMM_TC_BF16) and self.core_transforms()[0].bins > 32:
             return GEMM_EXACT
         return self.gemm
 

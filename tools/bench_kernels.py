@@ -82,8 +82,10 @@ def main():
         c = torch.randn(n_obj, C, device=dev)
         with torch.no_grad():
             for gname, gmode in (("exact", flows.modules.GEMM_EXACT), ("tc_3xf16", flows.modules.GEMM_TC_3XF16),
-                                 ("tc_bf16", flows.modules.GEMM_TC_BF16)):
-                if gmode != flows.modules.GEMM_EXACT and max(H) > 128:
+                                 ("tc_bf16", flows.modules.GEMM_TC_BF16), ("mma_3xf16", flows.modules.GEMM_MMA_3XF16)):
+                if gmode in (flows.modules.GEMM_TC_3XF16, flows.modules.GEMM_TC_BF16) and max(H) > 128:
+                    continue
+                if gmode == flows.modules.GEMM_MMA_3XF16 and name not in ("UF", "TF-1D", "TF-A"):
                     continue
                 flow.gemm = gmode
                 ms = timeit(lambda: flow(c).log_prob(x), reps=5)
@@ -93,8 +95,11 @@ def main():
                                 bytes_per_object=4 * (D + C) + 4, achieved_gbs=n_obj * (4 * (D + C) + 4) / (ms * 1e-3) / 1e9))
             flow.gemm = flows.modules.GEMM_EXACT
             nz = torch.randn(n_obj, D, device=dev)
-            for gname, gmode in (("exact", flows.modules.GEMM_EXACT), ("tc_3xf16", flows.modules.GEMM_TC_3XF16)):
-                if gmode != flows.modules.GEMM_EXACT and (max(H) > 128 or K > 32):
+            for gname, gmode in (("exact", flows.modules.GEMM_EXACT), ("tc_3xf16", flows.modules.GEMM_TC_3XF16),
+                                 ("mma_3xf16", flows.modules.GEMM_MMA_3XF16)):
+                if gmode == flows.modules.GEMM_TC_3XF16 and (max(H) > 128 or K > 32):
+                    continue
+                if gmode == flows.modules.GEMM_MMA_3XF16 and name not in ("UF", "TF-1D", "TF-A"):
                     continue
                 flow.gemm = gmode
                 ms = timeit(lambda: flow(c).sample_from_noise(nz), reps=3)
