@@ -172,6 +172,101 @@ __device__ __forceinline__ void mma_layer(const float* A, int lda, int K, const 
   __syncthreads();
 }
 
+
+// One univariate spline evaluated by FOUR consecutive lanes (a quad): lane q owns bins [q*Kq, (q+1)*Kq).  The
+// logits p = [K widths | K heights | K-1 derivatives] live in shared memory and are overwritten in place with the
+// upper knots of every bin, so that any lane can read the two knots of the selected bin.  Same operations as
+// rqs_univariate (flow_common.cuh: soft clip, max-subtracted softmax, cumulative knots, k = #(knots < v) - 1,
+// rational-quadratic map); only the order of the softmax / prefix sums differs (quad tree instead of sequential).
+// All 32 lanes of the warp must call it; every lane of the quad returns the result.
+__device__ __forceinline__ void rqs_quad(float* p, const SplineCfg<float>& cfg, bool inverse, float v, float& out,
+                                         float& ladj, int& bin, bool& inside) {
+  const int K = cfg.K, lane = threadIdx.x & 31, q = lane & 3, qbase = lane & ~3;
+  const int Kq = (K + 3) >> 2, j0 = min(K, q * Kq), j1 = min(K, j0 + Kq);
+  float ladj0 = 0.f;
+  if (!inverse) {
+    if (cfg.univariate == MF_UNIV_CIRCULAR_RQS) v = circular_wrap(v, cfg.bound);
+    if (cfg.univariate == MF_UNIV_PS_RQS) { v = (v + 1.f) * 0.5f; ladj0 = -0.6931471805599453f; }
+  }
+  float* pw = p;
+  float* ph = p + K;
+  float* pd = p + 2 * K;
+  float mw = -INFINITY, mh = -INFINITY;
+  for (int j = j0; j < j1; ++j) {
+    const float a = softclip(pw[j], cfg.inv_ls2), b = softclip(ph[j], cfg.inv_ls2);
+    pw[j] = a; ph[j] = b;
+    mw = fmaxf(mw, a); mh = fmaxf(mh, b);
+  }
+#pragma unroll
+  for (int o = 1; o < 4; o <<= 1) {
+    mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, o));
+    mh = fmaxf(mh, __shfl_xor_sync(0xffffffffu, mh, o));
+  }
+  float sw = 0.f, sh = 0.f;
+  for (int j = j0; j < j1; ++j) {
+    const float a = expf(pw[j] - mw), b = expf(ph[j] - mh);
+    pw[j] = a; ph[j] = b;
+    sw += a; sh += b;
+  }
+#pragma unroll
+  for (int o = 1; o < 4; o <<= 1) {
+    sw += __shfl_xor_sync(0xffffffffu, sw, o);
+    sh += __shfl_xor_sync(0xffffffffu, sh, o);
+  }
+  // normalised local prefix sums, then the quad-exclusive offsets
+  float cw = 0.f, ch = 0.f;
+  for (int j = j0; j < j1; ++j) {
+    cw += pw[j] / sw; ch += ph[j] / sh;
+    pw[j] = cw; ph[j] = ch;
+  }
+  float ow = 0.f, oh = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float tw = __shfl_sync(0xffffffffu, cw, qbase + i), th = __shfl_sync(0xffffffffu, ch, qbase + i);
+    if (i < q) { ow += tw; oh += th; }
+  }
+  int count = (q == 0 && -cfg.bound < v) ? 1 : 0;  // left edge knot
+  for (int j = j0; j < j1; ++j) {
+    const float kw = cfg.bound * (2.f * (ow + pw[j]) - 1.f), kh = cfg.bound * (2.f * (oh + ph[j]) - 1.f);
+    pw[j] = kw; ph[j] = kh;
+    count += ((inverse ? kh : kw) < v) ? 1 : 0;
+  }
+#pragma unroll
+  for (int o = 1; o < 4; o <<= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
+  __syncwarp();
+  int k = count - 1;
+  inside = (k >= 0) && (k < K);
+  k = k < 0 ? k + K : (k >= K ? k - K : k);
+  bin = k;
+  const float x0 = (k == 0) ? -cfg.bound : pw[k - 1], x1 = pw[k];
+  const float y0 = (k == 0) ? -cfg.bound : ph[k - 1], y1 = ph[k];
+  const float d0 = (k == 0) ? 1.f : expf(softclip(pd[k - 1], cfg.inv_ls1));
+  const float d1 = (k == K - 1) ? 1.f : expf(softclip(pd[k], cfg.inv_ls1));
+  const float s = (y1 - y0) / (x1 - x0);
+  const float msk = inside ? 1.f : 0.f;
+  if (!inverse) {
+    const float z = msk * (v - x0) / (x1 - x0);
+    const float omz = 1.f - z;
+    const float den = s + (d0 + d1 - 2.f * s) * z * omz;
+    const float y = y0 + (y1 - y0) * (s * z * z + d0 * z * omz) / den;
+    const float jac = s * s * (2.f * s * z * omz + d0 * omz * omz + d1 * z * z) / (den * den);
+    out = inside ? y : v;
+    ladj = msk * logf(jac) + ladj0;
+  } else {
+    const float y_ = msk * (v - y0);
+    const float a = (y1 - y0) * (s - d0) + y_ * (d0 + d1 - 2.f * s);
+    const float b = (y1 - y0) * d0 - y_ * (d0 + d1 - 2.f * s);
+    const float c = -s * y_;
+    const float z = 2.f * c / (-b - sqrtf(b * b - 4.f * a * c));
+    float x = x0 + z * (x1 - x0);
+    x = inside ? x : v;
+    if (cfg.univariate == MF_UNIV_CIRCULAR_RQS) x = circular_wrap(x, cfg.bound);
+    if (cfg.univariate == MF_UNIV_PS_RQS) x = 2.f * x - 1.f;
+    out = x;
+    ladj = 0.f;
+  }
+}
+
 struct WideSmem {
   int ld0, ldA, ldP;
   size_t in0, act, par, wst, xcur, xnew, ytgt, ladj, total;  // offsets in floats
@@ -281,22 +376,24 @@ flow_mma_kernel(const __grid_constant__ FlowLayout L, const __grid_constant__ Fl
           const float* wl = tb + L.w_off[Lh] + (size_t)gch * L.chunk_stride;
           const float* bl = tb + L.b_off[Lh] + (size_t)gch * L.chunk_stride;
           mma_layer<1, false>(cur, lda, L.kpad[Lh], wl, L.pw_ld, L.pw_ld, bl, par, S.ldP, false, wstage);
-          // ---- splines of the features of this chunk: thread per (row, feature)
+          // ---- splines of the features of this chunk: four lanes per (row, feature)
           const int f0 = gch * L.fpc;
           const int nf = min(L.fpc, D - f0);
-          for (int p = tid; p < kWM * nf; p += kWThreads) {
-            const int m = p % kWM, fl = p / kWM, f = f0 + fl;
-            if (m < rows) {
-              float* pp = par + (size_t)m * S.ldP + fl * L.PF;
-              const float v = (args.mode == 0) ? xcur[(size_t)m * D + f] : ytgt[(size_t)m * D + f];
-              float out, la;
-              int bin;
-              bool ins;
+          for (int p0 = 0; p0 < kWM * nf; p0 += kWThreads / 4) {  // warp-uniform trip count
+            const int p = p0 + (tid >> 2);
+            const int m = p % kWM, fl = min(p / kWM, nf - 1), f = f0 + fl;
+            const bool live = (p < kWM * nf) && (m < rows);
+            float* pp = par + (size_t)m * S.ldP + fl * L.PF;
+            const float v = (args.mode == 0) ? xcur[(size_t)m * D + f] : ytgt[(size_t)m * D + f];
+            float out, la;
+            int bin;
+            bool ins;
 #ifdef MF_MMA_NOSPLINE  // timing experiment only: skip the spline arithmetic
-              out = v + pp[0] * 1e-9f; la = 0.f; bin = 0; ins = true;
+            out = v + pp[0] * 1e-9f; la = 0.f; bin = 0; ins = true;
 #else
-              rqs_univariate<float>(pp, 1, cfg, args.mode == 1, v, out, la, bin, ins);
+            rqs_quad(pp, cfg, args.mode == 1, v, out, la, bin, ins);
 #endif
+            if (live && (tid & 3) == 0) {
               xnew[(size_t)m * D + f] = out;
               if (args.mode == 0) {
                 ytgt[(size_t)m * D + f] = la;  // per-feature ladj, summed in feature order below
