@@ -19,12 +19,12 @@ MASSES4 = [125.25, 172.5, 172.5, 1e-5]
 MASSES8 = [4.7, 4.7, 4.7, 1e-3, 1e-3, 4.7, 1e-3, 1e-3]
 
 
-def uf_flow(dev):
+def uf_flow(dev, gemm):
     """configs/flow_pretrain_labframe_sampling/flow_labframe_sampling_v3f.yaml:80-94"""
     torch.manual_seed(11)
     return flows.NSF(features=10, context=16, transforms=6, bins=40, hidden_features=[512] * 2, randperm=True,
                      base=flows.DiagNormal, base_args=[torch.zeros(10), 0.35 * torch.ones(10)],
-                     univariate_kwargs={"bound": 1.1}, passes=2).to(dev)
+                     univariate_kwargs={"bound": 1.1}, passes=2, gemm=gemm).to(dev)
 
 
 def main():
@@ -34,6 +34,8 @@ def main():
     ap.add_argument("--events5", type=int, default=1_000, help="config 5: events (x points each), sharded over ranks")
     ap.add_argument("--points5", type=int, default=1_000)
     ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--gemm", default="mma_3xf16", choices=["exact", "mma_3xf16"],
+                    help="conditioner arithmetic of the width-512 unfolding flow (tcgen05 modes stop at width 128)")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -81,7 +83,7 @@ def main():
             # config 3: unfolding flow sample -> sigmoid -> RAMBO forward -> get_PS (RAMBO inverse + mask) -> log_prob
             a, b = shard_range(args.events3, rank, world)
             N = b - a
-            flow = uf_flow(dev)
+            flow = uf_flow(dev, args.gemm)
             ps = PhaseSpace(13000, [21, 21], [25, 6, -6, 21], final_masses=torch.tensor(MASSES4), dev=dev, check_inputs=False)
             g = torch.Generator(device=dev).manual_seed(11 + rank)
             noise = torch.randn(N, 10, generator=g, device=dev)
@@ -97,13 +99,13 @@ def main():
                 return lp, mask
 
             ms = timed(step3)
-            emit(config=3, what="UF (D=10,C=16,T=6,K=40,[512]x2) sample + RAMBO n=4 forward + get_PS + log_prob, exact fp32 kernels",
+            emit(config=3, what=f"UF (D=10,C=16,T=6,K=40,[512]x2) sample + RAMBO n=4 forward + get_PS + log_prob, flow gemm={args.gemm}",
                  events_total=args.events3, events_per_gpu=N, ms=ms, events_per_s=args.events3 / ms * 1e3, n_gpus=world)
         if 5 in cfgs:
             # config 5: MEM sweep, importance-sampled points per event; context hoisted per event (ctx_group)
             a, b = shard_range(args.events5, rank, world)
             E, P = b - a, args.points5
-            flow = uf_flow(dev)
+            flow = uf_flow(dev, args.gemm)
             ps = PhaseSpace(13000, [21, 21], [25, 6, -6, 21], final_masses=torch.tensor(MASSES4), dev=dev, check_inputs=False)
             g = torch.Generator(device=dev).manual_seed(5 + rank)
             r = torch.rand(E * P, 10, generator=g, device=dev).clamp_(1e-4, 1 - 1e-4)
@@ -115,7 +117,7 @@ def main():
                 return lp - logw                                        # notebooks/TestFlows_ImportanceSampling.ipynb cell 52
 
             ms = timed(step5)
-            emit(config=5, what="MEM sweep: RAMBO n=4 forward + UF log_prob, context hoisted per event", events=args.events5,
+            emit(config=5, what=f"MEM sweep: RAMBO n=4 forward + UF log_prob, context hoisted per event, flow gemm={args.gemm}", events=args.events5,
                  points_per_event=P, ms=ms, points_per_s=args.events5 * P / ms * 1e3, n_gpus=world)
     if world > 1:
         dist.destroy_process_group()
