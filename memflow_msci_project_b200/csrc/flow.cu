@@ -433,6 +433,7 @@ int mf_flow_pack_weights(const mf_flow_desc* desc, const void* const* d_weights,
     rc = post_launch("flow_pack_kernel");
     if (rc != MF_OK) return rc;
   }
+  if (gemm == MF_GEMM_MMA_3XF16) return flow_mma_presplit(L, (float*)d_blob, st);
   return MF_OK;
 }
 

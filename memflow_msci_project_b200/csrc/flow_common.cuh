@@ -109,6 +109,7 @@ struct FlowLayout;
 struct FlowKernelArgs;
 struct BaseParams;
 int flow_mma_run(const FlowLayout& L, const FlowKernelArgs& a, const BaseParams& bp, cudaStream_t st);
+int flow_mma_presplit(const FlowLayout& L, float* blob, cudaStream_t st);  // in-place: fp32 k-major rows -> fp16 hi/lo k-pairs
 
 // tcgen05 path (flow_tc.cu)
 int flow_tc_blob_bytes(const mf_flow_desc& d, int gemm, long long* bytes);

@@ -11,8 +11,9 @@
 // 8 cycles per m16n8k8 TF32 MMA per scheduler (tools/probe_mma_sync.py), i.e. ~1/8 of the tcgen05 peak -- still
 // several times the CUDA-core FMA GEMM of flow.cu for these shapes.
 //
-// Weights: the fp32, pre-masked, transposed blob of the exact path (Wt[kpad][ld], flow.cu) streamed through a
-// cp.async double buffer; the spline stage is the one of flow.cu (thread per (object, feature), parameters in smem).
+// Weights: the pre-masked, transposed blob of the exact path (Wt[kpad][ld], flow.cu) converted in place at pack time
+// to fp16 hi/lo K-PAIRS -- the 8-byte slot (k/2, n) holds {half2 hi(k, k+1), half2 lo(k, k+1)}, i.e. one B-fragment
+// register pair of the MMA -- and streamed through a cp.async ring; four lanes evaluate one spline (rqs_quad).
 // Semantics: zuko NormalizingFlow.log_prob / sample as in flow.cu (same reference lines).
 #include <algorithm>
 
@@ -76,16 +77,17 @@ __device__ __forceinline__ void mma_layer(const float* A, int lda, int K, const 
   const int nk = K / kWK;
   const int nblocks = min(NB, (ncols + NBW - 1) / NBW);
   const int total = nblocks * nk;
-  // staging: stage q of the step sequence = [16 k-rows][128 columns] of (block nb, k-chunk kc); ncols is a multiple
-  // of 128, so every thread copies two 16-byte pieces per stage: rows tid/32 and tid/32 + 8, columns 4 (tid % 32)
+  // staging: stage q of the step sequence = [8 k-pair rows][128 columns] x 8 bytes of (block nb, k-chunk kc); ncols
+  // is a multiple of 128, so every thread copies two 16-byte pieces per stage: pair rows tid/64 and tid/64 + 4,
+  // columns 2 (tid % 64).  A pair row of the blob is 2 ldw floats long.
   int st_nb = 0, st_kc = 0, st_slot = 0, st_step = 0;
-  const int st_row = threadIdx.x >> 5, st_col = (threadIdx.x & 31) << 2;
+  const int st_row = threadIdx.x >> 6, st_col = (threadIdx.x & 63) << 2;  // float offsets inside a pair row
   auto stage = [&]() {
     if (st_step < total) {
-      float* dst = wstage + st_slot * (kWK * LDS) + st_row * LDS + st_col;
-      const float* src = Wt + (size_t)(st_kc * kWK + st_row) * ldw + st_nb * NBW + st_col;
+      float* dst = wstage + st_slot * (kWK * LDS) + st_row * (2 * LDS) + st_col;
+      const float* src = Wt + (size_t)(st_kc * (kWK / 2) + st_row) * (2 * ldw) + st_nb * (2 * NBW) + st_col;
       cp16(dst, src);
-      cp16(dst + 8 * LDS, src + (size_t)8 * ldw);
+      cp16(dst + 4 * (2 * LDS), src + (size_t)4 * (2 * ldw));
       if (++st_kc == nk) { st_kc = 0; ++st_nb; }
     }
     ++st_step;
@@ -120,10 +122,10 @@ __device__ __forceinline__ void mma_layer(const float* A, int lda, int K, const 
         }
         uint32_t bh[NT][2], bl[NT][2];
 #pragma unroll
-        for (int j = 0; j < NT; ++j) {
-          const float* wc = W + n_w + 8 * j + g;
-          tc::split_f16(wc[(2 * t) * LDS], wc[(2 * t + 1) * LDS], bh[j][0], bl[j][0]);
-          tc::split_f16(wc[(2 * t + 8) * LDS], wc[(2 * t + 9) * LDS], bh[j][1], bl[j][1]);
+        for (int j = 0; j < NT; ++j) {  // staged as [8 pair rows][132] 8-byte slots: t*132 + g covers 16 distinct 8-byte banks
+          const uint2* wc = reinterpret_cast<const uint2*>(W) + n_w + 8 * j + g;
+          const uint2 p0 = wc[t * LDS], p1 = wc[(t + 4) * LDS];
+          bh[j][0] = p0.x; bl[j][0] = p0.y; bh[j][1] = p1.x; bl[j][1] = p1.y;
         }
         // the three terms of a product accumulate into the same registers: issue term by term so that dependent MMAs
         // are 4*NT instructions apart instead of back to back
@@ -444,7 +446,38 @@ flow_mma_kernel(const __grid_constant__ FlowLayout L, const __grid_constant__ Fl
   }
 }
 
+// in place: two consecutive k-rows [ld] of fp32 weights -> one pair row of [ld] {half2 hi, half2 lo} slots
+__global__ void flow_mma_presplit_kernel(float* W, int kpad, int ld) {
+  extern __shared__ float rowbuf[];  // [2][ld]
+  for (int kp = blockIdx.x; kp < kpad / 2; kp += gridDim.x) {
+    float* base = W + (size_t)kp * 2 * ld;
+    for (int i = threadIdx.x; i < 2 * ld; i += blockDim.x) rowbuf[i] = base[i];
+    __syncthreads();
+    for (int n = threadIdx.x; n < ld; n += blockDim.x) store_split(base + 2 * n, rowbuf[n], rowbuf[ld + n]);
+    __syncthreads();
+  }
+}
+
 }  // namespace
+
+int flow_mma_presplit(const FlowLayout& L, float* blob, cudaStream_t st) {
+  const int Lh = L.n_layers - 1;
+  for (int t = 0; t < L.T; ++t) {
+    float* tb = blob + (size_t)t * L.t_stride;
+    for (int l = 0; l < Lh; ++l) {
+      flow_mma_presplit_kernel<<<64, 256, 2 * L.ld[l] * sizeof(float), st>>>(tb + L.w_off[l], L.kpad[l], L.ld[l]);
+      int rc = post_launch("flow_mma_presplit_kernel");
+      if (rc != MF_OK) return rc;
+    }
+    for (int g = 0; g < L.n_chunks; ++g) {
+      flow_mma_presplit_kernel<<<64, 256, 2 * L.pw_ld * sizeof(float), st>>>(tb + L.w_off[Lh] + (size_t)g * L.chunk_stride,
+                                                                            L.kpad[Lh], L.pw_ld);
+      int rc = post_launch("flow_mma_presplit_kernel");
+      if (rc != MF_OK) return rc;
+    }
+  }
+  return MF_OK;
+}
 
 int flow_mma_run(const FlowLayout& L, const FlowKernelArgs& a, const BaseParams& bp, cudaStream_t st) {
   int hmax = 0;

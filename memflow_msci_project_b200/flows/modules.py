@@ -27,6 +27,7 @@ MF_MAX_FEATURES = 64
 UNIV_RQS, UNIV_CIRCULAR_RQS, UNIV_PS_RQS = 0, 1, 2
 BASE_DIAG_NORMAL, BASE_BOX_UNIFORM = 0, 1
 GEMM_EXACT, GEMM_TC_3XF16, GEMM_TC_BF16, GEMM_MMA_3XF16 = 0, 1, 2, 3
+GEMM_AUTO = -1  # resolved per call: tcgen05 3xFP16 when the shape fits, mma.sync 3xFP16 up to width 512, else exact
 
 
 class FlowDesc(ctypes.Structure):
@@ -390,7 +391,8 @@ class MAF(nn.Module):
         else:
             args = base_args if base_args is not None else [torch.zeros(features), torch.ones(features)]
             self.base = Unconditional(base, *args)  # the fork registers base_args as parameters
-        self.gemm = {"exact": GEMM_EXACT, "tc_3xf16": GEMM_TC_3XF16, "tc_bf16": GEMM_TC_BF16, "mma_3xf16": GEMM_MMA_3XF16}[gemm]
+        self.gemm = {"exact": GEMM_EXACT, "tc_3xf16": GEMM_TC_3XF16, "tc_bf16": GEMM_TC_BF16, "mma_3xf16": GEMM_MMA_3XF16,
+                     "auto": GEMM_AUTO}[gemm]
         self._blob_cache = {}
         self._desc_cache = {}
         self._register_load_state_dict_pre_hook(self._rename_legacy_keys)
@@ -465,9 +467,20 @@ class MAF(nn.Module):
         exact CUDA-core kernel."""
         if dtype != torch.float32:
             return GEMM_EXACT
-        if sampling and self.gemm in (GEMM_TC_3XF16, GEMM_TC_BF16) and self.core_transforms()[0].bins > 32:
-            return GEMM_EXACT
-        return self.gemm
+        gemm = self.gemm
+        if gemm == GEMM_AUTO:
+            t0 = self.core_transforms()[0]
+            widths = [lin.weight.shape[0] for lin in t0.hyper.linears()[:-1]]
+            kp = -(-t0.bins // 8) * 8
+            if max(widths) <= 128 and -(-self.context // 8) * 8 + self.features <= 128 and 3 * kp <= 128:
+                gemm = GEMM_TC_3XF16
+            elif max(widths) <= 512 and 3 * t0.bins - 1 <= 128:
+                gemm = GEMM_MMA_3XF16
+            else:
+                gemm = GEMM_EXACT
+        if sampling and gemm in (GEMM_TC_3XF16, GEMM_TC_BF16) and self.core_transforms()[0].bins > 32:
+            return GEMM_MMA_3XF16 if self.gemm == GEMM_AUTO else GEMM_EXACT
+        return gemm
 
     def packed(self, device, dtype, identity_base=False, gemm=None):
         """(desc, blob): the kernel-side copy of the weights, rebuilt when any parameter changed."""

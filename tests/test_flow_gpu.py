@@ -476,3 +476,18 @@ def test_mma_context_group_equals_repeated_context(cuda):
         a = flow(c, ctx_group=G).log_prob(x)
         b = flow(c.repeat_interleave(G, dim=0)).log_prob(x)
     assert torch.equal(a, b)
+
+
+def test_gemm_auto_picks_the_widest_fitting_tensor_path(cuda):
+    """gemm="auto": tcgen05 3xFP16 when the shape fits, mma.sync 3xFP16 up to width 512 (same results as asking for it)."""
+    for name, expect in (("TF-A", flows.modules.GEMM_TC_3XF16), ("UF", flows.modules.GEMM_MMA_3XF16)):
+        flow = build(name, cuda, torch.float32, mode="default")
+        x, c = inputs(flow, 700, 5, cuda, torch.float32)
+        flow.gemm = flows.modules.GEMM_AUTO
+        assert flow.effective_gemm(torch.float32) == expect
+        assert flow.effective_gemm(torch.float64) == flows.modules.GEMM_EXACT
+        with torch.no_grad():
+            a = flow(c).log_prob(x)
+            flow.gemm = expect
+            b = flow(c).log_prob(x)
+        assert torch.equal(a, b)
