@@ -274,6 +274,16 @@ int mf_rqs_transform(const void* d_params, const void* d_x, int64_t n, int32_t b
                      double slope, int32_t inverse, void* d_y, void* d_ladj, int8_t* d_bins, uint8_t* d_inside,
                      int dtype, void* stream);
 
+/* Backward of the forward spline of mf_rqs_transform (plain MF_UNIV_RQS): gradients of a scalar loss w.r.t. the packed
+ * parameters [n, 3K-1] and w.r.t. x [n], given dL/dy [n] and dL/dladj [n] (d_grad_ladj may be NULL = 0).
+ * Replaces what torch autograd derives from zuko MonotonicRQSTransform.call_and_ladj in the reference's training steps
+ * (`loss.backward()` after `flow(c).log_prob(x)`, e.g. scripts/run_model_labframe_sampling.py:466-520).  The inverse
+ * direction follows by the implicit function theorem on the same entry point (flows/_autograd.py).
+ */
+int mf_rqs_backward(const void* d_params, const void* d_x, int64_t n, int32_t bins, double bound, double slope,
+                    const void* d_grad_y, const void* d_grad_ladj, void* d_grad_params, void* d_grad_x, int dtype,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

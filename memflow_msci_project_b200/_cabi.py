@@ -179,6 +179,15 @@ def tc_probe_gemm(a, w, mode):
     return out
 
 
+def rqs_backward(params, x, bins, bound, slope, grad_y, grad_ladj, grad_params, grad_x):
+    """Gradients of the forward spline w.r.t. packed parameters [n, 3K-1] and x [n] (mf_rqs_backward)."""
+    with torch.cuda.device(x.device):
+        rc = lib().mf_rqs_backward(_ptr(params), _ptr(x), ctypes.c_int64(x.numel()), ctypes.c_int32(bins),
+                                   ctypes.c_double(bound), ctypes.c_double(slope or 0.0), _ptr(grad_y), _ptr(grad_ladj),
+                                   _ptr(grad_params), _ptr(grad_x), ctypes.c_int(_dtype_code(x.dtype)), _stream(x.device))
+    check(rc, "mf_rqs_backward")
+
+
 def rqs_transform(params, x, bins, univariate, bound, slope, inverse, y, ladj, bins_out=None, inside=None):
     """zuko MonotonicRQSTransform on packed parameters [n, 3K-1] (mf_rqs_transform)."""
     with torch.cuda.device(x.device):

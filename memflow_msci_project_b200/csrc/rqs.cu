@@ -97,6 +97,121 @@ __global__ void __launch_bounds__(kRqsRows, 2) rqs_kernel(const T* __restrict__ 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Backward of the forward spline (x -> y, ladj): given dL/dy and dL/dladj per element, the gradient w.r.t. the 3K-1
+// unconstrained parameters of the element and w.r.t. x.  One thread per element on its parameter row in shared
+// memory; the row is overwritten IN PLACE with the gradient row and the tile is written back as one block.
+//   knots X_j = B (2 cumsum(softmax(sc(a)))_j - 1), same for Y; D_j = exp(sc(c_j));  sc(v) = v / (1 + |f v|)
+//   bin k: x0 = X_{k-1}, x1 = X_k, ..., d0 = D_{k-1} (1 at the boundary), d1 = D_k;
+//   z = (x-x0)/dx, q = z(1-z), s = dy/dx, den = s + (d0+d1-2s) q, num = s z^2 + d0 q, A = 2 s q + d0 (1-z)^2 + d1 z^2
+//   y = y0 + dy num/den, ladj = 2 ln s + ln A - 2 ln den.
+// Outside the spline interval (mask false) y = x and ladj = 0: dx = dy, zero parameter gradient, like the reference's
+// torch.where formulation (zuko MonotonicRQSTransform.call_and_ladj under autograd).
+template <typename T>
+__device__ void rqs_backward_row(T* p, const SplineCfg<T>& cfg, T x, T gy, T gl, T& gx) {
+  using M = FM<T>;
+  const int K = cfg.K;
+  T* pw = p;
+  T* ph = p + K;
+  T* pd = p + 2 * K;
+  const T B = cfg.bound;
+  // forward pieces: soft clip (keeping its derivative in place of the logit is not possible: two passes)
+  T mw = -INFINITY, mh = -INFINITY;
+  for (int j = 0; j < K; ++j) {
+    mw = fmax(mw, softclip(pw[j], cfg.inv_ls2));
+    mh = fmax(mh, softclip(ph[j], cfg.inv_ls2));
+  }
+  T sw = T(0), sh = T(0);
+  for (int j = 0; j < K; ++j) {
+    sw += M::exp_(softclip(pw[j], cfg.inv_ls2) - mw);
+    sh += M::exp_(softclip(ph[j], cfg.inv_ls2) - mh);
+  }
+  // scan: bin k and its knots (cumulative softmax on both axes)
+  int k = -1;
+  T cw = T(0), ch = T(0), cw0 = T(0), cw1 = T(0), ch0 = T(0), ch1 = T(0);
+  T prevw = T(0), prevh = T(0);
+  for (int j = 0; j < K; ++j) {
+    const T knot_prev = B * (T(2) * cw - T(1));
+    cw += M::exp_(softclip(pw[j], cfg.inv_ls2) - mw) / sw;
+    ch += M::exp_(softclip(ph[j], cfg.inv_ls2) - mh) / sh;
+    if (knot_prev < x) { k = j; cw0 = prevw; cw1 = cw; ch0 = prevh; ch1 = ch; }
+    prevw = cw; prevh = ch;
+  }
+  const bool inside = (k >= 0) && !(B * (T(2) * cw - T(1)) < x);
+  if (!inside) {
+    for (int j = 0; j < 3 * K - 1; ++j) p[j] = T(0);
+    gx = gy;
+    return;
+  }
+  const T x0 = B * (T(2) * cw0 - T(1)), x1 = B * (T(2) * cw1 - T(1));
+  const T y0 = B * (T(2) * ch0 - T(1)), y1 = B * (T(2) * ch1 - T(1));
+  const T d0 = (k == 0) ? T(1) : M::exp_(softclip(pd[k - 1], cfg.inv_ls1));
+  const T d1 = (k == K - 1) ? T(1) : M::exp_(softclip(pd[k], cfg.inv_ls1));
+  const T dx = x1 - x0, dy = y1 - y0;
+  const T s = dy / dx, z = (x - x0) / dx, omz = T(1) - z, q = z * omz;
+  const T den = s + (d0 + d1 - T(2) * s) * q;
+  const T num = s * z * z + d0 * q;
+  const T A = T(2) * s * q + d0 * omz * omz + d1 * z * z;
+  // reverse mode through (y, ladj)
+  const T g_num = gy * dy / den;
+  const T g_den = -gy * dy * num / (den * den) - T(2) * gl / den;
+  const T g_A = gl / A;
+  T g_dy = gy * num / den;
+  T g_s = T(2) * gl / s + g_den * (T(1) - T(2) * q) + g_num * z * z + g_A * T(2) * q;
+  const T g_d0 = (g_den + g_num) * q + g_A * omz * omz;
+  const T g_d1 = g_den * q + g_A * z * z;
+  const T g_q = g_den * (d0 + d1 - T(2) * s) + g_num * d0 + g_A * T(2) * s;
+  const T g_z = g_num * T(2) * s * z + g_A * (T(2) * d1 * z - T(2) * d0 * omz) + g_q * (T(1) - T(2) * z);
+  g_dy += g_s / dx;
+  T g_dx = -g_s * s / dx - g_z * z / dx;
+  gx = g_z / dx;
+  const T g_x0 = -g_z / dx - g_dx, g_x1 = g_dx;
+  const T g_y0 = gy - g_dy, g_y1 = g_dy;
+  // knots -> cumulative softmax -> softmax -> soft-clipped logits -> logits
+  //   dL/dW_i = 2B (g_x0 [i <= k-1] + g_x1 [i <= k]);  sum_j W_j dL/dW_j = 2B (g_x0 cumW_{k-1} + g_x1 cumW_k)
+  const T tb = T(2) * B;
+  const T Sw = tb * (g_x0 * cw0 + g_x1 * cw1), Sh = tb * (g_y0 * ch0 + g_y1 * ch1);
+  const T gd0 = (k == 0) ? T(0) : g_d0 * d0, gd1 = (k == K - 1) ? T(0) : g_d1 * d1;
+  const T c0 = (k > 0) ? pd[k - 1] : T(0), c1 = (k < K - 1) ? pd[k] : T(0);
+  for (int j = 0; j < K; ++j) {
+    const T a = pw[j], b = ph[j];
+    const T da = T(1) + M::abs_(a * cfg.inv_ls2), db = T(1) + M::abs_(b * cfg.inv_ls2);
+    const T Wj = M::exp_(a / da - mw) / sw, Hj = M::exp_(b / db - mh) / sh;
+    const T gW = tb * ((j <= k - 1 ? g_x0 : T(0)) + (j <= k ? g_x1 : T(0)));
+    const T gH = tb * ((j <= k - 1 ? g_y0 : T(0)) + (j <= k ? g_y1 : T(0)));
+    pw[j] = Wj * (gW - Sw) / (da * da);
+    ph[j] = Hj * (gH - Sh) / (db * db);
+  }
+  for (int j = 0; j < K - 1; ++j) pd[j] = T(0);
+  if (k > 0) { const T dd = T(1) + M::abs_(c0 * cfg.inv_ls1); pd[k - 1] = gd0 / (dd * dd); }
+  if (k < K - 1) { const T dd = T(1) + M::abs_(c1 * cfg.inv_ls1); pd[k] = gd1 / (dd * dd); }
+}
+
+template <typename T>
+__global__ void rqs_backward_kernel(const T* __restrict__ g_par, const T* __restrict__ g_x, long long n, int K, double bound,
+                                    double slope, const T* __restrict__ g_gy, const T* __restrict__ g_gl,
+                                    T* __restrict__ g_gpar, T* __restrict__ g_gx) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  T* s_par = reinterpret_cast<T*>(smem_raw);
+  const int R = blockDim.x, P = 3 * K - 1, tid = threadIdx.x;
+  SplineCfg<T> cfg;
+  cfg.K = K; cfg.univariate = MF_UNIV_RQS; cfg.bound = (T)bound;
+  cfg.inv_ls2 = slope > 0.0 ? (T)(2.0 / log(slope)) : T(0);
+  cfg.inv_ls1 = slope > 0.0 ? (T)(1.0 / log(slope)) : T(0);
+  const long long first = (long long)blockIdx.x * R;
+  const int rows = (int)min((long long)R, n - first);
+  for (int i = tid; i < rows * P; i += R) s_par[i] = g_par[first * P + i];  // coalesced, contiguous tile
+  __syncthreads();
+  if (tid < rows) {
+    T gx;
+    rqs_backward_row<T>(s_par + (size_t)tid * P, cfg, g_x[first + tid], g_gy[first + tid], g_gl ? g_gl[first + tid] : T(0), gx);
+    g_gx[first + tid] = gx;
+  }
+  __syncthreads();
+  for (int i = tid; i < rows * P; i += R) g_gpar[first * P + i] = s_par[i];
+}
+
 }  // namespace
 }  // namespace mf
 
@@ -130,4 +245,34 @@ extern "C" int mf_rqs_transform(const void* d_params, const void* d_x, int64_t n
                                                 slope, inverse, (double*)d_y, (double*)d_ladj, d_bins, d_inside, use_tma);
   }
   return post_launch("rqs_kernel");
+}
+
+extern "C" int mf_rqs_backward(const void* d_params, const void* d_x, int64_t n, int32_t bins, double bound, double slope,
+                               const void* d_grad_y, const void* d_grad_ladj, void* d_grad_params, void* d_grad_x, int dtype,
+                               void* stream) {
+  MF_REQUIRE(n >= 0, "mf_rqs_backward: negative count");
+  MF_REQUIRE((d_params && d_x && d_grad_y && d_grad_params && d_grad_x) || n == 0, "mf_rqs_backward: null argument");
+  MF_REQUIRE(bins >= 2 && bins <= 127, "mf_rqs_backward: bins=%d outside 2..127", bins);
+  MF_REQUIRE(bound > 0.0, "mf_rqs_backward: bound must be positive");
+  MF_REQUIRE(dtype == MF_F32 || dtype == MF_F64, "mf_rqs_backward: unsupported dtype %d", dtype);
+  if (n == 0) return MF_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int P = 3 * bins - 1;
+  const size_t esz = dtype == MF_F32 ? 4 : 8;
+  int rows = 128;
+  while (rows > 32 && (size_t)rows * P * esz > 56 * 1024) rows >>= 1;
+  const size_t smem = (size_t)rows * P * esz;
+  const unsigned grid = (unsigned)((n + rows - 1) / rows);
+  if (dtype == MF_F32) {
+    MF_CUDA_CHECK(cudaFuncSetAttribute(rqs_backward_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rqs_backward_kernel<float><<<grid, rows, smem, st>>>((const float*)d_params, (const float*)d_x, n, bins, bound, slope,
+                                                        (const float*)d_grad_y, (const float*)d_grad_ladj, (float*)d_grad_params,
+                                                        (float*)d_grad_x);
+  } else {
+    MF_CUDA_CHECK(cudaFuncSetAttribute(rqs_backward_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rqs_backward_kernel<double><<<grid, rows, smem, st>>>((const double*)d_params, (const double*)d_x, n, bins, bound, slope,
+                                                         (const double*)d_grad_y, (const double*)d_grad_ladj,
+                                                         (double*)d_grad_params, (double*)d_grad_x);
+  }
+  return post_launch("rqs_backward_kernel");
 }

@@ -1,12 +1,15 @@
 """Autograd bridges of the fused flow kernels (training path, BASELINE config 4).
 
 STATUS (round 1): the FORWARD of a differentiable ``log_prob`` / ``rsample`` is the fused sm_100a kernel;
-the BACKWARD is not a native kernel yet: it re-evaluates the flow with differentiable torch ops on the GPU
-(the zuko algorithm restated below) and lets torch autograd produce the gradients w.r.t. x, the context
-and every hyper-network parameter.  This keeps the reference's training loops working unchanged
-(`loss = -flow(c).log_prob(x).mean(); loss.backward()`), but the backward runs at eager-torch speed and is
-reported as such; it never runs on the CPU and never touches oracle/.
+the BACKWARD re-evaluates the flow transform by transform on the GPU: the hyper-network (masked linears + ReLU)
+with torch ops (cuBLAS GEMMs, torch autograd), the spline with native kernels -- forward `mf_rqs_transform`,
+backward `mf_rqs_backward` (closed-form gradient w.r.t. the 3K-1 logits and x; the inverse direction by the
+implicit function theorem) -- instead of ~300 eager elementwise kernels per transform.  This keeps the reference's
+training loops working unchanged (`loss = -flow(c).log_prob(x).mean(); loss.backward()`); it never runs on the CPU
+and never touches oracle/.  `MEMFLOW_B200_EAGER_SPLINE=1` selects the pure-torch spline restated below (the
+formulation the native backward is tested against).
 """
+import os
 import math
 
 import torch
@@ -66,39 +69,112 @@ def _wrap(x, bound):
     return torch.remainder(x + bound, 2 * bound) - bound
 
 
-def _hyper(t, x, c):
+def _hyper_phi(t, x, c):
     h = x if c is None else torch.cat((x, c), dim=-1)
     lins = t.hyper.linears()
     for i, lin in enumerate(lins):
         h = F.linear(h, lin.mask * lin.weight, lin.bias)
         if i < len(lins) - 1:
             h = torch.relu(h)
-    phi = h.unflatten(-1, (t.features, t.total))
+    return h.unflatten(-1, (t.features, t.total))
+
+
+def _hyper(t, x, c):
+    phi = _hyper_phi(t, x, c)
     K = t.bins
     return _rqs_knots(phi[..., :K], phi[..., K:2 * K], phi[..., 2 * K:], t.bound, t.slope)
+
+
+def _native_spline():
+    return os.environ.get("MEMFLOW_B200_EAGER_SPLINE") != "1"
+
+
+class _SplineForwardFn(torch.autograd.Function):
+    """(phi [n, 3K-1], x [n]) -> (y, ladj): mf_rqs_transform forward, mf_rqs_backward backward."""
+
+    @staticmethod
+    def forward(ctx, phi, x, K, bound, slope):
+        y, ladj = torch.empty_like(x), torch.empty_like(x)
+        _cabi.rqs_transform(phi, x, K, 0, bound, slope, False, y, ladj)
+        ctx.save_for_backward(phi, x)
+        ctx.meta = (K, bound, slope)
+        return y, ladj
+
+    @staticmethod
+    def backward(ctx, gy, gl):
+        phi, x = ctx.saved_tensors
+        K, bound, slope = ctx.meta
+        gphi, gx = torch.empty_like(phi), torch.empty_like(x)
+        _cabi.rqs_backward(phi, x, K, bound, slope, gy.contiguous(), gl.contiguous(), gphi, gx)
+        return gphi, gx, None, None, None
+
+
+class _SplineInverseFn(torch.autograd.Function):
+    """(phi, y) -> x = F^-1(y; phi).  With F(x, phi) = y: dx = (dy - dF/dphi dphi) / F_x, F_x = exp(ladj(x))."""
+
+    @staticmethod
+    def forward(ctx, phi, y, K, bound, slope):
+        x = torch.empty_like(y)
+        _cabi.rqs_transform(phi, y, K, 0, bound, slope, True, x, None)
+        ctx.save_for_backward(phi, x)
+        ctx.meta = (K, bound, slope)
+        return x
+
+    @staticmethod
+    def backward(ctx, gx):
+        phi, x = ctx.saved_tensors
+        K, bound, slope = ctx.meta
+        y2, ladj = torch.empty_like(x), torch.empty_like(x)
+        _cabi.rqs_transform(phi, x, K, 0, bound, slope, False, y2, ladj)
+        gy = gx * torch.exp(-ladj)
+        gphi, scratch = torch.empty_like(phi), torch.empty_like(x)
+        _cabi.rqs_backward(phi, x, K, bound, slope, (-gy).contiguous(), None, gphi, scratch)
+        return gphi, gy, None, None, None
+
+
+def _spline_forward(t, phi, xin):
+    """Spline of transform t on every (row, feature): phi [N, D, 3K-1], xin [N, D] -> (y, ladj) [N, D]."""
+    shape = xin.shape
+    y, l = _SplineForwardFn.apply(phi.reshape(-1, t.total).contiguous(), xin.reshape(-1).contiguous(), t.bins,
+                                  float(t.bound), float(t.slope or 0.0))
+    return y.view(shape), l.view(shape)
+
+
+def _spline_inverse(t, phi, y):
+    shape = y.shape
+    x = _SplineInverseFn.apply(phi.reshape(-1, t.total).contiguous(), y.reshape(-1).contiguous(), t.bins,
+                               float(t.bound), float(t.slope or 0.0))
+    return x.view(shape)
 
 
 def eager_forward(module, x, c):
     """Differentiable restatement: (z, ladj) of the spline transforms of ``module`` (rows x [N,D], c [N,C])."""
     ladj = x.new_zeros(x.shape[:-1])
+    native = _native_spline() and x.is_cuda
     for t in module.core_transforms():
-        knots = _hyper(t, x, c)
         xin, l0 = x, 0.0
         if t.univariate == UNIV_CIRCULAR_RQS:
             xin = _wrap(x, t.bound)
         elif t.univariate == UNIV_PS_RQS:
             xin, l0 = (x + 1) / 2, math.log(0.5)
-        x, l = _rqs_forward(xin, *knots)
+        if native:
+            x, l = _spline_forward(t, _hyper_phi(t, x, c), xin)
+        else:
+            x, l = _rqs_forward(xin, *_hyper(t, x, c))
         ladj = ladj + (l + l0).sum(-1)
     return x, ladj
 
 
 def eager_inverse(module, z, c):
     y = z
+    native = _native_spline() and z.is_cuda
     for t in reversed(module.core_transforms()):
         x = torch.zeros_like(y)
         for _ in range(t.passes):
-            x = _rqs_inverse(y, *_hyper(t, x, c))
+            if native:
+                x = _spline_inverse(t, _hyper_phi(t, x, c), y)
+            else:
+                x = _rqs_inverse(y, *_hyper(t, x, c))
             if t.univariate == UNIV_CIRCULAR_RQS:
                 x = _wrap(x, t.bound)
             elif t.univariate == UNIV_PS_RQS:

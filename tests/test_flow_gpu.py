@@ -340,10 +340,11 @@ def test_standalone_rqs_transform(cuda, K, dtype, N):
 
 
 # ------------------------------------------------------------------------------------------------
-# autograd: fused forward + (interim) eager-torch backward
-def test_log_prob_gradients_match_eager_autograd(cuda):
+# autograd: fused forward; backward = torch hyper-network + native spline backward, checked against pure eager torch
+@pytest.mark.parametrize("name", ["NCSF", "TF-A", "PSNSF"])
+def test_log_prob_gradients_match_eager_autograd(cuda, monkeypatch, name):
     from memflow_msci_project_b200.flows import _autograd as ag
-    flow = build("NCSF", cuda, torch.float64, mode="stress")
+    flow = build(name, cuda, torch.float64, mode="stress")
     x, c = inputs(flow, 300, 3, cuda, torch.float64, outside_frac=0.0)
     x = x.requires_grad_(True)
     c = c.requires_grad_(True)
@@ -356,6 +357,7 @@ def test_log_prob_gradients_match_eager_autograd(cuda):
         p.grad = None
     x2 = x.detach().clone().requires_grad_(True)
     c2 = c.detach().clone().requires_grad_(True)
+    monkeypatch.setenv("MEMFLOW_B200_EAGER_SPLINE", "1")   # reference: the spline in plain differentiable torch ops
     z, ladj = ag.eager_forward(flow, x2, c2)
     lp2 = flow.base().log_prob(z) + ladj
     (-lp2.mean()).backward()
@@ -364,6 +366,74 @@ def test_log_prob_gradients_match_eager_autograd(cuda):
     assert len(g_fused) == len(g_eager) and len(g_fused) > 4
     for a, b in zip(g_fused, g_eager):
         assert torch.allclose(a, b, atol=1e-9, rtol=1e-7)
+
+
+@pytest.mark.parametrize("K,slope,dtype", [(16, 1e-3, torch.float64), (8, None, torch.float64), (40, 1e-3, torch.float64),
+                                           (16, 1e-3, torch.float32)])
+def test_native_spline_backward_matches_torch_autograd(cuda, K, slope, dtype):
+    """mf_rqs_backward (closed form) and the implicit-function inverse gradient vs autograd of the torch restatement."""
+    from memflow_msci_project_b200.flows import _autograd as ag
+    g = torch.Generator().manual_seed(K)
+    n, P, bound = 4000, 3 * K - 1, 1.3
+    phi = (1.5 * torch.randn(n, P, generator=g)).to(cuda, dtype)
+    x = (0.9 * torch.randn(n, generator=g)).to(cuda, dtype)     # ~15 % outside [-bound, bound]
+    gy = torch.randn(n, generator=g).to(cuda, dtype)
+    gl = torch.randn(n, generator=g).to(cuda, dtype)
+
+    def eager(phi_, x_, inverse):
+        knots = ag._rqs_knots(phi_[:, :K], phi_[:, K:2 * K], phi_[:, 2 * K:], bound, slope)
+        return ag._rqs_inverse(x_, *knots) if inverse else ag._rqs_forward(x_, *knots)
+
+    tol = dict(atol=1e-9, rtol=1e-8) if dtype == torch.float64 else dict(atol=2e-3, rtol=2e-3)
+    # forward direction
+    p1, x1 = phi.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    y, l = ag._SplineForwardFn.apply(p1, x1, K, bound, slope or 0.0)
+    ((y * gy).sum() + (l * gl).sum()).backward()
+    p2, x2 = phi.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    y2, l2 = eager(p2, x2, False)
+    ((y2 * gy).sum() + (l2 * gl).sum()).backward()
+    assert torch.allclose(x1.grad, x2.grad, **tol)
+    if dtype == torch.float64:
+        assert torch.allclose(p1.grad, p2.grad, **tol)
+    else:   # fp32: compare against the fp64 gradient of the same inputs, relative to the gradient scale of the row
+        p3, x3 = phi.double().requires_grad_(True), x.double().requires_grad_(True)
+        y3, l3 = eager(p3, x3, False)
+        ((y3 * gy.double()).sum() + (l3 * gl.double()).sum()).backward()
+        scale = p3.grad.abs().max(dim=1, keepdim=True).values.clamp_min(1e-3)
+        assert ((p1.grad.double() - p3.grad).abs() / scale).quantile(0.999).item() < 1e-3
+    # inverse direction
+    p1, y1 = phi.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    xi = ag._SplineInverseFn.apply(p1, y1, K, bound, slope or 0.0)
+    (xi * gy).sum().backward()
+    if dtype == torch.float64:
+        p2, y2_ = phi.clone().requires_grad_(True), x.clone().requires_grad_(True)
+        (eager(p2, y2_, True) * gy).sum().backward()
+        assert torch.allclose(y1.grad, y2_.grad, atol=1e-8, rtol=1e-7)
+        assert torch.allclose(p1.grad, p2.grad, atol=1e-8, rtol=1e-7)
+    else:
+        assert torch.isfinite(p1.grad).all() and torch.isfinite(y1.grad).all()
+
+
+def test_rsample_gradients_match_eager_autograd(cuda, monkeypatch):
+    from memflow_msci_project_b200.flows import _autograd as ag
+    flow = build("TF-B", cuda, torch.float64, mode="stress")
+    _, c = inputs(flow, 200, 3, cuda, torch.float64)
+    zn = torch.randn(200, 3, dtype=torch.float64, device=cuda, generator=torch.Generator(device=cuda).manual_seed(1))
+    z0 = (flow.base().mean + flow.base().stddev * zn if hasattr(flow.base(), "stddev") else zn).detach()
+    c1 = c.clone().requires_grad_(True)
+    x1 = ag.eager_inverse(flow, z0, c1)                       # native spline kernels
+    x1.square().sum().backward()
+    g1 = [c1.grad.clone()] + [p.grad.clone() for p in flow.parameters() if p.grad is not None]
+    for p in flow.parameters():
+        p.grad = None
+    monkeypatch.setenv("MEMFLOW_B200_EAGER_SPLINE", "1")
+    c2 = c.clone().requires_grad_(True)
+    x2 = ag.eager_inverse(flow, z0, c2)
+    x2.square().sum().backward()
+    g2 = [c2.grad] + [p.grad for p in flow.parameters() if p.grad is not None]
+    assert torch.allclose(x1, x2, atol=1e-9)
+    for a, b in zip(g1, g2):
+        assert torch.allclose(a, b, atol=1e-8, rtol=1e-6)
 
 
 def test_rsample_is_differentiable(cuda):

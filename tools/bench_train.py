@@ -2,8 +2,9 @@
 """Training-step benchmark (BASELINE.json configs[3]): transfer-flow likelihood + sampling loss, batch 64k events
 per GPU (x10 objects), Adam, and ONE flat NCCL gradient all-reduce per step under torchrun.
 
-The forward of log_prob and rsample runs in the fused sm_100a kernels; the backward is the interim eager-torch
-recompute of flows/_autograd.py, so this number is dominated by eager torch and reported as such.
+The forward of log_prob and rsample runs in the fused sm_100a kernels; the backward recomputes the flow transform by
+transform (flows/_autograd.py): hyper-network in torch (cuBLAS), spline forward / backward in the
+native kernels mf_rqs_transform / mf_rqs_backward.
 
     python tools/bench_train.py [--events 65536] [--steps 3] [--warmup 2] [--no-sampling-loss]
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/bench_train.py ...
@@ -77,7 +78,7 @@ def main():
                           "events_per_gpu": args.events, "objects_per_event": args.objects, "n_gpus": world, "ms_per_step": ms,
                           "events_per_s": args.events * world / ms * 1e3, "parameters": nparam, "loss": float(loss.item()),
                           "fused_kernel_launches_per_step": (_cabi.launch_count() - l0) / args.steps,
-                          "backward": "eager torch recompute (interim)", "peak_mem_GB": torch.cuda.max_memory_allocated() / 2**30}), flush=True)
+                          "backward": "recompute per transform: torch hyper-network (cuBLAS) + native spline forward/backward kernels", "peak_mem_GB": torch.cuda.max_memory_allocated() / 2**30}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
