@@ -28,8 +28,6 @@ FLAGS = [
 EXTRA_FLAGS = {"rambo.cu": ["--use_fast_math"]}
 if os.environ.get("MF_TC_TRACE") == "1":  # cycle-level trace of the tensor-core flow kernel (tools/trace_tc.py)
     EXTRA_FLAGS["flow_tc.cu"] = ["-DMF_TC_TRACE"]
-if os.environ.get("MF_MMA_NOSPLINE") == "1":  # timing experiment: wide-flow kernel without the spline arithmetic
-    EXTRA_FLAGS["flow_mma.cu"] = ["-DMF_MMA_NOSPLINE"]
 
 
 def _stale(target, deps):

@@ -390,11 +390,7 @@ flow_mma_kernel(const __grid_constant__ FlowLayout L, const __grid_constant__ Fl
             float out, la;
             int bin;
             bool ins;
-#ifdef MF_MMA_NOSPLINE  // timing experiment only: skip the spline arithmetic
-            out = v + pp[0] * 1e-9f; la = 0.f; bin = 0; ins = true;
-#else
             rqs_quad(pp, cfg, args.mode == 1, v, out, la, bin, ins);
-#endif
             if (live && (tid & 3) == 0) {
               xnew[(size_t)m * D + f] = out;
               if (args.mode == 0) {
