@@ -453,11 +453,13 @@ rambo_forward_kernel(const __grid_constant__ mf_rambo_desc d, const __grid_const
 // -------------------------------------------------------------------------------------------
 // inverse map of one event (getPSpoint_batch :615-736, get_PS unfolding_flow/utils.py:1056-1152).
 // pin: this event's final-state momenta [n][4] in shared memory (un-permuted).  rout: uniforms.
+// swz: particle slot XOR of this event's row (0, or row & 7 when the tile was staged with the 16-byte-chunk swizzle
+// that makes 128-byte rows conflict-free: all lanes read the same particle index at the same time).
 template <typename TIO, typename TC, int NF>
 __device__ __forceinline__ void rambo_inverse_event(const mf_rambo_desc& d, const RamboAux& aux,
                                                     const TIO* pin, TIO* rout, TC x1, TC x2,
                                                     TC& prob_out, int& flags, bool want_prob,
-                                                    bool& r_out_of_range) {
+                                                    bool& r_out_of_range, int swz) {
   constexpr int NMAX = NF ? NF : MF_MAX_FINAL;
   constexpr int UNR = NF ? NF : 1;
   const int n = NF ? NF : d.n_final;
@@ -470,7 +472,7 @@ __device__ __forceinline__ void rambo_inverse_event(const mf_rambo_desc& d, cons
   for (int jj = 0; jj < NMAX; ++jj) {
     const int j = n - 1 - jj;
     if (jj < n) {
-      const TIO* p = pin + 4 * aux.perm[j];
+      const TIO* p = pin + 4 * (aux.perm[j] ^ swz);
       QE += (TC)p[0]; Qx += (TC)p[1]; Qy += (TC)p[2]; Qz += (TC)p[3];
       TC m2 = QE * QE - Qx * Qx - Qy * Qy - Qz * Qz;
       Mi[j] = M::sqrt_(m2);
@@ -483,7 +485,7 @@ __device__ __forceinline__ void rambo_inverse_event(const mf_rambo_desc& d, cons
   // second pass: j = n-1 .. 1, rebuild Q_{j-1} = Q_j + P_{j-1} from the back
   TC SE = TC(0), Sx = TC(0), Sy = TC(0), Sz = TC(0);
   {
-    const TIO* p = pin + 4 * aux.perm[n - 1];
+    const TIO* p = pin + 4 * (aux.perm[n - 1] ^ swz);
     SE = (TC)p[0]; Sx = (TC)p[1]; Sy = (TC)p[2]; Sz = (TC)p[3];
   }
 #pragma unroll UNR
@@ -494,7 +496,7 @@ __device__ __forceinline__ void rambo_inverse_event(const mf_rambo_desc& d, cons
       TC u = K[j] / K[j - 1];
       const int e = n - i;
       TC rm = TC(e + 1) * ipow(u, e) - TC(e) * ipow(u, e + 1);  // :672-674
-      const TIO* p = pin + 4 * aux.perm[j - 1];
+      const TIO* p = pin + 4 * (aux.perm[j - 1] ^ swz);
       TC pE = (TC)p[0], px = (TC)p[1], py = (TC)p[2], pz = (TC)p[3];
       SE += pE; Sx += px; Sy += py; Sz += pz;  // Q_{j-1}
       // boost_t(P_{j-1}, -Q_vec/Q_E) (:678, phasespace/utils.py:88-118)
@@ -579,8 +581,21 @@ rambo_inverse_kernel(const __grid_constant__ mf_rambo_desc d, const __grid_const
   const bool full = (tile == kEPB);
   const bool tma = use_tma && full;
   const int tid = threadIdx.x;
+  // 128-byte rows (n = 8, fp32): every lane reads the same particle of its own row, i.e. the same bank group -- a
+  // 32-way conflict on a flat tile.  Stage those tiles with coalesced 16-byte loads and store chunk c of row r at
+  // c ^ (r & 7); the reads below XOR the particle index the same way.
+  const bool swizzled = (sizeof(TIO) == 4) && (n == 8) && (vec_ok != 0);
+  const int swz = swizzled ? (tid & 7) : 0;
 
-  if (tma) {
+  if (swizzled) {
+    const float4* src = reinterpret_cast<const float4*>(g_mom + first * mdim);
+    float4* dst = reinterpret_cast<float4*>(s_in);
+    for (int i = tid; i < tile * 8; i += kEPB) {
+      const int row = i >> 3, c = i & 7;
+      dst[row * 8 + (c ^ (row & 7))] = __ldg(src + i);
+    }
+    __syncthreads();
+  } else if (tma) {
     if (tid == 0) {
       mbar_init(&bar, 1);
       fence_mbar_init();
@@ -617,7 +632,7 @@ rambo_inverse_kernel(const __grid_constant__ mf_rambo_desc d, const __grid_const
     }
     bool oor = false;
     rambo_inverse_event<TIO, TC, NF>(d, aux, s_in + tid * mdim, s_out + tid * ndim, x1, x2, prob,
-                                     flags, (mode == 0) && g_prob != nullptr, oor);
+                                     flags, (mode == 0) && g_prob != nullptr, oor, swz);
     if (mode == 0) {
       if (g_prob) g_prob[e] = (TIO)prob;
       if (g_flags) g_flags[e] = flags;
@@ -625,7 +640,7 @@ rambo_inverse_kernel(const __grid_constant__ mf_rambo_desc d, const __grid_const
       // CM test of get_PS is 1e-5 (:1079-1081); recompute from the tile
       TC sx = TC(0), sy = TC(0), sz = TC(0);
       for (int k = 0; k < n; ++k) {
-        const TIO* p = s_in + tid * mdim + 4 * k;
+        const TIO* p = s_in + tid * mdim + 4 * (k ^ swz);
         sx += (TC)p[1]; sy += (TC)p[2]; sz += (TC)p[3];
       }
       problem |= (sx * sx + sy * sy + sz * sz > TC(1e-5));
