@@ -261,9 +261,7 @@ class NormalizingFlow:
         xb = xb.contiguous()
         cb = cb.to(dtype).contiguous() if cb is not None else None
         N, D = xb.shape
-        gemm = m.effective_gemm(dtype)
-        if self._ctx_group > 1 and gemm in (GEMM_TC_3XF16, GEMM_TC_BF16):
-            gemm = GEMM_EXACT  # context grouping is not implemented in the tcgen05 kernel
+        gemm = m.effective_gemm(dtype, ctx_group=self._ctx_group)
         desc, blob = m.packed(xb.device, dtype, gemm=gemm)
         desc = self._with_group(desc)
         z = torch.empty_like(xb)
@@ -304,9 +302,7 @@ class NormalizingFlow:
         zb, cb, batch = self._rows(z)
         zb = zb.contiguous()
         cb = cb.to(dtype).contiguous() if cb is not None else None
-        gemm = m.effective_gemm(dtype, sampling=True)
-        if self._ctx_group > 1 and gemm in (GEMM_TC_3XF16, GEMM_TC_BF16):
-            gemm = GEMM_EXACT
+        gemm = m.effective_gemm(dtype, sampling=True, ctx_group=self._ctx_group)
         desc, blob = m.packed(zb.device, dtype, identity_base=True, gemm=gemm)
         desc = self._with_group(desc)
         x = torch.empty_like(zb)
@@ -371,7 +367,7 @@ class MAF(nn.Module):
 
     def __init__(self, features, context=0, transforms=3, randperm=False, bins=8, hidden_features=(64, 64),
                  passes=None, univariate=UNIV_RQS, bound=5.0, slope=1e-3, base=None, base_args=None,
-                 univariate_kwargs=None, dtype=None, gemm="exact", **unused):
+                 univariate_kwargs=None, dtype=None, gemm="auto", **unused):
         super().__init__()
         if unused:
             raise TypeError(f"unsupported keyword arguments: {sorted(unused)}")
@@ -462,24 +458,23 @@ class MAF(nn.Module):
                 d.base_a[f], d.base_b[f] = float(a[f]), float(b[f])
         return d
 
-    def effective_gemm(self, dtype, sampling=False):
-        """Tensor-core modes cover fp32; fp64 flows (and tensor-core sampling with more than 32 bins) run the
-        exact CUDA-core kernel."""
+    def effective_gemm(self, dtype, sampling=False, ctx_group=1):
+        """Conditioner arithmetic of one call.  fp64 flows run the CUDA-core kernel.  "auto": tcgen05 3xFP16 when the
+        shape fits that kernel, else the warp-level MMA kernel up to hidden width 512, else the CUDA-core kernel.
+        What the tcgen05 kernel does not take (sampling with more than 32 bins, context grouping) goes to the MMA
+        kernel under "auto" and to the CUDA-core kernel when a tcgen05 mode was asked for explicitly."""
         if dtype != torch.float32:
             return GEMM_EXACT
+        t0 = self.core_transforms()[0]
+        widths = [lin.weight.shape[0] for lin in t0.hyper.linears()[:-1]]
+        mma_ok = max(widths) <= 512 and 3 * t0.bins - 1 <= 128
         gemm = self.gemm
         if gemm == GEMM_AUTO:
-            t0 = self.core_transforms()[0]
-            widths = [lin.weight.shape[0] for lin in t0.hyper.linears()[:-1]]
             kp = -(-t0.bins // 8) * 8
-            if max(widths) <= 128 and -(-self.context // 8) * 8 + self.features <= 128 and 3 * kp <= 128:
-                gemm = GEMM_TC_3XF16
-            elif max(widths) <= 512 and 3 * t0.bins - 1 <= 128:
-                gemm = GEMM_MMA_3XF16
-            else:
-                gemm = GEMM_EXACT
-        if sampling and gemm in (GEMM_TC_3XF16, GEMM_TC_BF16) and self.core_transforms()[0].bins > 32:
-            return GEMM_MMA_3XF16 if self.gemm == GEMM_AUTO else GEMM_EXACT
+            tc_ok = max(widths) <= 128 and -(-self.context // 8) * 8 + self.features <= 128 and 3 * kp <= 128
+            gemm = GEMM_TC_3XF16 if tc_ok else (GEMM_MMA_3XF16 if mma_ok else GEMM_EXACT)
+        if gemm in (GEMM_TC_3XF16, GEMM_TC_BF16) and ((sampling and t0.bins > 32) or ctx_group > 1):
+            return GEMM_MMA_3XF16 if (self.gemm == GEMM_AUTO and mma_ok) else GEMM_EXACT
         return gemm
 
     def packed(self, device, dtype, identity_base=False, gemm=None):

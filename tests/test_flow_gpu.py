@@ -67,6 +67,7 @@ def build(name, dev, dtype, seed=7, mode="stress"):
                 lin.weight.mul_(3.0)
             if mode in ("bias", "stress"):
                 lin.bias.uniform_(-1.5, 1.5)
+    flow.gemm = flows.modules.GEMM_EXACT   # the tests pick the conditioner arithmetic explicitly (the default is "auto")
     return flow.to(dev).to(dtype)
 
 
