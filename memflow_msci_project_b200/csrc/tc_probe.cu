@@ -160,7 +160,12 @@ __global__ void __launch_bounds__(128, 1) tc_issue_probe_kernel(float* __restric
   __shared__ __align__(8) uint64_t bar[4];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5;
-  for (int i = tid; i < (16384 + 32768) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  // variant 3: random fp16 operands in (0.25, 2) with random signs instead of zeros (data-dependent MMA rate?)
+  for (int i = tid; i < (16384 + 32768) / 4; i += 128) {
+    uint32_t h = (uint32_t)i * 2654435761u;
+    h ^= h >> 15;
+    reinterpret_cast<uint32_t*>(smem)[i] = (variant == 3) ? ((h & 0x83ff83ffu) | 0x34003400u | ((h >> 3) & 0x08000800u)) : 0u;
+  }
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) mbar_init(&bar[i], 1);
     for (int i = 2; i < 4; ++i) mbar_init(&bar[i], 1000000);
@@ -172,6 +177,24 @@ __global__ void __launch_bounds__(128, 1) tc_issue_probe_kernel(float* __restric
   __syncthreads();
   tc::fence_after_thread_sync();
   const uint32_t tmem = tmem_base_s;
+  if (variant == 3) {  // random A operand planes in TMEM (columns 128..191 of both accumulators' slots)
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    for (int slot = 0; slot < 2; ++slot)
+      for (int c = 0; c < 64; c += 8) {
+        uint32_t r[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          uint32_t h = (uint32_t)(tid * 64 + c + i + slot * 7919) * 2246822519u;
+          h ^= h >> 13;
+          r[i] = (h & 0x83ff83ffu) | 0x34003400u | ((h >> 3) & 0x08000800u);
+        }
+        tc::tmem_st8(tmem + lane_off + slot * 256 + 128 + c, r);
+      }
+    tc::tmem_st_wait();
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    tc::fence_after_thread_sync();
+  }
   if (warp < issuers) {
     const uint32_t idesc = tc::make_idesc_f16(0, 128, n);
     const uint32_t a_s = smem_u32(smem), b_s = smem_u32(smem + 16384);
@@ -193,7 +216,7 @@ __global__ void __launch_bounds__(128, 1) tc_issue_probe_kernel(float* __restric
       }
       __syncwarp();
     } else
-    if (variant == 1) {  // the whole issue loop inside one elected thread, four k-steps unrolled
+    if (variant == 1 || variant == 3) {  // the whole issue loop inside one elected thread, four k-steps unrolled
       if (tc::elect_one()) {
         uint64_t db[4], da[4];
 #pragma unroll
@@ -224,7 +247,7 @@ __global__ void __launch_bounds__(128, 1) tc_issue_probe_kernel(float* __restric
     const long long t1 = clock64();
     mbar_wait(&bar[warp], 0);
     const long long t2 = clock64();
-    if ((tid & 31) == 0) { out[2 * warp] = (float)(t1 - t0); out[2 * warp + 1] = (float)(t2 - t0); }
+    if ((tid & 31) == 0 && blockIdx.x == 0) { out[2 * warp] = (float)(t1 - t0); out[2 * warp + 1] = (float)(t2 - t0); }
   }
   tc::fence_before_thread_sync();
   __syncthreads();
@@ -310,6 +333,8 @@ extern "C" int mf_tc_probe_gemm(const float* d_a, const float* d_w, float* d_out
   MF_REQUIRE(d_a && d_w && d_out, "mf_tc_probe_gemm: null argument");
   MF_REQUIRE(k >= 16 && k % 16 == 0 && k <= 256, "mf_tc_probe_gemm: K=%d must be a multiple of 16 in 16..256", k);
   MF_REQUIRE(n >= 16 && n % 16 == 0 && n <= 256, "mf_tc_probe_gemm: N=%d must be a multiple of 16 in 16..256", n);
+  int all_sms = 0;
+  if (mode >= 1000) { all_sms = 1; mode -= 1000; }
   if (mode >= 300) {  // legacy mma.sync rate: mode = 300 + warps per scheduler; k = iterations
     const int wps = (mode - 300) % 10, f16 = (mode - 300) / 10;
     MF_REQUIRE(d_out && wps >= 1 && wps <= 8 && f16 <= 1, "mf_tc_probe_gemm: bad mma.sync probe mode");
@@ -323,11 +348,12 @@ extern "C" int mf_tc_probe_gemm(const float* d_a, const float* d_w, float* d_out
     return post_launch("spline_probe_kernel");
   }
   if (mode >= 100) {  // timing: mode = 100 + 10 * (A in TMEM) + issuers; k = MMA count per issuer
+    const int grid = all_sms ? 148 : 1;  // mode + 1000: the same probe on every SM at once (chip-level effects)
     const int variant = (mode - 100) / 20, ts = ((mode - 100) / 10) % 2, issuers = (mode - 100) % 10;
-    MF_REQUIRE(d_out && issuers >= 1 && issuers <= 2 && ts <= 1 && variant <= 2 && n <= 128 && n % 16 == 0, "mf_tc_probe_gemm: bad timing mode");
+    MF_REQUIRE(d_out && issuers >= 1 && issuers <= 2 && ts <= 1 && variant <= 3 && n <= 128 && n % 16 == 0, "mf_tc_probe_gemm: bad timing mode");
     const size_t sm = 16384 + 32768;
     MF_CUDA_CHECK(cudaFuncSetAttribute(tc_issue_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    tc_issue_probe_kernel<<<1, 128, sm, static_cast<cudaStream_t>(stream)>>>(d_out, k, n, ts, issuers, variant);
+    tc_issue_probe_kernel<<<grid, 128, sm, static_cast<cudaStream_t>(stream)>>>(d_out, k, n, ts, issuers, variant);
     return post_launch("tc_issue_probe_kernel");
   }
   MF_REQUIRE(mode >= 0 && mode <= 4, "mf_tc_probe_gemm: bad mode");
