@@ -1,5 +1,7 @@
 """CPU: the flow oracle against the reference's only recorded known-answer and its own invariants;
 the product's host logic (mask construction, module tree, state-dict layout) against the oracle."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -119,3 +121,37 @@ def test_differentiable_restatement_matches_oracle(ctor, kw):
     assert np.abs(z.detach().numpy() - z_ref).max() < 1e-12 and np.abs(ladj.detach().numpy() - ladj_ref).max() < 1e-11
     xb = ag.eager_inverse(flow, torch.from_numpy(z_ref), c)
     assert np.abs(xb.detach().numpy() - fo.flow_inverse(spec, z_ref, c.numpy() if c is not None else None)).max() < 1e-10
+
+
+def test_gemm_auto_resolution_table():
+    """Which kernel a call takes under gemm="auto" (flows/modules.py::MAF.effective_gemm) -- host logic only."""
+    import torch
+    from memflow_msci_project_b200 import flows
+    from memflow_msci_project_b200.flows import modules as fm
+    mk = lambda **kw: flows.NSF(**kw)
+    tfa = mk(features=3, context=65, transforms=2, bins=16, hidden_features=[128] * 4)
+    uf = mk(features=10, context=16, transforms=2, bins=40, hidden_features=[512] * 2)
+    tf1d = mk(features=1, context=66, transforms=2, bins=16, hidden_features=[256] * 3)
+    huge = mk(features=2, context=4, transforms=1, bins=8, hidden_features=[1024])
+    manybins = mk(features=2, context=4, transforms=1, bins=50, hidden_features=[64])
+    f32, f64 = torch.float32, torch.float64
+    assert tfa.gemm == fm.GEMM_AUTO                                         # the default
+    assert tfa.effective_gemm(f32) == fm.GEMM_TC_3XF16
+    assert tfa.effective_gemm(f32, sampling=True) == fm.GEMM_TC_3XF16
+    assert tfa.effective_gemm(f32, ctx_group=8) == fm.GEMM_MMA_3XF16        # context grouping: not in the tcgen05 kernel
+    assert tfa.effective_gemm(f64) == fm.GEMM_EXACT
+    assert uf.effective_gemm(f32) == fm.GEMM_MMA_3XF16 and uf.effective_gemm(f32, sampling=True) == fm.GEMM_MMA_3XF16
+    assert tf1d.effective_gemm(f32) == fm.GEMM_MMA_3XF16
+    assert huge.effective_gemm(f32) == fm.GEMM_EXACT                        # wider than 512
+    assert manybins.effective_gemm(f32) == fm.GEMM_EXACT                    # 3K-1 > 128
+    tfa.gemm = fm.GEMM_TC_3XF16                                             # asked for explicitly: falls to the parity anchor
+    assert tfa.effective_gemm(f32, ctx_group=8) == fm.GEMM_EXACT
+
+
+def test_gemm_constants_match_header():
+    import re
+    from memflow_msci_project_b200.flows import modules as fm
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "memflow_b200.h")).read()
+    vals = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define (MF_GEMM_\w+) (\d+)", hdr)}
+    assert vals == {"MF_GEMM_EXACT": fm.GEMM_EXACT, "MF_GEMM_TC_3XF16": fm.GEMM_TC_3XF16,
+                    "MF_GEMM_TC_BF16": fm.GEMM_TC_BF16, "MF_GEMM_MMA_3XF16": fm.GEMM_MMA_3XF16}
