@@ -299,7 +299,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--events", type=int, default=1_000_000, help="events per GPU per step")
-    ap.add_argument("--ref-events", type=int, default=300_000, help="events per step of the CPU port leg (10-20 s of host work)")
+    ap.add_argument("--ref-events", type=int, default=600_000, help="events per step of the CPU port leg (about 10 s on the bench box, 30 s on 8 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="chunks of the host->device pipeline of the e2e leg")
     ap.add_argument("--gemm", default="tc_3xf16", choices=["exact", "tc_3xf16", "tc_bf16"],
