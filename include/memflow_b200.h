@@ -274,6 +274,17 @@ int mf_rqs_transform(const void* d_params, const void* d_x, int64_t n, int32_t b
                      double slope, int32_t inverse, void* d_y, void* d_ladj, int8_t* d_bins, uint8_t* d_inside,
                      int dtype, void* stream);
 
+/* Sampling schedule.  zuko inverts an autoregressive transform with `passes` full sweeps of the hyper-network; the
+ * features of order group s are final after sweep s and every later sweep recomputes them to the same value.  Given the
+ * effective orders (zuko `MaskedAutoregressiveTransform.order`, the buffer `transforms.{t}.order` of a checkpoint,
+ * values 0..passes-1) as a HOST array [transforms][features], this marks per sweep the last-layer feature chunks that
+ * hold a feature becoming final there; mf_flow_sample then evaluates only those.  Optional: after
+ * mf_flow_pack_weights every chunk is evaluated in every sweep (the literal algorithm); results are the same.
+ * Synchronises the stream.
+ */
+int mf_flow_set_sample_schedule(const mf_flow_desc* desc, const int32_t* h_orders, int dtype, int gemm, void* d_blob,
+                                int64_t blob_bytes, void* stream);
+
 /* Backward of the forward spline of mf_rqs_transform (plain MF_UNIV_RQS): gradients of a scalar loss w.r.t. the packed
  * parameters [n, 3K-1] and w.r.t. x [n], given dL/dy [n] and dL/dladj [n] (d_grad_ladj may be NULL = 0).
  * Replaces what torch autograd derives from zuko MonotonicRQSTransform.call_and_ladj in the reference's training steps

@@ -129,6 +129,16 @@ def flow_pack_weights(desc, weights, biases, masks, dtype, gemm, blob):
     check(rc, "mf_flow_pack_weights")
 
 
+def flow_set_sample_schedule(desc, orders, dtype, gemm, blob):
+    """Mark, per sweep, the last-layer chunks whose features become final there (mf_flow_set_sample_schedule).
+    orders: host int32 array [transforms][features] of zuko's effective orders."""
+    arr = (ctypes.c_int32 * len(orders))(*[int(v) for v in orders])
+    with torch.cuda.device(blob.device):
+        rc = lib().mf_flow_set_sample_schedule(ctypes.byref(desc), arr, ctypes.c_int(_dtype_code(dtype)), ctypes.c_int(gemm),
+                                               _ptr(blob), ctypes.c_int64(blob.numel()), _stream(blob.device))
+    check(rc, "mf_flow_set_sample_schedule")
+
+
 def _flow_workspace(desc, n, dtype, gemm, op, device):
     L = lib()
     L.mf_flow_workspace_bytes.restype = ctypes.c_int64

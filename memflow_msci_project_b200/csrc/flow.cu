@@ -254,7 +254,19 @@ flow_kernel(const __grid_constant__ FlowLayout L, const __grid_constant__ FlowKe
           lda = L.buf_w;
         }
         T* par = ((Lh - 1) & 1) ? buf0 : buf1;  // the buffer not holding the last hidden layer
+        // sampling: a chunk is evaluated in sweep `sw` only if one of its features becomes final there (its inputs
+        // are final, later sweeps would recompute the same value; the other features of the pass are provisional
+        // and masked out of everything that is kept) -- same result as zuko's full sweeps, fewer last-layer GEMMs
+        const unsigned long long live = (args.mode == 1 && args.sched) ? args.sched[(size_t)t * MF_MAX_FEATURES + sw] : ~0ull;
         for (int g = 0; g < L.n_chunks; ++g) {
+          if (!((live >> g) & 1ull)) {
+            const int f0s = g * L.fpc, nfs = min(L.fpc, D - f0s);
+            for (int p = tid; p < TM * nfs; p += kThreads) {
+              const int m = p % TM, f = f0s + p / TM;
+              xnew[(size_t)m * D + f] = in0[(size_t)m * L.in0_ld + f];
+            }
+            continue;
+          }
           const T* wl = tb + L.w_off[Lh] + (size_t)g * L.chunk_stride;
           const T* bl = tb + L.b_off[Lh] + (size_t)g * L.chunk_stride;
           for (int c0 = 0; c0 < L.pw_ld; c0 += kNC)
@@ -283,6 +295,7 @@ flow_kernel(const __grid_constant__ FlowLayout L, const __grid_constant__ FlowKe
           }
           __syncthreads();
         }
+        __syncthreads();
         // ---- x <- transformed values; ladj += sum over features (DependentTransform(.., 1))
         for (int i = tid; i < TM * D; i += kThreads) {
           const int m = i / D, f = i % D;
@@ -362,6 +375,11 @@ int launch_flow(const FlowLayout& L, const FlowKernelArgs& a, const BaseParams& 
   return MF_EUNSUPPORTED;
 }
 
+inline long long exact_sched_offset(const FlowLayout& L, int dtype) {  // 8-byte aligned end of the weight region
+  const long long w = (long long)L.t_stride * L.T * (dtype == MF_F32 ? 4 : 8);
+  return (w + 7) / 8 * 8;
+}
+
 inline bool is_tcgen05(int gemm) { return gemm == MF_GEMM_TC_3XF16 || gemm == MF_GEMM_TC_BF16; }
 
 int check_flow_common(const mf_flow_desc* desc, int dtype, int gemm) {
@@ -391,7 +409,7 @@ int64_t mf_flow_blob_bytes(const mf_flow_desc* desc, int dtype, int gemm) {
   }
   FlowLayout L;
   if (make_flow_layout(*desc, &L) != MF_OK) return -1;
-  return (int64_t)L.t_stride * L.T * (dtype == MF_F32 ? 4 : 8);
+  return exact_sched_offset(L, dtype) + kSchedBytes;
 }
 
 int mf_flow_pack_weights(const mf_flow_desc* desc, const void* const* d_weights,
@@ -405,7 +423,7 @@ int mf_flow_pack_weights(const mf_flow_desc* desc, const void* const* d_weights,
   FlowLayout L;
   rc = make_flow_layout(*desc, &L);
   if (rc != MF_OK) return rc;
-  const int64_t need = (int64_t)L.t_stride * L.T * (dtype == MF_F32 ? 4 : 8);
+  const int64_t need = exact_sched_offset(L, dtype) + kSchedBytes;
   MF_REQUIRE(blob_bytes >= need, "blob too small: %lld < %lld bytes", (long long)blob_bytes, (long long)need);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int nl = L.n_layers;
@@ -433,6 +451,7 @@ int mf_flow_pack_weights(const mf_flow_desc* desc, const void* const* d_weights,
     rc = post_launch("flow_pack_kernel");
     if (rc != MF_OK) return rc;
   }
+  MF_CUDA_CHECK(cudaMemsetAsync((char*)d_blob + exact_sched_offset(L, dtype), 0xFF, kSchedBytes, st));
   if (gemm == MF_GEMM_MMA_3XF16) return flow_mma_presplit(L, (float*)d_blob, st);
   return MF_OK;
 }
@@ -457,8 +476,11 @@ static int flow_run(const mf_flow_desc* desc, const FlowKernelArgs& a, int dtype
   BaseParams bp;
   for (int f = 0; f < MF_MAX_FEATURES; ++f) { bp.a[f] = desc->base_a[f]; bp.b[f] = desc->base_b[f]; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (gemm == MF_GEMM_MMA_3XF16) return flow_mma_run(L, a, bp, st);
-  return dtype == MF_F32 ? launch_flow<float>(L, a, bp, st) : launch_flow<double>(L, a, bp, st);
+  FlowKernelArgs as = a;
+  if (a.mode == 1)
+    as.sched = reinterpret_cast<const unsigned long long*>(static_cast<const char*>(a.blob) + exact_sched_offset(L, dtype));
+  if (gemm == MF_GEMM_MMA_3XF16) return flow_mma_run(L, as, bp, st);
+  return dtype == MF_F32 ? launch_flow<float>(L, as, bp, st) : launch_flow<double>(L, as, bp, st);
 }
 
 int mf_flow_log_prob(const mf_flow_desc* desc, const void* d_blob, const void* d_x, const void* d_ctx,
@@ -497,6 +519,42 @@ int mf_flow_sample(const mf_flow_desc* desc, const void* d_blob, const void* d_n
   a.mode = 1; a.passes = desc->passes; a.base = desc->base; a.univariate = desc->univariate;
   a.bound = desc->bound; a.slope = desc->slope;
   return flow_run(desc, a, dtype, gemm, stream);
+}
+
+int mf_flow_set_sample_schedule(const mf_flow_desc* desc, const int32_t* h_orders, int dtype, int gemm, void* d_blob,
+                                int64_t blob_bytes, void* stream) {
+  int rc = check_flow_common(desc, dtype, gemm);
+  if (rc != MF_OK) return rc;
+  MF_REQUIRE(h_orders && d_blob, "mf_flow_set_sample_schedule: null argument");
+  MF_REQUIRE(desc->passes >= 1 && desc->passes <= desc->features, "passes=%d outside 1..features", desc->passes);
+  long long off = 0;
+  int fpc = 1;
+  if (is_tcgen05(gemm)) {
+    rc = flow_tc_sched_layout(*desc, gemm, &off, &fpc);
+    if (rc != MF_OK) return rc;
+  } else {
+    FlowLayout L;
+    rc = make_flow_layout(*desc, &L);
+    if (rc != MF_OK) return rc;
+    off = exact_sched_offset(L, dtype);
+    fpc = L.fpc;
+  }
+  MF_REQUIRE(blob_bytes >= off + kSchedBytes, "blob too small for the sampling schedule");
+  static thread_local unsigned long long words[MF_MAX_TRANSFORMS * MF_MAX_FEATURES];
+  for (int t = 0; t < desc->transforms; ++t)
+    for (int s = 0; s < MF_MAX_FEATURES; ++s) {
+      unsigned long long m = 0;
+      for (int f = 0; f < desc->features; ++f) {
+        const int group = h_orders[t * desc->features + f];
+        MF_REQUIRE(group >= 0 && group < desc->passes, "order[%d][%d]=%d outside 0..passes-1", t, f, group);
+        if (group == s) m |= 1ull << (f / fpc);
+      }
+      words[t * MF_MAX_FEATURES + s] = m;
+    }
+  MF_CUDA_CHECK(cudaMemcpyAsync((char*)d_blob + off, words, (size_t)desc->transforms * MF_MAX_FEATURES * 8,
+                                cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+  MF_CUDA_CHECK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));  // `words` is reused by the next call
+  return MF_OK;
 }
 
 }  // extern "C"

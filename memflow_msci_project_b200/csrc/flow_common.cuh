@@ -88,6 +88,7 @@ struct FlowKernelArgs {
   void* ladj;
   int8_t* bins;
   uint8_t* inside;
+  const unsigned long long* sched;  // sampling: [T][MF_MAX_FEATURES] chunk bitmasks per sweep (NULL: every chunk every sweep)
   void* work;         // caller-provided scratch (mf_flow_workspace_bytes)
   long long work_bytes;
   int ctx_group;      // x rows per context row (>= 1)
@@ -104,6 +105,10 @@ struct BaseParams {
 };
 
 
+// Sampling schedule kept at the tail of every blob: word [t][s] has bit g set when feature chunk g of transform t holds a
+// feature that becomes final in sweep s (mf_flow_set_sample_schedule); all ones after packing = zuko's literal sweeps.
+constexpr long long kSchedBytes = (long long)MF_MAX_TRANSFORMS * MF_MAX_FEATURES * 8;
+
 // warp-level MMA path for wide hyper-networks (flow_mma.cu); uses the blob of the exact path
 struct FlowLayout;
 struct FlowKernelArgs;
@@ -117,6 +122,7 @@ int flow_tc_pack(const mf_flow_desc& d, const void* const* w, const void* const*
                  int gemm, void* blob, long long blob_bytes, cudaStream_t st);
 int flow_tc_run(const mf_flow_desc& d, const FlowKernelArgs& a, const BaseParams& bp, int gemm, cudaStream_t st);
 long long flow_tc_workspace_bytes(const mf_flow_desc& d, long long n, int gemm, int op);
+int flow_tc_sched_layout(const mf_flow_desc& d, int gemm, long long* offset, int* features_per_chunk);
 
 #ifdef __CUDACC__
 template <typename T> struct FM;

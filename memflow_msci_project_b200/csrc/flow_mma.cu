@@ -374,7 +374,17 @@ flow_mma_kernel(const __grid_constant__ FlowLayout L, const __grid_constant__ Fl
           cur = act;
           lda = S.ldA;
         }
+        // sampling: only the chunks holding a feature that becomes final in this sweep (flow.cu, same schedule)
+        const unsigned long long live = (args.mode == 1 && args.sched) ? args.sched[(size_t)t * MF_MAX_FEATURES + sw] : ~0ull;
         for (int gch = 0; gch < L.n_chunks; ++gch) {
+          if (!((live >> gch) & 1ull)) {
+            const int f0s = gch * L.fpc, nfs = min(L.fpc, D - f0s);
+            for (int p = tid; p < kWM * nfs; p += kWThreads) {
+              const int m = p % kWM, f = f0s + p / kWM;
+              xnew[(size_t)m * D + f] = xcur[(size_t)m * D + f];
+            }
+            continue;
+          }
           const float* wl = tb + L.w_off[Lh] + (size_t)gch * L.chunk_stride;
           const float* bl = tb + L.b_off[Lh] + (size_t)gch * L.chunk_stride;
           mma_layer<1, false>(cur, lda, L.kpad[Lh], wl, L.pw_ld, L.pw_ld, bl, par, S.ldP, false, wstage);
@@ -402,6 +412,7 @@ flow_mma_kernel(const __grid_constant__ FlowLayout L, const __grid_constant__ Fl
           }
           __syncthreads();
         }
+        __syncthreads();
         for (int i = tid; i < kWM * D; i += kWThreads) {
           const int m = i / D;
           if (m < rows) xcur[i] = xnew[i];

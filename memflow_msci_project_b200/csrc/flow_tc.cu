@@ -823,11 +823,24 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
+static long long tc_sched_offset(const TcLayout& L) {  // sampling schedule after the biases, 8-byte aligned
+  return (L.bias_off + (long long)L.bias_stride * L.T * 4 + 7) / 8 * 8;
+}
+
 int flow_tc_blob_bytes(const mf_flow_desc& d, int gemm, long long* bytes) {
   TcLayout L;
   int rc = make_tc_layout(d, gemm, &L);
   if (rc != MF_OK) return rc;
-  *bytes = L.bias_off + (long long)L.bias_stride * L.T * 4;
+  *bytes = tc_sched_offset(L) + kSchedBytes;
+  return MF_OK;
+}
+
+int flow_tc_sched_layout(const mf_flow_desc& d, int gemm, long long* offset, int* features_per_chunk) {
+  TcLayout L;
+  int rc = make_tc_layout(d, gemm, &L);
+  if (rc != MF_OK) return rc;
+  *offset = tc_sched_offset(L);
+  *features_per_chunk = std::max(1, 128 / L.PFt);
   return MF_OK;
 }
 
@@ -837,7 +850,7 @@ int flow_tc_pack(const mf_flow_desc& d, const void* const* w, const void* const*
   TcLayout L;
   int rc = make_tc_layout(d, gemm, &L);
   if (rc != MF_OK) return rc;
-  const long long need = L.bias_off + (long long)L.bias_stride * L.T * 4;
+  const long long need = tc_sched_offset(L) + kSchedBytes;
   MF_REQUIRE(blob_bytes >= need, "blob too small: %lld < %lld bytes", blob_bytes, need);
   const int nl = d.n_hidden + 1;
   for (int t = 0; t < L.T; ++t) {
@@ -854,6 +867,7 @@ int flow_tc_pack(const mf_flow_desc& d, const void* const* w, const void* const*
     rc = post_launch("flow_tc_pack_kernel");
     if (rc != MF_OK) return rc;
   }
+  MF_CUDA_CHECK(cudaMemsetAsync((char*)blob + tc_sched_offset(L), 0xFF, kSchedBytes, st));
   return MF_OK;
 }
 

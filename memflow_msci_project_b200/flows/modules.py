@@ -498,6 +498,8 @@ class MAF(nn.Module):
             nbytes = _cabi.flow_blob_bytes(desc, dtype, gemm)
             blob = torch.empty(nbytes, dtype=torch.uint8, device=device)
             _cabi.flow_pack_weights(desc, ws, bs, ms, dtype, gemm, blob)
+            orders = [int(v) for t in core for v in t.order.tolist()]
+            _cabi.flow_set_sample_schedule(desc, orders, dtype, gemm, blob)
             cached = (key, blob)
             self._blob_cache[gemm] = cached
         base_key = tuple((t.data_ptr(), t._version) for t in self.base.tensors())

@@ -562,3 +562,27 @@ def test_gemm_auto_picks_the_widest_fitting_tensor_path(cuda):
             flow.gemm = expect
             b = flow(c).log_prob(x)
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("name,gemm,dtype", [("UF", flows.modules.GEMM_EXACT, torch.float64), ("UF", flows.modules.GEMM_MMA_3XF16, torch.float32),
+                                             ("TF-A", flows.modules.GEMM_EXACT, torch.float32), ("TF-B", flows.modules.GEMM_EXACT, torch.float64)])
+def test_sample_schedule_equals_literal_sweeps(cuda, name, gemm, dtype):
+    """mf_flow_set_sample_schedule (only the chunks whose features become final in a sweep) gives bit-for-bit the samples
+    of zuko's literal algorithm (every chunk in every sweep = the blob right after mf_flow_pack_weights)."""
+    from memflow_msci_project_b200 import _cabi
+    flow = build(name, cuda, dtype, mode="stress")
+    flow.gemm = gemm
+    _, c = inputs(flow, 777, 4, cuda, dtype)
+    noise = torch.randn(777, flow.features, dtype=dtype, device=cuda, generator=torch.Generator(device=cuda).manual_seed(3))
+    with torch.no_grad():
+        xs = flow(c)._inverse(noise)                            # scheduled (the host mirror sets the schedule when packing)
+    desc, blob = flow.packed(cuda, dtype, identity_base=True, gemm=gemm)
+    params = [(lin.weight, lin.bias, lin.mask) for t in flow.core_transforms() for lin in t.hyper.linears()]
+    ws = [p[0].detach().to(dtype).contiguous() for p in params]
+    bs = [p[1].detach().to(dtype).contiguous() for p in params]
+    ms = [p[2].detach().to(torch.uint8).contiguous() for p in params]
+    blob2 = torch.empty_like(blob)
+    _cabi.flow_pack_weights(desc, ws, bs, ms, dtype, gemm, blob2)  # schedule = all chunks, all sweeps
+    x2 = torch.empty_like(noise)
+    _cabi.flow_sample(desc, blob2, noise.contiguous(), c.contiguous(), x2, gemm)
+    assert torch.equal(xs, x2)
