@@ -549,6 +549,7 @@ int mf_flow_set_sample_schedule(const mf_flow_desc* desc, const int32_t* h_order
         MF_REQUIRE(group >= 0 && group < desc->passes, "order[%d][%d]=%d outside 0..passes-1", t, f, group);
         if (group == s) m |= 1ull << (f / fpc);
       }
+      if (m == 0) m = 1;  // a sweep without a chunk would leave the kernels' job sequence without its last-layer step
       words[t * MF_MAX_FEATURES + s] = m;
     }
   MF_CUDA_CHECK(cudaMemcpyAsync((char*)d_blob + off, words, (size_t)desc->transforms * MF_MAX_FEATURES * 8,

@@ -419,6 +419,14 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
   const int n_units = L.T * sweeps;                    // one unit = one hyper-network evaluation of a tile
   const unsigned char* blob = static_cast<const unsigned char*>(args.blob);
   const float* bias_all = reinterpret_cast<const float*>(blob + L.bias_off);
+  // sampling schedule (mf_flow_set_sample_schedule): in sweep s only the last-layer chunks holding a feature that becomes
+  // final there are evaluated; every role walks the same (unit, job) sequence and skips the same jobs
+  const unsigned long long* sched = inverse ? args.sched : nullptr;
+  auto job_live = [&](int unit, int ji) -> bool {
+    if (sched == nullptr || !L.job[ji].last) return true;
+    const int tr = L.T - 1 - unit / sweeps;
+    return (sched[(size_t)tr * MF_MAX_FEATURES + (unit % sweeps)] >> (ji - L.L)) & 1ull;
+  };
 
   if (tid == 0) {
     for (int s = 0; s < kMaxStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
@@ -444,6 +452,7 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
           const int tr = inverse ? (L.T - 1 - unit / sweeps) : unit;
           const unsigned char* tb = blob + (long long)tr * L.t_stride;
           for (int ji = 0; ji < L.njobs; ++ji) {
+            if (!job_live(unit, ji)) continue;
             const TcJob& j = L.job[ji];
             const uint32_t part_bytes = (uint32_t)j.N * 128u;
             for (int kb = 0; kb < j.nkb; ++kb, ++it) {
@@ -472,14 +481,18 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
     for (long long p = blockIdx.x; p < n_pairs; p += gridDim.x) {
       const int nact = (2 * p + 1 < n_tiles) ? 2 : 1;  // odd tile count: slot 1 idles in the last pair
       for (int unit = 0; unit < n_units; ++unit) {
+        bool first_last = true;  // the first EXECUTED last-layer chunk of a unit waits for the last hidden activations
         for (int ji = 0; ji < L.njobs; ++ji) {
+          if (!job_live(unit, ji)) continue;
           const TcJob& j = L.job[ji];
           const uint32_t idesc = tc::make_idesc_f16(NSPLIT == 3 ? 0 : 1, 128, j.N);
+          const bool wait_a = j.last ? first_last : (j.needs_a != 0);
+          if (j.last) first_last = false;
           for (int t = 0; t < nact; ++t) {
             const uint32_t d_tmem = tmem + (uint32_t)(t * 256);
             const uint32_t a_tmem = d_tmem + 128;  // hi plane; lo plane 64 columns further
             const uint32_t a_base = smem_u32(a_buf + (size_t)t * kParts * kPlane);
-            if (j.needs_a) { mbar_wait(&a_ready[t], aph[t]); aph[t] ^= 1; }
+            if (wait_a) { mbar_wait(&a_ready[t], aph[t]); aph[t] ^= 1; }
             if (jobctr[t] >= 1) mbar_wait(&acc_free[t], (jobctr[t] - 1) & 1);  // accumulator drained
             MF_TRACE(lane == 0, 100 + 10 * t + ji);
             tc::fence_after_thread_sync();
@@ -687,6 +700,7 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
         fence_proxy_async_smem();
         mbar_arrive(&a_ready[t]);
         for (int ji = 0; ji < L.njobs; ++ji) {
+          if (!job_live(unit, ji)) continue;
           const TcJob& j = L.job[ji];
           const uint32_t jpar = jobctr & 1;
           ++jobctr;
@@ -696,6 +710,9 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
           {
             int ju = unit, jn = ji + 1;
             if (jn == L.njobs) { jn = 0; ++ju; }
+            while (ju < n_units && !job_live(ju, jn)) {  // next job that is actually executed
+              if (++jn == L.njobs) { jn = 0; ++ju; }
+            }
             if (ju < n_units) {
               const int trn = inverse ? (L.T - 1 - ju / sweeps) : ju;
               const TcJob& nj = L.job[jn];
@@ -890,6 +907,8 @@ int flow_tc_run(const mf_flow_desc& d, const FlowKernelArgs& a, const BaseParams
   int rc = make_tc_layout(d, gemm, &L);
   if (rc != MF_OK) return rc;
   MF_REQUIRE(a.z != nullptr, "tensor-core flow path needs the z / x output buffer (it is the working copy of x)");
+  FlowKernelArgs a_run = a;
+  if (a.mode == 1) a_run.sched = reinterpret_cast<const unsigned long long*>(static_cast<const char*>(a.blob) + tc_sched_offset(L));
   if (a.ctx_group > 1) {
     set_error("context grouping (ctx_group=%d) is implemented on the MF_GEMM_EXACT path only", a.ctx_group);
     return MF_EUNSUPPORTED;
@@ -916,7 +935,7 @@ int flow_tc_run(const mf_flow_desc& d, const FlowKernelArgs& a, const BaseParams
 #define MF_TC_LAUNCH(NS, EWV)                                                                                   \
   do {                                                                                                          \
     MF_CUDA_CHECK(cudaFuncSetAttribute(flow_tc_kernel<NS, EWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    flow_tc_kernel<NS, EWV><<<grid, (3 + 8 * EWV) * 32, smem, st>>>(L, a, bp);                                  \
+    flow_tc_kernel<NS, EWV><<<grid, (3 + 8 * EWV) * 32, smem, st>>>(L, a_run, bp);                                  \
   } while (0)
   if (L.nsplit == 3) { if (ew == 2) MF_TC_LAUNCH(3, 2); else MF_TC_LAUNCH(3, 1); }
   else               { if (ew == 2) MF_TC_LAUNCH(1, 2); else MF_TC_LAUNCH(1, 1); }

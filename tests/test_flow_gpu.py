@@ -565,7 +565,9 @@ def test_gemm_auto_picks_the_widest_fitting_tensor_path(cuda):
 
 
 @pytest.mark.parametrize("name,gemm,dtype", [("UF", flows.modules.GEMM_EXACT, torch.float64), ("UF", flows.modules.GEMM_MMA_3XF16, torch.float32),
-                                             ("TF-A", flows.modules.GEMM_EXACT, torch.float32), ("TF-B", flows.modules.GEMM_EXACT, torch.float64)])
+                                             ("TF-A", flows.modules.GEMM_EXACT, torch.float32), ("TF-B", flows.modules.GEMM_EXACT, torch.float64),
+                                             ("TF-A", flows.modules.GEMM_TC_3XF16, torch.float32), ("TF-B", flows.modules.GEMM_TC_3XF16, torch.float32),
+                                             ("NCSF", flows.modules.GEMM_TC_3XF16, torch.float32)])
 def test_sample_schedule_equals_literal_sweeps(cuda, name, gemm, dtype):
     """mf_flow_set_sample_schedule (only the chunks whose features become final in a sweep) gives bit-for-bit the samples
     of zuko's literal algorithm (every chunk in every sweep = the blob right after mf_flow_pack_weights)."""
