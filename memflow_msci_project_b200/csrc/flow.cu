@@ -409,7 +409,7 @@ int64_t mf_flow_blob_bytes(const mf_flow_desc* desc, int dtype, int gemm) {
   }
   FlowLayout L;
   if (make_flow_layout(*desc, &L) != MF_OK) return -1;
-  return exact_sched_offset(L, dtype) + kSchedBytes;
+  return exact_sched_offset(L, dtype) + kSchedBytes + (gemm == MF_GEMM_MMA_3XF16 ? kKlimBytes : 0);
 }
 
 int mf_flow_pack_weights(const mf_flow_desc* desc, const void* const* d_weights,
@@ -423,7 +423,7 @@ int mf_flow_pack_weights(const mf_flow_desc* desc, const void* const* d_weights,
   FlowLayout L;
   rc = make_flow_layout(*desc, &L);
   if (rc != MF_OK) return rc;
-  const int64_t need = exact_sched_offset(L, dtype) + kSchedBytes;
+  const int64_t need = exact_sched_offset(L, dtype) + kSchedBytes + (gemm == MF_GEMM_MMA_3XF16 ? kKlimBytes : 0);
   MF_REQUIRE(blob_bytes >= need, "blob too small: %lld < %lld bytes", (long long)blob_bytes, (long long)need);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int nl = L.n_layers;
@@ -452,7 +452,9 @@ int mf_flow_pack_weights(const mf_flow_desc* desc, const void* const* d_weights,
     if (rc != MF_OK) return rc;
   }
   MF_CUDA_CHECK(cudaMemsetAsync((char*)d_blob + exact_sched_offset(L, dtype), 0xFF, kSchedBytes, st));
-  if (gemm == MF_GEMM_MMA_3XF16) return flow_mma_presplit(L, (float*)d_blob, st);
+  if (gemm == MF_GEMM_MMA_3XF16)
+    return flow_mma_presplit(L, (float*)d_blob,
+                             reinterpret_cast<unsigned short*>((char*)d_blob + exact_sched_offset(L, dtype) + kSchedBytes), st);
   return MF_OK;
 }
 
@@ -479,7 +481,10 @@ static int flow_run(const mf_flow_desc* desc, const FlowKernelArgs& a, int dtype
   FlowKernelArgs as = a;
   if (a.mode == 1)
     as.sched = reinterpret_cast<const unsigned long long*>(static_cast<const char*>(a.blob) + exact_sched_offset(L, dtype));
-  if (gemm == MF_GEMM_MMA_3XF16) return flow_mma_run(L, as, bp, st);
+  if (gemm == MF_GEMM_MMA_3XF16) {
+    as.klim = reinterpret_cast<const unsigned short*>(static_cast<const char*>(a.blob) + exact_sched_offset(L, dtype) + kSchedBytes);
+    return flow_mma_run(L, as, bp, st);
+  }
   return dtype == MF_F32 ? launch_flow<float>(L, as, bp, st) : launch_flow<double>(L, as, bp, st);
 }
 

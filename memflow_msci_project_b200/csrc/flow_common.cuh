@@ -88,6 +88,7 @@ struct FlowKernelArgs {
   void* ladj;
   int8_t* bins;
   uint8_t* inside;
+  const unsigned short* klim;        // mma mode: k-step limits per 128-column block (NULL: full K)
   const unsigned long long* sched;  // sampling: [T][MF_MAX_FEATURES] chunk bitmasks per sweep (NULL: every chunk every sweep)
   void* work;         // caller-provided scratch (mf_flow_workspace_bytes)
   long long work_bytes;
@@ -114,7 +115,12 @@ struct FlowLayout;
 struct FlowKernelArgs;
 struct BaseParams;
 int flow_mma_run(const FlowLayout& L, const FlowKernelArgs& a, const BaseParams& bp, cudaStream_t st);
-int flow_mma_presplit(const FlowLayout& L, float* blob, cudaStream_t st);  // in-place: fp32 k-major rows -> fp16 hi/lo k-pairs
+// in place: fp32 k-major rows -> fp16 hi/lo k-pairs; then the k-step limits of every 128-column block (klim region)
+int flow_mma_presplit(const FlowLayout& L, float* blob, unsigned short* klim, cudaStream_t st);
+// mma mode keeps, after the sampling schedule, [T][kKlimEntries] uint16: k16-steps up to the last nonzero weight row of
+// every 128-column block (hidden layer l, block nb -> 4 l + nb; last-layer chunk g -> 32 + g)
+constexpr int kKlimEntries = 128;
+constexpr long long kKlimBytes = (long long)MF_MAX_TRANSFORMS * kKlimEntries * 2;
 
 // tcgen05 path (flow_tc.cu)
 int flow_tc_blob_bytes(const mf_flow_desc& d, int gemm, long long* bytes);

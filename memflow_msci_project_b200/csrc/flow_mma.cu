@@ -60,7 +60,7 @@ constexpr int kNS = 5;  // weight ring depth (stages of [16 k-rows][128 columns]
 template <int NB, bool SPLIT_OUT>
 __device__ __forceinline__ void mma_layer(const float* A, int lda, int K, const float* __restrict__ Wt, int ldw,
                                           int ncols, const float* __restrict__ bias, float* Out, int ldo, bool relu,
-                                          float* wstage) {
+                                          float* wstage, const unsigned short* __restrict__ klim) {
   constexpr int NT = 2;
   constexpr int NBW = 64 * NT;                        // columns per N-block
   constexpr int LDS = NBW + 4;                        // staged row stride: 2t*LDS + g hits 32 distinct banks
@@ -76,7 +76,21 @@ __device__ __forceinline__ void mma_layer(const float* A, int lda, int K, const 
 
   const int nk = K / kWK;
   const int nblocks = min(NB, (ncols + NBW - 1) / NBW);
-  const int total = nblocks * nk;
+  // autoregressive masks leave the weight rows beyond some k exactly zero for a whole 128-column block (hidden units
+  // sorted by degree make the masked matrices block-triangular): only the k-steps up to that row are streamed and issued
+  int nkb[NB];
+  int total = 0;
+#pragma unroll
+  for (int nb = 0; nb < NB; ++nb) {
+    nkb[nb] = (nb < nblocks) ? (klim ? max(1, min(nk, (int)klim[nb])) : nk) : 0;
+    total += nkb[nb];
+  }
+  auto steps_of = [&](int nb) {
+    int v = nkb[0];
+#pragma unroll
+    for (int i = 1; i < NB; ++i) v = (nb == i) ? nkb[i] : v;
+    return v;
+  };
   // staging: stage q of the step sequence = [8 k-pair rows][128 columns] x 8 bytes of (block nb, k-chunk kc); ncols
   // is a multiple of 128, so every thread copies two 16-byte pieces per stage: pair rows tid/64 and tid/64 + 4,
   // columns 2 (tid % 64).  A pair row of the blob is 2 ldw floats long.
@@ -88,7 +102,7 @@ __device__ __forceinline__ void mma_layer(const float* A, int lda, int K, const 
       const float* src = Wt + (size_t)(st_kc * (kWK / 2) + st_row) * (2 * ldw) + st_nb * (2 * NBW) + st_col;
       cp16(dst, src);
       cp16(dst + 4 * (2 * LDS), src + (size_t)4 * (2 * ldw));
-      if (++st_kc == nk) { st_kc = 0; ++st_nb; }
+      if (++st_kc == steps_of(st_nb)) { st_kc = 0; ++st_nb; }
     }
     ++st_step;
     st_slot = (st_slot + 1 == kNS) ? 0 : st_slot + 1;
@@ -102,7 +116,7 @@ __device__ __forceinline__ void mma_layer(const float* A, int lda, int K, const 
   for (int nb = 0; nb < NB; ++nb) {
     if (nb >= nblocks) break;
     const bool mine = nb * NBW + n_w < ncols;  // warp-uniform
-    for (int kc = 0; kc < nk; ++kc, ++s) {
+    for (int kc = 0; kc < nkb[nb]; ++kc, ++s) {
       cp_wait<kNS - 2>();
       __syncthreads();     // stage s visible to all; everyone is done with step s-1, whose buffer is refilled next
       stage();
@@ -370,7 +384,8 @@ flow_mma_kernel(const __grid_constant__ FlowLayout L, const __grid_constant__ Fl
         const float* cur = in0;
         int lda = S.ld0;
         for (int l = 0; l < Lh; ++l) {
-          mma_layer<NB, true>(cur, lda, L.kpad[l], tb + L.w_off[l], L.ld[l], L.ld[l], tb + L.b_off[l], act, S.ldA, true, wstage);
+          mma_layer<NB, true>(cur, lda, L.kpad[l], tb + L.w_off[l], L.ld[l], L.ld[l], tb + L.b_off[l], act, S.ldA, true, wstage,
+                              args.klim ? args.klim + (size_t)t * kKlimEntries + 4 * l : nullptr);
           cur = act;
           lda = S.ldA;
         }
@@ -387,7 +402,8 @@ flow_mma_kernel(const __grid_constant__ FlowLayout L, const __grid_constant__ Fl
           }
           const float* wl = tb + L.w_off[Lh] + (size_t)gch * L.chunk_stride;
           const float* bl = tb + L.b_off[Lh] + (size_t)gch * L.chunk_stride;
-          mma_layer<1, false>(cur, lda, L.kpad[Lh], wl, L.pw_ld, L.pw_ld, bl, par, S.ldP, false, wstage);
+          mma_layer<1, false>(cur, lda, L.kpad[Lh], wl, L.pw_ld, L.pw_ld, bl, par, S.ldP, false, wstage,
+                              args.klim ? args.klim + (size_t)t * kKlimEntries + 32 + gch : nullptr);
           // ---- splines of the features of this chunk: four lanes per (row, feature)
           const int f0 = gch * L.fpc;
           const int nf = min(L.fpc, D - f0);
@@ -465,9 +481,23 @@ __global__ void flow_mma_presplit_kernel(float* W, int kpad, int ld) {
   }
 }
 
+// one thread per 128-column block: k16-steps up to the last pair row holding a nonzero weight (presplit layout)
+__global__ void flow_mma_klimit_kernel(const float* W, int kpad, int ld, unsigned short* out) {
+  const int nb = blockIdx.x * blockDim.x + threadIdx.x;
+  if (nb * 128 >= ld) return;
+  int last = -1;
+  for (int kp = kpad / 2 - 1; kp >= 0 && last < 0; --kp) {
+    const uint2* row = reinterpret_cast<const uint2*>(W + (size_t)kp * 2 * ld) + nb * 128;
+    for (int n = 0; n < 128; ++n)
+      if ((row[n].x & 0x7fff7fffu) != 0u) { last = kp; break; }
+  }
+  out[nb] = (unsigned short)(last < 0 ? 1 : last / 8 + 1);
+}
+
 }  // namespace
 
-int flow_mma_presplit(const FlowLayout& L, float* blob, cudaStream_t st) {
+int flow_mma_presplit(const FlowLayout& L, float* blob, unsigned short* klim, cudaStream_t st) {
+  MF_CUDA_CHECK(cudaMemsetAsync(klim, 0xFF, kKlimBytes, st));  // 0xFFFF = no limit for entries nobody computes
   const int Lh = L.n_layers - 1;
   for (int t = 0; t < L.T; ++t) {
     float* tb = blob + (size_t)t * L.t_stride;
@@ -475,12 +505,23 @@ int flow_mma_presplit(const FlowLayout& L, float* blob, cudaStream_t st) {
       flow_mma_presplit_kernel<<<64, 256, 2 * L.ld[l] * sizeof(float), st>>>(tb + L.w_off[l], L.kpad[l], L.ld[l]);
       int rc = post_launch("flow_mma_presplit_kernel");
       if (rc != MF_OK) return rc;
+      if (l > 0 && l < 8) {  // layer 0 reads (x | context): the context columns come last, nothing to trim
+        flow_mma_klimit_kernel<<<1, 32, 0, st>>>(tb + L.w_off[l], L.kpad[l], L.ld[l], klim + (size_t)t * kKlimEntries + 4 * l);
+        rc = post_launch("flow_mma_klimit_kernel");
+        if (rc != MF_OK) return rc;
+      }
     }
     for (int g = 0; g < L.n_chunks; ++g) {
       flow_mma_presplit_kernel<<<64, 256, 2 * L.pw_ld * sizeof(float), st>>>(tb + L.w_off[Lh] + (size_t)g * L.chunk_stride,
                                                                             L.kpad[Lh], L.pw_ld);
       int rc = post_launch("flow_mma_presplit_kernel");
       if (rc != MF_OK) return rc;
+      if (g < kKlimEntries - 32) {
+        flow_mma_klimit_kernel<<<1, 32, 0, st>>>(tb + L.w_off[Lh] + (size_t)g * L.chunk_stride, L.kpad[Lh], L.pw_ld,
+                                                klim + (size_t)t * kKlimEntries + 32 + g);
+        rc = post_launch("flow_mma_klimit_kernel");
+        if (rc != MF_OK) return rc;
+      }
     }
   }
   return MF_OK;

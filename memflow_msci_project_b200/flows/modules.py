@@ -495,6 +495,8 @@ class MAF(nn.Module):
             ws = [p.detach().to(dtype).contiguous() for p in params[0::3]]
             bs = [p.detach().to(dtype).contiguous() for p in params[1::3]]
             ms = [p.detach().to(torch.uint8).contiguous() for p in params[2::3]]
+            if gemm == GEMM_MMA_3XF16:
+                ws, bs, ms = _sort_hidden_units(ws, bs, ms, len(core))
             nbytes = _cabi.flow_blob_bytes(desc, dtype, gemm)
             blob = torch.empty(nbytes, dtype=torch.uint8, device=device)
             _cabi.flow_pack_weights(desc, ws, bs, ms, dtype, gemm, blob)
@@ -508,6 +510,29 @@ class MAF(nn.Module):
             dent = (base_key, self.make_desc(identity_base))
             self._desc_cache[identity_base] = dent
         return dent[1], cached[1]
+
+
+def _sort_hidden_units(ws, bs, ms, n_transforms):
+    """Reorder the hidden units of every hyper-network by the number of inputs their mask lets through.
+
+    The order of hidden units is free (rows of W_l, b_l and the matching columns of W_{l+1} move together; the
+    function computed is the same up to the summation order inside a dot product).  zuko assigns autoregressive
+    degrees round-robin; sorted by degree the masked weight matrices become block-triangular, and the warp-level MMA
+    kernel stops streaming a 128-column block at its last nonzero weight row (flow_mma_klimit_kernel)."""
+    nl = len(ws) // n_transforms
+    ws, bs, ms = list(ws), list(bs), list(ms)
+    for t in range(n_transforms):
+        prev = None
+        for l in range(nl):
+            i = t * nl + l
+            w, b, m = ws[i], bs[i], ms[i]
+            if prev is not None:
+                w, m = w[:, prev], m[:, prev]
+            if l < nl - 1:
+                prev = torch.sort(m.sum(dim=1, dtype=torch.int32), stable=True).indices
+                w, b, m = w[prev], b[prev], m[prev]
+            ws[i], bs[i], ms[i] = w.contiguous(), b.contiguous(), m.contiguous()
+    return ws, bs, ms
 
 
 class NSF(MAF):
