@@ -393,7 +393,9 @@ __device__ __forceinline__ void rqs_forward_tmem_reg(uint32_t taddr, const float
 // ------------------------------------------------------------------------------------------------
 // EW = epilogue warp sets per tile slot: with EW = 2 two warps share every TMEM lane quarter and split the
 // columns of a hidden layer / the features of a spline chunk between them (16 epilogue warps per CTA).
-template <int NSPLIT, int EW>
+// INV: sampling (transforms in reverse, `passes` sweeps each) -- a compile-time flag so that the log_prob kernel carries
+// none of the sweep / schedule logic
+template <int NSPLIT, int EW, bool INV>
 __global__ void __launch_bounds__((3 + 8 * EW) * 32, 1)
 flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowKernelArgs args,
                const __grid_constant__ BaseParams bp) {
@@ -414,7 +416,7 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
   const long long n = args.n;
   const long long n_tiles = (n + 127) / 128;
   const long long n_pairs = (n_tiles + 1) / 2;
-  const bool inverse = args.mode == 1;                 // sampling: transforms in reverse, `passes` sweeps each
+  constexpr bool inverse = INV;
   const int sweeps = inverse ? args.passes : 1;
   const int n_units = L.T * sweeps;                    // one unit = one hyper-network evaluation of a tile
   const unsigned char* blob = static_cast<const unsigned char*>(args.blob);
@@ -932,13 +934,15 @@ int flow_tc_run(const mf_flow_desc& d, const FlowKernelArgs& a, const BaseParams
   if (a.mode == 0)
     MF_REQUIRE(a.work != nullptr && a.work_bytes >= a.n * 4, "tensor-core log_prob needs a workspace of mf_flow_workspace_bytes() bytes");
   const int ew = tc_epilogue_sets();
-#define MF_TC_LAUNCH(NS, EWV)                                                                                   \
-  do {                                                                                                          \
-    MF_CUDA_CHECK(cudaFuncSetAttribute(flow_tc_kernel<NS, EWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    flow_tc_kernel<NS, EWV><<<grid, (3 + 8 * EWV) * 32, smem, st>>>(L, a_run, bp);                                  \
+#define MF_TC_LAUNCH2(NS, EWV, INVV)                                                                                  \
+  do {                                                                                                                \
+    MF_CUDA_CHECK(cudaFuncSetAttribute(flow_tc_kernel<NS, EWV, INVV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    flow_tc_kernel<NS, EWV, INVV><<<grid, (3 + 8 * EWV) * 32, smem, st>>>(L, a_run, bp);                              \
   } while (0)
+#define MF_TC_LAUNCH(NS, EWV) do { if (a.mode == 1) MF_TC_LAUNCH2(NS, EWV, true); else MF_TC_LAUNCH2(NS, EWV, false); } while (0)
   if (L.nsplit == 3) { if (ew == 2) MF_TC_LAUNCH(3, 2); else MF_TC_LAUNCH(3, 1); }
   else               { if (ew == 2) MF_TC_LAUNCH(1, 2); else MF_TC_LAUNCH(1, 1); }
+#undef MF_TC_LAUNCH2
 #undef MF_TC_LAUNCH
   return post_launch("flow_tc_kernel");
 }
