@@ -15,7 +15,7 @@ timeout 500 ncu --set full --clock-control none --import-source on -k regex:flow
 timeout 100 python tools/profile_target.py rambo > gpurun_out/prof_rambo_plain.log 2>&1 && \
 timeout 500 ncu --set full --clock-control none --import-source on -k regex:"rambo_forward|rambo_inverse" -c 8 -o gpurun_out/prof_rambo python tools/profile_target.py rambo > gpurun_out/ncu_rambo.log 2>&1
 timeout 100 python tools/probe_issue.py > gpurun_out/probe_issue.txt 2>&1
-timeout 100 python tools/probe_issue_fixed.py >> gpurun_out/probe_issue.txt 2>&1
+timeout 100 python tools/probe_issue_batch.py >> gpurun_out/probe_issue.txt 2>&1
 timeout 100 python tools/probe_spline.py > gpurun_out/probe_spline.txt 2>&1
 timeout 400 python tools/bench_train.py --steps 3 --warmup 2 > gpurun_out/train.jsonl 2>&1
 timeout 300 python tools/bench_train.py --steps 3 --warmup 2 --no-sampling-loss >> gpurun_out/train.jsonl 2>&1
