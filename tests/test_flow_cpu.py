@@ -155,3 +155,24 @@ def test_gemm_constants_match_header():
     vals = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define (MF_GEMM_\w+) (\d+)", hdr)}
     assert vals == {"MF_GEMM_EXACT": fm.GEMM_EXACT, "MF_GEMM_TC_3XF16": fm.GEMM_TC_3XF16,
                     "MF_GEMM_TC_BF16": fm.GEMM_TC_BF16, "MF_GEMM_MMA_3XF16": fm.GEMM_MMA_3XF16}
+
+
+@pytest.mark.parametrize("D,passes,randperm", [(3, None, False), (10, 2, True), (7, 3, True), (5, 5, False)])
+def test_scheduled_inverse_equals_literal_sweeps_in_the_oracle(D, passes, randperm):
+    """The argument behind mf_flow_set_sample_schedule, checked on the CPU oracle alone: updating in sweep s only the
+    features of order group s gives exactly the samples of zuko's literal `passes` full sweeps."""
+    spec = fo.random_spec(D, 4, 8, 3, [32, 32], seed=5, passes=passes, randperm=randperm, weight_scale=3.0)
+    rng = np.random.default_rng(1)
+    z = rng.standard_normal((200, D))
+    c = rng.standard_normal((200, 4))
+    literal = fo.flow_inverse(spec, z, c)
+    y = z.copy()
+    for t in reversed(spec.transforms):
+        x = np.zeros_like(y)
+        order = np.asarray(t["order"])
+        for s in range(t["passes"]):
+            knots = fo._univariate_params(spec, t, x, c, np.float64)
+            xn = fo._uni_inverse(spec, y, knots)
+            x = np.where(order[None, :] == s, xn, x)      # only the group that becomes final in this sweep
+        y = x
+    assert np.array_equal(literal, y)
