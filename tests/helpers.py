@@ -22,7 +22,7 @@ def rel_err(a, b):
     return np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
 
 
-GOLDEN_RAMBO = ["n3_Htt", "n4_HttG", "n8_ttH_decay"]
+GOLDEN_RAMBO = ["n3_Htt", "n4_HttG", "n5_HttGG", "n6_tt_decay", "n8_ttH_decay"]
 
 
 def spec_from_module(flow):

@@ -38,6 +38,8 @@ CASES = {
     "n4_HttG": ([125.25, 172.5, 172.5, 1e-5], 768, 1234),                       # scripts/run_model_labframe_sampling.py:259
     "n3_Htt": ([125.25, 172.5, 172.5], 512, 1235),                              # notebooks/TestMadgraphChain.ipynb cell 4
     "n8_ttH_decay": ([4.7, 4.7, 4.7, 1e-3, 1e-3, 4.7, 1e-3, 1e-3], 768, 1236),  # BASELINE config 1
+    "n5_HttGG": ([125.25, 172.5, 172.5, 1e-5, 1e-5], 384, 1237),                # ttH + two ISR partons
+    "n6_tt_decay": ([80.4, 4.7, 80.4, 4.7, 1e-5, 125.25], 384, 1238),          # W b W b g H
     # n=2 is not a reference case: bisect_vec_batch returns None for zero mass columns
     # (rambo_generator.py:402-403) and generateIntermediatesMassless_batch then raises.
 }
