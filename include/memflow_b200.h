@@ -277,8 +277,8 @@ int mf_rqs_transform(const void* d_params, const void* d_x, int64_t n, int32_t b
 /* Sampling schedule.  zuko inverts an autoregressive transform with `passes` full sweeps of the hyper-network; the
  * features of order group s are final after sweep s and every later sweep recomputes them to the same value.  Given the
  * effective orders (zuko `MaskedAutoregressiveTransform.order`, the buffer `transforms.{t}.order` of a checkpoint,
- * values 0..passes-1) as a HOST array [transforms][features], this marks per sweep the last-layer feature chunks that
- * hold a feature becoming final there; mf_flow_sample then evaluates only those.  Optional: after
+ * values 0..passes-1) as a HOST array [transforms][features], this marks per sweep the features that become final
+ * there; mf_flow_sample then evaluates only those splines and only the last-layer chunks that hold one of them.  Optional: after
  * mf_flow_pack_weights every chunk is evaluated in every sweep (the literal algorithm); results are the same.
  * Synchronises the stream.
  */

@@ -259,7 +259,7 @@ flow_kernel(const __grid_constant__ FlowLayout L, const __grid_constant__ FlowKe
         // and masked out of everything that is kept) -- same result as zuko's full sweeps, fewer last-layer GEMMs
         const unsigned long long live = (args.mode == 1 && args.sched) ? args.sched[(size_t)t * MF_MAX_FEATURES + sw] : ~0ull;
         for (int g = 0; g < L.n_chunks; ++g) {
-          if (!((live >> g) & 1ull)) {
+          if (!((live >> (g * L.fpc)) & ((1ull << min(L.fpc, D - g * L.fpc)) - 1ull))) {
             const int f0s = g * L.fpc, nfs = min(L.fpc, D - f0s);
             for (int p = tid; p < TM * nfs; p += kThreads) {
               const int m = p % TM, f = f0s + p / TM;
@@ -284,6 +284,10 @@ flow_kernel(const __grid_constant__ FlowLayout L, const __grid_constant__ FlowKe
               T out, la;
               int bin;
               bool ins;
+              if (!((live >> f) & 1ull)) {  // provisional feature of this sweep: keep the current value
+                xnew[(size_t)m * D + f] = in0[(size_t)m * L.in0_ld + f];
+                continue;
+              }
               rqs_univariate<T>(pp, 1, cfg, args.mode == 1, v, out, la, bin, ins);
               xnew[(size_t)m * D + f] = out;
               if (args.mode == 0) {
@@ -552,9 +556,9 @@ int mf_flow_set_sample_schedule(const mf_flow_desc* desc, const int32_t* h_order
       for (int f = 0; f < desc->features; ++f) {
         const int group = h_orders[t * desc->features + f];
         MF_REQUIRE(group >= 0 && group < desc->passes, "order[%d][%d]=%d outside 0..passes-1", t, f, group);
-        if (group == s) m |= 1ull << (f / fpc);
+        if (group == s) m |= 1ull << f;
       }
-      if (m == 0) m = 1;  // a sweep without a chunk would leave the kernels' job sequence without its last-layer step
+      if (m == 0) m = 1;  // a sweep without a feature would leave the kernels' job sequence without its last-layer step
       words[t * MF_MAX_FEATURES + s] = m;
     }
   MF_CUDA_CHECK(cudaMemcpyAsync((char*)d_blob + off, words, (size_t)desc->transforms * MF_MAX_FEATURES * 8,

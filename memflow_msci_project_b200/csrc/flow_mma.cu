@@ -392,7 +392,7 @@ flow_mma_kernel(const __grid_constant__ FlowLayout L, const __grid_constant__ Fl
         // sampling: only the chunks holding a feature that becomes final in this sweep (flow.cu, same schedule)
         const unsigned long long live = (args.mode == 1 && args.sched) ? args.sched[(size_t)t * MF_MAX_FEATURES + sw] : ~0ull;
         for (int gch = 0; gch < L.n_chunks; ++gch) {
-          if (!((live >> gch) & 1ull)) {
+          if (!((live >> (gch * L.fpc)) & ((1ull << min(L.fpc, D - gch * L.fpc)) - 1ull))) {
             const int f0s = gch * L.fpc, nfs = min(L.fpc, D - f0s);
             for (int p = tid; p < kWM * nfs; p += kWThreads) {
               const int m = p % kWM, f = f0s + p / kWM;
@@ -410,15 +410,16 @@ flow_mma_kernel(const __grid_constant__ FlowLayout L, const __grid_constant__ Fl
           for (int p0 = 0; p0 < kWM * nf; p0 += kWThreads / 4) {  // warp-uniform trip count
             const int p = p0 + (tid >> 2);
             const int m = p % kWM, fl = min(p / kWM, nf - 1), f = f0 + fl;
-            const bool live = (p < kWM * nf) && (m < rows);
+            const bool live_q = (p < kWM * nf) && (m < rows);
+            const bool final_f = (live >> f) & 1ull;  // provisional features of this sweep keep their current value
             float* pp = par + (size_t)m * S.ldP + fl * L.PF;
             const float v = (args.mode == 0) ? xcur[(size_t)m * D + f] : ytgt[(size_t)m * D + f];
             float out, la;
             int bin;
             bool ins;
             rqs_quad(pp, cfg, args.mode == 1, v, out, la, bin, ins);
-            if (live && (tid & 3) == 0) {
-              xnew[(size_t)m * D + f] = out;
+            if (live_q && (tid & 3) == 0) {
+              xnew[(size_t)m * D + f] = final_f ? out : xcur[(size_t)m * D + f];
               if (args.mode == 0) {
                 ytgt[(size_t)m * D + f] = la;  // per-feature ladj, summed in feature order below
                 if (args.bins) args.bins[((size_t)t * args.n + tile0 + m) * D + f] = (int8_t)bin;

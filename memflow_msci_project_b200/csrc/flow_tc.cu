@@ -427,7 +427,7 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
   auto job_live = [&](int unit, int ji) -> bool {
     if (sched == nullptr || !L.job[ji].last) return true;
     const int tr = L.T - 1 - unit / sweeps;
-    return (sched[(size_t)tr * MF_MAX_FEATURES + (unit % sweeps)] >> (ji - L.L)) & 1ull;
+    return ((sched[(size_t)tr * MF_MAX_FEATURES + (unit % sweeps)] >> L.job[ji].feat0) & ((1ull << L.job[ji].nfeat) - 1ull)) != 0ull;
   };
 
   if (tid == 0) {
@@ -774,10 +774,12 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
           } else {
             // last-layer chunk: splines of the chunk's features straight out of TMEM
 #pragma unroll 1
+            const unsigned long long fmask = sched ? sched[(size_t)tr * MF_MAX_FEATURES + (unit % sweeps)] : ~0ull;
             for (int fl = eset; fl < j.nfeat; fl += EW) {  // one copy of the spline code (instruction cache)
               const int f = j.feat0 + fl;
               const float xv = xnext;
               if (fl + EW < j.nfeat && valid) xnext = xsrc[fl + EW];  // next feature's input, in flight during this spline
+              if (!((fmask >> f) & 1ull)) continue;  // sampling: provisional feature of this sweep, keeps its value
               float out, la;
               int bin;
               bool ins;
