@@ -696,7 +696,6 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
             put1(row, xcol0 + f, 0.f);
           }
         }
-        const float* bias_t = bias_all + (size_t)tr * L.bias_stride;
         // ---- layer-0 operand: the context part was staged at the tile start, the D columns of x were written
         //      by this thread when it produced them (tile start / spline output of the previous unit)
         fence_proxy_async_smem();
@@ -773,8 +772,8 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
             MF_TRACE(gt == 0, 400 + 300 * t + ji);
           } else {
             // last-layer chunk: splines of the chunk's features straight out of TMEM
-#pragma unroll 1
             const unsigned long long fmask = sched ? sched[(size_t)tr * MF_MAX_FEATURES + (unit % sweeps)] : ~0ull;
+#pragma unroll 1
             for (int fl = eset; fl < j.nfeat; fl += EW) {  // one copy of the spline code (instruction cache)
               const int f = j.feat0 + fl;
               const float xv = xnext;
