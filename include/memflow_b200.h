@@ -284,6 +284,10 @@ int mf_rqs_transform(const void* d_params, const void* d_x, int64_t n, int32_t b
  */
 int mf_flow_set_sample_schedule(const mf_flow_desc* desc, const int32_t* h_orders, int dtype, int gemm, void* d_blob,
                                 int64_t blob_bytes, void* stream);
+/* Byte offset of the schedule inside the blob: MF_MAX_TRANSFORMS x MF_MAX_FEATURES uint64 words, word [t][s] = bitmask of
+ * the features of transform t that become final in sweep s.  A caller that re-packs every training step can keep the
+ * words on the device and copy them in place instead of calling mf_flow_set_sample_schedule (which synchronises). */
+int64_t mf_flow_sched_offset(const mf_flow_desc* desc, int dtype, int gemm);
 
 /* Backward of the forward spline of mf_rqs_transform (plain MF_UNIV_RQS): gradients of a scalar loss w.r.t. the packed
  * parameters [n, 3K-1] and w.r.t. x [n], given dL/dy [n] and dL/dladj [n] (d_grad_ladj may be NULL = 0).

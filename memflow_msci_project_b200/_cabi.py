@@ -129,6 +129,15 @@ def flow_pack_weights(desc, weights, biases, masks, dtype, gemm, blob):
     check(rc, "mf_flow_pack_weights")
 
 
+def flow_sched_offset(desc, dtype, gemm):
+    L = lib()
+    L.mf_flow_sched_offset.restype = ctypes.c_int64
+    off = L.mf_flow_sched_offset(ctypes.byref(desc), ctypes.c_int(_dtype_code(dtype)), ctypes.c_int(gemm))
+    if off < 0:
+        check(-1, "mf_flow_sched_offset")
+    return int(off)
+
+
 def flow_set_sample_schedule(desc, orders, dtype, gemm, blob):
     """Mark, per sweep, the last-layer chunks whose features become final there (mf_flow_set_sample_schedule).
     orders: host int32 array [transforms][features] of zuko's effective orders."""

@@ -530,6 +530,16 @@ int mf_flow_sample(const mf_flow_desc* desc, const void* d_blob, const void* d_n
   return flow_run(desc, a, dtype, gemm, stream);
 }
 
+int64_t mf_flow_sched_offset(const mf_flow_desc* desc, int dtype, int gemm) {
+  if (check_flow_common(desc, dtype, gemm) != MF_OK) return -1;
+  long long off = 0;
+  int fpc = 1;
+  if (is_tcgen05(gemm)) return flow_tc_sched_layout(*desc, gemm, &off, &fpc) == MF_OK ? (int64_t)off : -1;
+  FlowLayout L;
+  if (make_flow_layout(*desc, &L) != MF_OK) return -1;
+  return exact_sched_offset(L, dtype);
+}
+
 int mf_flow_set_sample_schedule(const mf_flow_desc* desc, const int32_t* h_orders, int dtype, int gemm, void* d_blob,
                                 int64_t blob_bytes, void* stream) {
   int rc = check_flow_common(desc, dtype, gemm);

@@ -477,6 +477,26 @@ class MAF(nn.Module):
             return GEMM_MMA_3XF16 if (self.gemm == GEMM_AUTO and mma_ok) else GEMM_EXACT
         return gemm
 
+    def _sched_words(self, device):
+        """uint8 view of the [T][64] uint64 schedule words of mf_flow_set_sample_schedule (cached per device)."""
+        core = self.core_transforms()
+        orders = tuple(tuple(int(v) for v in t.order.tolist()) for t in core)
+        cached = getattr(self, "_sched_cache", None)
+        if cached is None or cached[0] != (str(device), orders):
+            import numpy as np
+            words = np.zeros((len(core), 64), dtype=np.uint64)
+            for ti, od in enumerate(orders):
+                for s in range(64):
+                    m = 0
+                    for f, g in enumerate(od):
+                        if g == s:
+                            m |= 1 << f
+                    words[ti, s] = m if m else 1
+            t = torch.from_numpy(words.view(np.uint8).reshape(-1).copy()).to(device)
+            cached = ((str(device), orders), t)
+            self._sched_cache = cached
+        return cached[1]
+
     def packed(self, device, dtype, identity_base=False, gemm=None):
         """(desc, blob): the kernel-side copy of the weights, rebuilt when any parameter changed."""
         gemm = self.gemm if gemm is None else gemm
@@ -500,8 +520,11 @@ class MAF(nn.Module):
             nbytes = _cabi.flow_blob_bytes(desc, dtype, gemm)
             blob = torch.empty(nbytes, dtype=torch.uint8, device=device)
             _cabi.flow_pack_weights(desc, ws, bs, ms, dtype, gemm, blob)
-            orders = [int(v) for t in core for v in t.order.tolist()]
-            _cabi.flow_set_sample_schedule(desc, orders, dtype, gemm, blob)
+            # sampling schedule (features that become final per sweep): the words depend on the orders only, so they
+            # are built once and copied device-to-device after every re-pack (no host synchronisation per step)
+            sched = self._sched_words(device)
+            off = _cabi.flow_sched_offset(desc, dtype, gemm)
+            blob[off:off + sched.numel()].copy_(sched)
             cached = (key, blob)
             self._blob_cache[gemm] = cached
         base_key = tuple((t.data_ptr(), t._version) for t in self.base.tensors())
