@@ -36,13 +36,22 @@ CONFIGS = {
     "TF-B": (flows.NSF, dict(features=3, context=65, transforms=4, bins=30, hidden_features=[128] * 2, randperm=True,
                              base=flows.DiagNormal, base_args=[torch.zeros(3), 0.35 * torch.ones(3)],
                              univariate_kwargs={"bound": 1.0}, passes=2)),
-    # configs/flow_pretrain_labframe_sampling/flow_labframe_sampling_v3f.yaml:80-94 (T reduced 6 -> 3 for oracle speed)
-    "UF": (flows.NSF, dict(features=10, context=16, transforms=3, bins=40, hidden_features=[512] * 2, randperm=True,
+    # configs/flow_pretrain_labframe_sampling/flow_labframe_sampling_v3f.yaml:80-94 (all 6 transforms)
+    "UF": (flows.NSF, dict(features=10, context=16, transforms=6, bins=40, hidden_features=[512] * 2, randperm=True,
                            base=flows.DiagNormal, base_args=[torch.zeros(10), 0.35 * torch.ones(10)],
                            univariate_kwargs={"bound": 1.1}, passes=2)),
     # ttH Transfermer per-feature flow (memflow/ttH/train_TransferFlow.ipynb cell 11)
     "TF-1D": (flows.UniformNSF, dict(features=1, context=66, bins=16, bound=1.0, transforms=5, hidden_features=[256] * 3,
                                      randperm=False, passes=None)),
+    # SURVEY Appendix B "UF-common": the most frequent unfolding-flow shape of the reference's configs (126 x K=35,
+    # 134 x T=10, 132 x H=128, L=4, coupling masks = passes 2, bound 1.5, DiagNormal(0, 0.3), random feature orders)
+    "UF-common": (flows.NSF, dict(features=10, context=32, transforms=10, bins=35, hidden_features=[128] * 4, randperm=True,
+                                  base=flows.DiagNormal, base_args=[torch.zeros(10), 0.3 * torch.ones(10)],
+                                  univariate_kwargs={"bound": 1.5}, passes=2)),
+    # K = 40 (32 reference configs) on a transfer-flow shape that fits the tcgen05 kernel
+    "TF-K40": (flows.NSF, dict(features=3, context=65, transforms=3, bins=40, hidden_features=[128] * 2, randperm=True,
+                               base=flows.DiagNormal, base_args=[torch.zeros(3), 0.35 * torch.ones(3)],
+                               univariate_kwargs={"bound": 1.1}, passes=2)),
     "NCSF": (flows.NCSF_gaussian, dict(features=2, context=8, bins=8, transforms=3, hidden_features=[64] * 2)),
     "UniformNCSF": (flows.UniformNCSF, dict(features=1, context=5, bins=10, bound=3.14159, transforms=2,
                                             hidden_features=[32] * 2)),
@@ -245,7 +254,7 @@ def test_one_dimensional_normalisation(cuda):
 
 # ------------------------------------------------------------------------------------------------
 # tensor-core paths (tcgen05): same oracle, same fp32 gate for the 3xFP16 split mode
-TC_CONFIGS = ["TF-A", "TF-B", "NCSF", "UniformNCSF", "PSNSF", "no-context"]
+TC_CONFIGS = ["TF-A", "TF-B", "UF-common", "TF-K40", "NCSF", "UniformNCSF", "PSNSF", "no-context"]
 
 
 @pytest.mark.parametrize("name", TC_CONFIGS)
@@ -282,6 +291,86 @@ def _check_split_log_prob(cuda, name, mode, N, gemm):
     mism = (bins.cpu().numpy() != k_ref) | (inside.cpu().numpy().astype(bool) != m_ref)
     print(f"    bin/mask mismatches: {mism.sum()} of {mism.size}")
     assert mism.mean() < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------
+# benchmark-scale code path: many tile pairs per persistent CTA (the `p += gridDim.x` loop, mbarrier phases carried
+# across tile pairs, the L2 prefetch branch, the odd-tile / ragged tail) -- BASELINE config 2 at a size where every CTA
+# loops several times.  Each object is one TMEM lane / one thread: results must not depend on N or on the tile an
+# object lands in, so a tile-aligned slice evaluated alone must reproduce the big launch BIT FOR BIT.
+BIG_N = 2 * 148 * 256 * 3 + 77   # 1777 tiles of 128: 6+ persistent iterations per CTA, odd tile count, 77-row tail
+
+
+def _big_inputs(flow, dev, kind):
+    x, c = inputs(flow, BIG_N, 101, dev, torch.float32, outside_frac=0.002)
+    if kind == "sample":
+        g = torch.Generator().manual_seed(55)
+        bk = flow.base_kind()
+        x = (torch.randn(BIG_N, flow.features, generator=g) if bk == flows.modules.BASE_DIAG_NORMAL
+             else torch.rand(BIG_N, flow.features, generator=g)).to(dev)
+    return x, c
+
+
+@pytest.mark.parametrize("name,gemm", [("TF-A", flows.modules.GEMM_TC_3XF16), ("UF-common", flows.modules.GEMM_TC_3XF16),
+                                       ("TF-A", flows.modules.GEMM_MMA_3XF16), ("TF-A", flows.modules.GEMM_EXACT),
+                                       ("UF", flows.modules.GEMM_MMA_3XF16)])
+def test_benchmark_scale_log_prob(cuda, name, gemm):
+    flow = build(name, cuda, torch.float32, mode="bias")
+    flow.gemm = gemm
+    n_big = BIG_N if name == "TF-A" else BIG_N // 4 + 13
+    x, c = _big_inputs(flow, cuda, "log_prob")
+    x, c = x[:n_big].contiguous(), c[:n_big].contiguous()
+    with torch.no_grad():
+        lp = flow(c).log_prob(x)
+        z = flow(c).transform(x)
+    torch.cuda.synchronize()
+    assert lp.shape == (n_big,) and torch.isfinite(z).all()
+    # (1) strided subsample (every tile, every lane position over the run) against the fp64 oracle
+    idx = torch.arange(0, n_big, max(1, n_big // 20000) | 1, device=cuda)   # odd stride: walks through all lane positions
+    spec = spec_from_module(flow)
+    xn, cn = x[idx].double().cpu().numpy(), c[idx].double().cpu().numpy()
+    z_ref, ladj_ref = fo.flow_forward(spec, xn, cn)
+    lp_ref = fo.base_log_prob(spec, z_ref) + ladj_ref
+    z32, ladj32 = fo.flow_forward(spec, xn, cn, dtype=np.float32)
+    lp32 = (fo.base_log_prob(spec, z32) + ladj32).astype(np.float64)
+    got = lp[idx].double().cpu().numpy()
+    fin = np.isfinite(lp_ref)
+    assert np.array_equal(np.isfinite(got), fin)
+    err = np.abs(got[fin] - lp_ref[fin]) / scale_lp(lp_ref[fin])
+    print(f"benchmark-scale {name} gemm={gemm} N={n_big}: subsample of {idx.numel()}")
+    fp32_gate(err, np.abs(lp32[fin] - lp_ref[fin]) / scale_lp(lp_ref[fin]), "log_prob", factor=3.0, floor=2e-6)
+    # (2) tile-aligned slices evaluated alone == the same rows of the big launch, bit for bit
+    for s0 in (0, 128 * 1001 if n_big > 128 * 1030 else 128 * 101, (n_big // 128 - 20) * 128):
+        s1 = min(n_big, s0 + 3000)
+        with torch.no_grad():
+            lp_s = flow(c[s0:s1].contiguous()).log_prob(x[s0:s1].contiguous())
+        assert torch.equal(lp_s, lp[s0:s1]), f"rows {s0}:{s1} depend on the launch size"
+
+
+@pytest.mark.parametrize("name,gemm", [("TF-A", flows.modules.GEMM_TC_3XF16), ("TF-B", flows.modules.GEMM_TC_3XF16),
+                                       ("TF-A", flows.modules.GEMM_MMA_3XF16), ("TF-A", flows.modules.GEMM_EXACT)])
+def test_benchmark_scale_sample(cuda, name, gemm):
+    flow = build(name, cuda, torch.float32, mode="bias")
+    flow.gemm = gemm
+    n_big = BIG_N // 2 + 5
+    noise, c = _big_inputs(flow, cuda, "sample")
+    noise, c = noise[:n_big].contiguous(), c[:n_big].contiguous()
+    xs = flow(c).sample_from_noise(noise)
+    torch.cuda.synchronize()
+    assert torch.isfinite(xs).all()
+    idx = torch.arange(0, n_big, (n_big // 10000) | 1, device=cuda)
+    spec = spec_from_module(flow)
+    zb = fo.base_sample_from_noise(spec, noise[idx].double().cpu().numpy())
+    cn = c[idx].double().cpu().numpy()
+    x_ref = fo.flow_inverse(spec, zb, cn)
+    x32 = fo.flow_inverse(spec, zb, cn, dtype=np.float32).astype(np.float64)
+    err = (np.abs(xs[idx].double().cpu().numpy() - x_ref) / np.maximum(1.0, np.abs(x_ref))).max(-1)
+    print(f"benchmark-scale sample {name} gemm={gemm} N={n_big}:")
+    fp32_gate(err, (np.abs(x32 - x_ref) / np.maximum(1.0, np.abs(x_ref))).max(-1), "sample", factor=3.0, floor=2e-6)
+    for s0 in (0, 128 * 401, (n_big // 128 - 20) * 128):
+        s1 = min(n_big, s0 + 3000)
+        xs_s = flow(c[s0:s1].contiguous()).sample_from_noise(noise[s0:s1].contiguous())
+        assert torch.equal(xs_s, xs[s0:s1]), f"rows {s0}:{s1} depend on the launch size"
 
 
 @pytest.mark.parametrize("name", ["TF-A", "TF-B"])
@@ -469,7 +558,7 @@ def test_host_pipeline_matches_single_shot(cuda):
     assert torch.equal(out, ref.cpu())
 
 
-@pytest.mark.parametrize("name", ["TF-A", "TF-B", "NCSF", "PSNSF", "no-context"])
+@pytest.mark.parametrize("name", ["TF-A", "TF-B", "UF-common", "TF-K40", "NCSF", "PSNSF", "no-context"])
 @pytest.mark.parametrize("mode", ["default", "stress"])
 def test_tc_3xf16_sample_parity(cuda, name, mode):
     """Tensor-core sampling kernel vs the fp64 oracle inverse on identical noise (fp32 gate as for log_prob)."""
@@ -519,7 +608,7 @@ def test_context_group_equals_repeated_context(cuda):
 
 # ------------------------------------------------------------------------------------------------
 # warp-level MMA path for wide hyper-networks (flow_mma.cu, hidden width up to 512): same split arithmetic, same gates
-MMA_CONFIGS = ["UF", "TF-1D", "TF-A", "NCSF", "no-context"]
+MMA_CONFIGS = ["UF", "TF-1D", "TF-A", "UF-common", "NCSF", "no-context"]
 
 
 @pytest.mark.parametrize("name", MMA_CONFIGS)
