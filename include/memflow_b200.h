@@ -256,14 +256,6 @@ int mf_event_reduce(const void* d_logprob, const uint8_t* d_mask, const void* d_
                     int32_t n_objects, void* d_out, int dtype, void* stream);
 
 /*
- * Test hook: single-CTA tcgen05 GEMM  out[128,N] = A[128,K] * W[N,K]^T (fp32 in/out) that exercises the
- * tensor-core building blocks of the flow kernels in isolation.  mode 0: fp16 hi/lo split, 3 MMAs per
- * k-step; 1: bf16; 2: fp16.  K, N multiples of 16, <= 256.
- */
-int mf_tc_probe_gemm(const float* d_a, const float* d_w, float* d_out, int32_t k, int32_t n, int32_t mode,
-                     void* stream);
-
-/*
  * Standalone zuko MonotonicRQSTransform on materialised parameters (a17): forward + log|dy/dx| or inverse of n
  * independent scalars.
  *   d_params [n, 3K-1]  (K widths | K heights | K-1 derivatives), unconstrained hyper-network outputs

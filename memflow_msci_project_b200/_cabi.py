@@ -188,13 +188,30 @@ def event_reduce(logprob, mask, logw, out):
     check(rc, "mf_event_reduce")
 
 
+PROBE_LIB_PATH = os.path.join(_HERE, "_lib", "libmemflow_b200_probe.so")
+_probe = None
+
+
+def probe_lib():
+    """Test-only library with the tcgen05 building-block checks and micro-benchmarks (csrc/tc_probe.cu); not part of
+    the product ABI."""
+    global _probe
+    if _probe is None:
+        if not os.path.exists(PROBE_LIB_PATH):
+            raise MemflowB200Error(f"{PROBE_LIB_PATH} not found: build it with `python -m memflow_msci_project_b200.build`")
+        _probe = ctypes.CDLL(PROBE_LIB_PATH)
+        _probe.mf_last_error.restype = ctypes.c_char_p
+    return _probe
+
+
 def tc_probe_gemm(a, w, mode):
-    """out[128,N] = a[128,K] @ w[N,K]^T on the tensor cores (test hook, mf_tc_probe_gemm)."""
+    """out[128,N] = a[128,K] @ w[N,K]^T on the tensor cores (test hook of the probe library)."""
     out = torch.empty((128, w.shape[0]), dtype=torch.float32, device=a.device)
     with torch.cuda.device(a.device):
-        rc = lib().mf_tc_probe_gemm(_ptr(a), _ptr(w), _ptr(out), ctypes.c_int32(a.shape[1]), ctypes.c_int32(w.shape[0]),
-                                    ctypes.c_int32(mode), _stream(a.device))
-    check(rc, "mf_tc_probe_gemm")
+        rc = probe_lib().mf_tc_probe_gemm(_ptr(a), _ptr(w), _ptr(out), ctypes.c_int32(a.shape[1]), ctypes.c_int32(w.shape[0]),
+                                          ctypes.c_int32(mode), _stream(a.device))
+    if rc != 0:
+        raise MemflowB200Error(f"mf_tc_probe_gemm failed (rc={rc}): {probe_lib().mf_last_error().decode(errors='replace')}")
     return out
 
 

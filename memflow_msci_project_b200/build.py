@@ -14,7 +14,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(OUT_DIR, "libmemflow_b200.so")
-SOURCES = ["abi.cu", "rambo.cu", "flow.cu", "reduce.cu", "tc_probe.cu", "flow_tc.cu", "rqs.cu", "flow_mma.cu"]
+SOURCES = ["abi.cu", "rambo.cu", "flow.cu", "reduce.cu", "flow_tc.cu", "rqs.cu", "flow_mma.cu"]
+# micro-benchmarks / building-block checks of the tcgen05 pieces: a separate TEST-ONLY library
+# (tests/test_tc_probe_gpu.py, tools/probe_*.py); nothing of it is linked into the product library
+PROBE_LIB = os.path.join(OUT_DIR, "libmemflow_b200_probe.so")
+PROBE_SOURCES = ["abi.cu", "tc_probe.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -42,7 +46,7 @@ def build(force=False, verbose=False):
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(HERE, "..", "include", "memflow_b200.h"))
     objs, jobs = [], []
-    for src in SOURCES:
+    for src in SOURCES + [p for p in PROBE_SOURCES if p not in SOURCES]:
         s = os.path.join(CSRC, src)
         o = os.path.join(OUT_DIR, src.replace(".cu", ".o"))
         objs.append(o)
@@ -64,12 +68,15 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as ex:
         list(ex.map(compile_one, jobs))
-    if jobs or force or _stale(LIB, objs):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
-                                                      "-ccbin", "/usr/bin/g++", "-lcudart"]
-        res = subprocess.run(cmd, capture_output=True, text=True)
-        if res.returncode != 0:
-            raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+    obj_of = lambda src: os.path.join(OUT_DIR, src.replace(".cu", ".o"))
+    for lib, srcs in ((LIB, SOURCES), (PROBE_LIB, PROBE_SOURCES)):
+        lobjs = [obj_of(x) for x in srcs]
+        if jobs or force or _stale(lib, lobjs):
+            cmd = [NVCC, "-shared", "-o", lib] + lobjs + ["-gencode", "arch=compute_100a,code=sm_100a",
+                                                          "-ccbin", "/usr/bin/g++", "-lcudart"]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
     return LIB
 
 

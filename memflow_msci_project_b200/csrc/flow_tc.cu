@@ -1,29 +1,31 @@
-// flow_tc.cu -- fused conditional RQ-spline MAF log_prob with the conditioner GEMMs on tcgen05.
+// flow_tc.cu -- fused conditional RQ-spline MAF log_prob / sample with the conditioner GEMMs on tcgen05.
 //
-// One persistent CTA per SM works on PAIRS of 128-object tiles.  Warp roles (352 threads):
-//   warp 0        weight loader: streams the packed, pre-swizzled weight K-blocks from L2 into a 3-stage
-//                 shared-memory ring with 1-D bulk async copies (TMA engine) completing on mbarriers
-//   warps 1, 2    MMA issuers of tile slot 0 / 1: one elected lane issues tcgen05.mma (M=128, N<=128, K=16,
-//                 fp32 accumulate in TMEM) and tcgen05.commit; both consume every weight stage (measured: one
-//                 issuer sustains ~1 MMA per 105 cycles, the tensor core needs 64 -> two issuers)
+// One persistent CTA per SM works on PAIRS of 128-object tiles (two "tile slots").  Warp roles (352 threads):
+//   warp 0        weight loader: streams the packed, pre-swizzled weight K-blocks from L2 into a shared-memory ring
+//                 (as many 32 KB stages as fit next to the layer-0 operands) with 1-D bulk async copies (TMA engine)
+//                 completing on mbarriers
+//   warp 1        MMA issuer: walks the job schedule, the two tile slots take turns job by job; per weight K-block ONE
+//                 elected lane issues the tcgen05.mma (M=128, N<=128, K=16, kind::f16, fp32 accumulate in TMEM) back to
+//                 back and commits the stage / accumulator mbarriers
+//   warp 2        spare (keeps the epilogue warps aligned to the TMEM lane quarters, warp % 4)
 //   warps 3-6     epilogue group of tile slot 0 (thread = object = TMEM lane)
 //   warps 7-10    epilogue group of tile slot 1
-// The two tile slots ping-pong: while the tensor core works on one tile's layer, the other tile's epilogue
-// (TMEM accumulator -> registers -> bias + ReLU -> fp16 hi/lo operand planes -> back into TMEM with tcgen05.st)
-// runs on the CUDA cores.  Hidden activations therefore never leave TMEM: layer l+1 takes its A operand straight
-// from TMEM (tcgen05.mma with a TMEM A operand), only the layer-0 operand (x | context) sits in shared memory,
-// where the context part is staged ONCE per tile and only the D columns of x are refreshed per transform.
-// The spline parameters of the last layer are consumed straight out of TMEM by the thread that owns the
-// object, so they never touch shared memory or HBM either.
-// TMEM map of tile slot t (256 columns): [0,128) fp32 accumulator, [128,192) hi plane, [192,256) lo plane
-// (64 columns = 128 packed 16-bit K elements).
+// While the tensor core works on one slot's job, the other slot's epilogue (TMEM accumulator -> registers -> bias +
+// ReLU -> fp16 hi/lo operand planes -> back into TMEM with tcgen05.st) runs on the CUDA cores.  Hidden activations never
+// leave TMEM: layer l+1 takes its A operand straight from TMEM (tcgen05.mma, TS form); only the layer-0 operand
+// (context | x) sits in shared memory, where the context part is staged ONCE per tile and only the D columns of x are
+// refreshed per transform.  The spline parameters of the last layer are consumed straight out of TMEM by the thread
+// that owns the object (spline_reg.cuh), so they never touch shared memory or HBM either.
+// TMEM map of tile slot t (256 columns): [0,128) fp32 accumulator, [128,192) hi plane, [192,256) lo plane (64 columns =
+// 128 packed 16-bit K elements).  Last-layer chunks whose parameters fit 64 columns (3 roundup(K,8) <= 64) alternate
+// between the accumulator halves [0,64) / [64,128): the MMAs of chunk c+1 run while the splines of chunk c are evaluated.
 //
 // Numerics.  MF_GEMM_TC_3XF16: every fp32 operand value v is split into fp16 hi = rn(v), lo = rn(v - hi) and
 // each product is formed as hi*hi + hi*lo + lo*hi with fp32 accumulation: 22 significant bits, i.e. fp32-class
 // accuracy (measured 4e-7 of sum|terms|, tests/test_tc_probe_gpu.py).  MF_GEMM_TC_BF16: single bf16 MMA.
 //
-// Supported shapes (others are served by the CUDA-core kernel in flow.cu): D + C <= 128, every hidden width
-// <= 128, 3 * roundup(K, 8) <= 128.
+// Supported shapes (others are served by flow_mma.cu / flow.cu): roundup(C,8) + D <= 128, every hidden width <= 128,
+// 3 * roundup(K, 8) <= 128 (K <= 40), soft clip enabled (slope > 0), ctx_group = 1.
 #include <algorithm>
 
 #include "flow_common.cuh"
@@ -67,6 +69,8 @@ struct TcJob {
   int in_dim, out_dim;
   long long w_off;  // bytes from the transform base to K-block 0 ([hi block][lo block] per K-block)
   int b_off;        // floats from the transform bias base
+  int region;       // accumulator region (barrier pair) of a last-layer chunk; hidden layers use region 0 and all columns
+  int acc_col;      // first accumulator column of the job (0 or 64)
 };
 
 struct TcLayout {
@@ -80,6 +84,8 @@ struct TcLayout {
   int in0_tail;          // ... followed by this many single k-steps in SWIZZLE_32B blocks
   int in0_plane_bytes;   // bytes of one operand plane of one tile
   int stages;            // weight ring depth
+  int fpc;               // features per last-layer chunk
+  int nregions;          // 2: last-layer chunks alternate between the accumulator halves
   long long t_stride;    // bytes per transform (weights)
   long long bias_off;    // byte offset of the fp32 bias region in the blob
   int bias_stride;       // floats per transform
@@ -117,7 +123,7 @@ int make_tc_layout(const mf_flow_desc& d, int gemm, TcLayout* L) {
     j.N = round_up(j.out_dim, 16);
     j.ksteps = round_up(l == 0 ? L->xcol0 + d.features : j.in_dim, 16) / 16;
     j.nkb = (j.ksteps + 3) / 4;
-    j.needs_a = 1; j.last = 0; j.feat0 = 0; j.nfeat = 0; j.layer = l; j.row0 = 0;
+    j.needs_a = 1; j.last = 0; j.feat0 = 0; j.nfeat = 0; j.layer = l; j.row0 = 0; j.region = 0; j.acc_col = 0;
     j.w_off = woff; woff += (long long)j.nkb * parts * j.N * 128;
     j.b_off = boff; boff += j.N;
   }
@@ -129,8 +135,13 @@ int make_tc_layout(const mf_flow_desc& d, int gemm, TcLayout* L) {
     const size_t avail = 232448 - kStaticSmem - (size_t)2 * parts * L->in0_plane_bytes;
     L->stages = (int)std::min<size_t>(kMaxStages, avail / ((size_t)parts * kWPartBytes));
   }
-  const int fpc = std::max(1, 128 / L->PFt);
-  for (int f0 = 0; f0 < d.features; f0 += fpc) {
+  // features per last-layer chunk: as many as fit the 128 accumulator columns; when that takes more than one chunk
+  // and a feature fits 64 columns, chunks of <= 64 columns alternate between the two accumulator halves instead
+  int fpc = std::max(1, 128 / L->PFt);
+  L->nregions = 1;
+  if (d.features > fpc && L->PFt <= 64) { fpc = 64 / L->PFt; L->nregions = 2; }
+  L->fpc = fpc;
+  for (int f0 = 0, ci = 0; f0 < d.features; f0 += fpc, ++ci) {
     MF_REQUIRE(nj < kMaxJobs, "too many last-layer chunks for the tensor-core path");
     TcJob& j = L->job[nj++];
     j.in_dim = d.hidden[d.n_hidden - 1];
@@ -141,6 +152,7 @@ int make_tc_layout(const mf_flow_desc& d, int gemm, TcLayout* L) {
     j.ksteps = round_up(j.in_dim, 16) / 16;
     j.nkb = (j.ksteps + 3) / 4;
     j.needs_a = (f0 == 0) ? 1 : 0; j.last = 1; j.layer = d.n_hidden; j.row0 = f0 * (3 * d.bins - 1);
+    j.region = (L->nregions == 2) ? (ci & 1) : 0; j.acc_col = j.region * 64;
     j.w_off = woff; woff += (long long)j.nkb * parts * j.N * 128;
     j.b_off = boff; boff += j.N;
   }
@@ -208,17 +220,6 @@ __global__ void flow_tc_pack_kernel(TcLayout L, TcPackArgs<T> a, unsigned char* 
 }
 
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
-  uint32_t r[8];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr)
-               : "memory");
-  tc::tmem_ld_wait();
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -226,118 +227,10 @@ __device__ __forceinline__ void group_bar(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// Spline of one feature with its 3K-1 unconstrained parameters in TMEM (this thread's lane):
-// columns [0,K) widths, [Kp,Kp+K) heights, [2Kp, 2Kp+K-1) derivatives.  Forward transform + log-det.
-// sb: the parameters' biases in shared memory (same column layout).
-__device__ __forceinline__ void ld8b(uint32_t taddr, const float* sb, float* v) {
-  tmem_ld8(taddr, v);
-  const float4 b0 = *reinterpret_cast<const float4*>(sb), b1 = *reinterpret_cast<const float4*>(sb + 4);
-  v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-  v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-}
-
-__device__ __forceinline__ void rqs_forward_tmem(uint32_t taddr, const float* sb, const SplineCfg<float>& cfg, int Kp,
-                                                 float v, float& out, float& ladj, int& bin, bool& inside) {
-  const int K = cfg.K;
-  const int nch = Kp >> 3;
-  float ladj0 = 0.f;
-  if (cfg.univariate == MF_UNIV_CIRCULAR_RQS) v = circular_wrap(v, cfg.bound);
-  if (cfg.univariate == MF_UNIV_PS_RQS) { v = (v + 1.f) * 0.5f; ladj0 = -0.6931471805599453f; }
-  const bool clipped = cfg.inv_ls2 != 0.f;  // soft-clipped logits are bounded by |ln slope| / 2: no max pass
-  float mw = 0.f, mh = 0.f;
-  if (!clipped) {
-    mw = -INFINITY; mh = -INFINITY;
-    for (int c = 0; c < nch; ++c) {
-      float a[8], b[8];
-      ld8b(taddr + c * 8, sb + c * 8, a);
-      ld8b(taddr + Kp + c * 8, sb + Kp + c * 8, b);
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (c * 8 + j < K) {
-          mw = fmaxf(mw, softclipf(a[j], cfg.inv_ls2));
-          mh = fmaxf(mh, softclipf(b[j], cfg.inv_ls2));
-        }
-    }
-  }
-  float sw = 0.f, sh = 0.f;
-  for (int c = 0; c < nch; ++c) {
-    float a[8], b[8];
-    ld8b(taddr + c * 8, sb + c * 8, a);
-    ld8b(taddr + Kp + c * 8, sb + Kp + c * 8, b);
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (c * 8 + j < K) {
-        sw += __expf(softclipf(a[j], cfg.inv_ls2) - mw);
-        sh += __expf(softclipf(b[j], cfg.inv_ls2) - mh);
-      }
-  }
-  // scan the horizontal knots: bound * (2 cumsum(softmax(w)) - 1); k = #(knots < v) - 1
-  int k = -1;
-  float x0 = 0.f, x1 = 1.f, cum = 0.f, prev = -cfg.bound;
-  for (int c = 0; c < nch; ++c) {
-    float a[8];
-    ld8b(taddr + c * 8, sb + c * 8, a);
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (c * 8 + j < K) {
-        cum += __expf(softclipf(a[j], cfg.inv_ls2) - mw) / sw;
-        const float knot = cfg.bound * (2.f * cum - 1.f);
-        if (prev < v) { k = c * 8 + j; x0 = prev; x1 = knot; }
-        prev = knot;
-      }
-  }
-  if (prev < v) k = K;
-  inside = (k >= 0) && (k < K);
-  k = k < 0 ? k + K : (k >= K ? k - K : k);
-  bin = k;
-  // vertical knots of bin k
-  float part = 0.f, ek = 0.f;
-  for (int c = 0; c < nch; ++c) {
-    float b[8];
-    ld8b(taddr + Kp + c * 8, sb + Kp + c * 8, b);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int jj = c * 8 + j;
-      if (jj <= k) {
-        const float e = __expf(softclipf(b[j], cfg.inv_ls2) - mh) / sh;
-        if (jj < k) part += e; else ek = e;
-      }
-    }
-  }
-  const float y0 = cfg.bound * (2.f * part - 1.f), y1 = cfg.bound * (2.f * (part + ek) - 1.f);
-  // derivatives at the two knots (boundary derivatives are 1)
-  float d0 = 1.f, d1 = 1.f;
-  {
-    // tcgen05.ld is a warp-collective (.sync.aligned) with a warp-uniform address: all derivative chunks
-    // are loaded by every lane and each lane picks the two columns of its own bin in registers
-    const int i0 = k - 1, i1 = k;  // indices into the K-1 derivative logits
-    float t0 = 0.f, t1 = 0.f;
-    for (int c = 0; c < nch; ++c) {
-      float dv[8];
-      ld8b(taddr + 2 * Kp + c * 8, sb + 2 * Kp + c * 8, dv);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        t0 = (c * 8 + j == i0) ? dv[j] : t0;
-        t1 = (c * 8 + j == i1) ? dv[j] : t1;
-      }
-    }
-    if (i0 >= 0) d0 = __expf(softclipf(t0, cfg.inv_ls1));
-    if (i1 < K - 1) d1 = __expf(softclipf(t1, cfg.inv_ls1));
-  }
-  if (!inside) { x0 = 0.f; x1 = 1.f; }
-  const float s = (y1 - y0) / (x1 - x0);
-  const float msk = inside ? 1.f : 0.f;
-  const float z = msk * (v - x0) / (x1 - x0);
-  const float omz = 1.f - z;
-  const float den = s + (d0 + d1 - 2.f * s) * z * omz;
-  const float y = y0 + (y1 - y0) * (s * z * z + d0 * z * omz) / den;
-  const float jac = s * s * (2.f * s * z * omz + d0 * omz * omz + d1 * z * z) / (den * den);
-  out = inside ? y : v;
-  ladj = (inside ? __logf(jac) : 0.f) + ladj0;
-}
-
-// Same transform with all logits of the feature held in registers (Kp = 8 * NCH <= 32): every TMEM column is
-// loaded once, every exponential is evaluated once, and the two knot scans run in one pass.
+// Spline of one feature with its 3K-1 unconstrained parameters in TMEM (this thread's lane): columns [0,K) widths,
+// [KP,KP+K) heights, [2KP, 2KP+K-1) derivatives (KP = 8 NCH; padded columns hold exact zeros).
+// sb: the parameters' biases in shared memory in the same column layout, PRE-SCALED by the soft-clip factors
+// (widths / heights by inv2, derivatives by inv1), so that accumulator * inv + sb is the scaled logit of spline_reg.cuh.
 __device__ __forceinline__ void tmem_ld8_raw(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -345,13 +238,22 @@ __device__ __forceinline__ void tmem_ld8_raw(uint32_t taddr, uint32_t* r) {
                : "memory");
 }
 
-template <int NCH>
-__device__ __forceinline__ void rqs_forward_tmem_reg(uint32_t taddr, const float* sb, const SplineCfg<float>& cfg,
-                                                     bool inverse, float v, float& out, float& ladj, int& bin,
-                                                     bool& inside, long long* ts = nullptr) {
+// 8 accumulator columns -> scaled logits: acc * inv + sb, two columns per FFMA2
+__device__ __forceinline__ void scale8(const uint32_t* r, const float* sb, float inv, float* o) {
+  const float4 b0 = *reinterpret_cast<const float4*>(sb), b1 = *reinterpret_cast<const float4*>(sb + 4);
+  const float2 i2 = f2_bcast(inv);
+  float2 t;
+  t = f2_fma(make_float2(__uint_as_float(r[0]), __uint_as_float(r[1])), i2, make_float2(b0.x, b0.y)); o[0] = t.x; o[1] = t.y;
+  t = f2_fma(make_float2(__uint_as_float(r[2]), __uint_as_float(r[3])), i2, make_float2(b0.z, b0.w)); o[2] = t.x; o[3] = t.y;
+  t = f2_fma(make_float2(__uint_as_float(r[4]), __uint_as_float(r[5])), i2, make_float2(b1.x, b1.y)); o[4] = t.x; o[5] = t.y;
+  t = f2_fma(make_float2(__uint_as_float(r[6]), __uint_as_float(r[7])), i2, make_float2(b1.z, b1.w)); o[6] = t.x; o[7] = t.y;
+}
+
+template <int NCH, bool INV>
+__device__ __forceinline__ void spline_tmem(uint32_t taddr, const float* sb, const RqsScaled& cf, float v, float& out,
+                                            float& ladj, int& bin, bool& inside) {
   constexpr int KP = 8 * NCH;
   float lw[KP], lh[KP];
-  if (ts) ts[0] = clock64();
   {
     uint32_t rw[KP], rh[KP];
 #pragma unroll
@@ -360,43 +262,126 @@ __device__ __forceinline__ void rqs_forward_tmem_reg(uint32_t taddr, const float
       tmem_ld8_raw(taddr + KP + c * 8, rh + c * 8);
     }
     tc::tmem_ld_wait();
-    if (ts) ts[1] = clock64();
 #pragma unroll
-    for (int j = 0; j < KP; ++j) {  // accumulator + bias
-      lw[j] = __uint_as_float(rw[j]) + sb[j];
-      lh[j] = __uint_as_float(rh[j]) + sb[KP + j];
+    for (int c = 0; c < NCH; ++c) {
+      scale8(rw + c * 8, sb + c * 8, cf.inv2, lw + c * 8);
+      scale8(rh + c * 8, sb + KP + c * 8, cf.inv2, lh + c * 8);
     }
   }
-  int k;
-  float x0, x1, y0, y1, ladj0, t0, t1;
-  rqs_scan_reg<NCH>(lw, lh, cfg, inverse, v, k, inside, x0, x1, y0, y1, ladj0);
-  if (ts) ts[2] = clock64() + (long long)(x0 == 12345.f);
-  {  // derivative logits are fetched only now (short register live ranges); the load is warp-uniform
-    uint32_t rd[KP];
+  uint32_t rd[2][8];
+  tmem_ld8_raw(taddr + 2 * KP, rd[0]);  // derivative logits: in flight during the exponentials, one chunk ahead after that
+  float ladj0 = 0.f;
+  if (!INV) v = rqs_premap(cf, v, ladj0);
+  float sw, sh;
+  rqs_ms_exp<NCH>(lw, lh, cf, sw, sh);
+  RqsMsState st;
+  rqs_ms_begin<INV>(st, cf, v, sw, sh);
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) tmem_ld8_raw(taddr + 2 * KP + c * 8, rd + c * 8);
+  for (int c = 0; c < NCH; ++c) {
     tc::tmem_ld_wait();
-    t0 = 0.f; t1 = 0.f;
-#pragma unroll
-    for (int j = 0; j < KP; ++j) {
-      const float dj = __uint_as_float(rd[j]) + sb[2 * KP + j];
-      t0 = (j == k - 1) ? dj : t0;
-      t1 = (j == k) ? dj : t1;
-    }
+    if (c + 1 < NCH) tmem_ld8_raw(taddr + 2 * KP + (c + 1) * 8, rd[(c + 1) & 1]);
+    float d8[8];
+    scale8(rd[c & 1], sb + 2 * KP + c * 8, cf.inv1, d8);
+    rqs_ms_chunk<INV>(st, lw + c * 8, lh + c * 8, d8, c * 8);
   }
-  bin = k;
-  if (ts) ts[3] = clock64() + (long long)(t0 == 12345.f);
-  rqs_finish(cfg, inverse, v, k, inside, x0, x1, y0, y1, t0, t1, ladj0, out, ladj);
-  if (ts) ts[4] = clock64() + (long long)(out == 12345.f);
+  rqs_ms_finish<INV>(st, cf, v, sw, sh, ladj0, out, ladj, bin, inside);
 }
 
 // ------------------------------------------------------------------------------------------------
-// EW = epilogue warp sets per tile slot: with EW = 2 two warps share every TMEM lane quarter and split the
-// columns of a hidden layer / the features of a spline chunk between them (16 epilogue warps per CTA).
+// fp32 pair -> (hi, lo) fp16 pairs with hi + lo = v to ~2^-22 relative; v - float(hi) is exact in fp32
+__device__ __forceinline__ void split_f16_pair(float2 v, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(v.x, v.y);
+  const float2 l2 = f2_fma(__half22float2(h), f2_bcast(-1.f), v);
+  const __half2 l = __floats2half2_rn(l2.x, l2.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// tcgen05.mma under a (uniform) enable predicate: the tail k-steps of a job are switched off without branches
+__device__ __forceinline__ void mma_ts_p(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate,
+                                         uint32_t enable) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "setp.ne.b32 q, %5, 0;\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(enable)
+      : "memory");
+}
+__device__ __forceinline__ void mma_ss_p(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate,
+                                         uint32_t enable) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "setp.ne.b32 q, %5, 0;\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(enable)
+      : "memory");
+}
+
+// One job of one tile slot, issued by ONE thread as a single straight-line batch (up to 8 k-steps = 2 weight K-blocks,
+// 3 MMAs per k-step in the 3xFP16 mode): everything the MMAs need is computed before the first one is issued, so the
+// tensor pipe is fed back to back (measured: bookkeeping between the K-blocks of a job used to cost ~500 cycles of an
+// idle pipe per K-block -- an MMA "cost" 85-105 cycles whatever its N was).
+//   hidden layers / last-layer chunks: A operand planes in TMEM (hi at a_tmem, lo 64 columns further)
+template <int NSPLIT>
+__device__ __forceinline__ void issue_job_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t w_base0, uint32_t w_base1, uint32_t idesc,
+                                             int ksteps, uint64_t* empty0, uint64_t* empty1, bool release, uint64_t* full) {
+  const uint64_t b0h = tc::make_smem_desc(w_base0), b0l = tc::make_smem_desc(w_base0 + kWPartBytes);
+  const uint64_t b1h = tc::make_smem_desc(w_base1), b1l = tc::make_smem_desc(w_base1 + kWPartBytes);
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    const uint32_t en = ks < ksteps ? 1u : 0u;
+    const uint64_t bh = (ks < 4 ? b0h : b1h) + (uint64_t)((ks & 3) * 2), bl = (ks < 4 ? b0l : b1l) + (uint64_t)((ks & 3) * 2);
+    const uint32_t a = a_tmem + (uint32_t)ks * 8u;
+    mma_ts_p(d_tmem, a, bh, idesc, ks ? 1u : 0u, en);
+    if (NSPLIT == 3) {
+      mma_ts_p(d_tmem, a, bl, idesc, 1u, en);
+      mma_ts_p(d_tmem, a + 64u, bh, idesc, 1u, en);
+    }
+    if (ks == 3 && release) tc::mma_commit(empty0);  // K-block 0 consumed by both slots
+  }
+  if (release && ksteps > 4) tc::mma_commit(empty1);
+  tc::mma_commit(full);
+}
+//   layer 0: (ctx | x) operand planes in shared memory: `nfull` 64-wide SWIZZLE_128B K-blocks, then single k-steps in
+//   SWIZZLE_32B blocks (a_hi / a_lo: plane bases, tail_off: byte offset of the first tail k-step inside a plane)
+template <int NSPLIT>
+__device__ __forceinline__ void issue_job_ss(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, int nfull, uint32_t tail_off,
+                                             uint32_t w_base0, uint32_t w_base1, uint32_t idesc, int ksteps, uint64_t* empty0,
+                                             uint64_t* empty1, bool release, uint64_t* full) {
+  const uint64_t b0h = tc::make_smem_desc(w_base0), b0l = tc::make_smem_desc(w_base0 + kWPartBytes);
+  const uint64_t b1h = tc::make_smem_desc(w_base1), b1l = tc::make_smem_desc(w_base1 + kWPartBytes);
+  const uint64_t fh0 = tc::make_smem_desc(a_hi), fl0 = tc::make_smem_desc(a_lo);
+  const uint64_t fh1 = tc::make_smem_desc(a_hi + kKBlockBytes), fl1 = tc::make_smem_desc(a_lo + kKBlockBytes);
+  const uint64_t th = tc::make_smem_desc_sw32(a_hi + tail_off), tl = tc::make_smem_desc_sw32(a_lo + tail_off);
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    const uint32_t en = ks < ksteps ? 1u : 0u;
+    const uint64_t bh = (ks < 4 ? b0h : b1h) + (uint64_t)((ks & 3) * 2), bl = (ks < 4 ? b0l : b1l) + (uint64_t)((ks & 3) * 2);
+    const bool isfull = (ks >> 2) < nfull;
+    const int kt = ks - 4 * nfull;  // tail k-step index
+    const uint64_t ah = isfull ? (ks < 4 ? fh0 : fh1) + (uint64_t)((ks & 3) * 2) : th + (uint64_t)kt * (kTailBytes >> 4);
+    const uint64_t al = isfull ? (ks < 4 ? fl0 : fl1) + (uint64_t)((ks & 3) * 2) : tl + (uint64_t)kt * (kTailBytes >> 4);
+    mma_ss_p(d_tmem, ah, bh, idesc, ks ? 1u : 0u, en);
+    if (NSPLIT == 3) {
+      mma_ss_p(d_tmem, ah, bl, idesc, 1u, en);
+      mma_ss_p(d_tmem, al, bh, idesc, 1u, en);
+    }
+    if (ks == 3 && release) tc::mma_commit(empty0);
+  }
+  if (release && ksteps > 4) tc::mma_commit(empty1);
+  tc::mma_commit(full);
+}
+
 // INV: sampling (transforms in reverse, `passes` sweeps each) -- a compile-time flag so that the log_prob kernel carries
-// none of the sweep / schedule logic
-template <int NSPLIT, int EW, bool INV>
-__global__ void __launch_bounds__((3 + 8 * EW) * 32, 1)
+// none of the sweep / schedule logic.  NCHK = roundup(K, 8) / 8 (spline logits held in registers).
+template <int NSPLIT, int NCHK, bool INV>
+__global__ void __launch_bounds__(11 * 32, 1)
 flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowKernelArgs args,
                const __grid_constant__ BaseParams bp) {
   constexpr int kParts = (NSPLIT == 3) ? 2 : 1;           // operand planes (hi, lo)
@@ -408,7 +393,7 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
   const uint32_t kFullBytes = (uint32_t)L.in0_full * kKBlockBytes;  // tail k-steps start here inside a plane
   unsigned char* w_ring = smem + 2 * kParts * kPlane;
   const uint32_t kStages = (uint32_t)L.stages;
-  __shared__ __align__(8) uint64_t w_full[kMaxStages], w_empty[kMaxStages], a_ready[2], acc_full[2], acc_free[2];
+  __shared__ __align__(8) uint64_t w_full[kMaxStages], w_empty[kMaxStages], a_ready[2], acc_full[2][2], acc_free[2][2];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float sbias[2][2][128];  // [tile slot][job parity][column]
 
@@ -433,9 +418,8 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
   if (tid == 0) {
     for (int s = 0; s < kMaxStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     for (int t = 0; t < 2; ++t) {
-      mbar_init(&a_ready[t], 128 * EW);
-      mbar_init(&acc_full[t], 1);
-      mbar_init(&acc_free[t], 128 * EW);
+      mbar_init(&a_ready[t], 128);
+      for (int r = 0; r < 2; ++r) { mbar_init(&acc_full[t][r], 1); mbar_init(&acc_free[t][r], 128); }
     }
     fence_mbar_init();
   }
@@ -448,7 +432,7 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
   if (warp == 0) {
     // ===================== weight loader =====================
     if (lane == 0) {
-      uint32_t it = 0;
+      uint32_t s = 0, ph = 0;  // ring position / phase of the next stage to fill
       for (long long p = blockIdx.x; p < n_pairs; p += gridDim.x) {
         for (int unit = 0; unit < n_units; ++unit) {
           const int tr = inverse ? (L.T - 1 - unit / sweeps) : unit;
@@ -457,14 +441,14 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
             if (!job_live(unit, ji)) continue;
             const TcJob& j = L.job[ji];
             const uint32_t part_bytes = (uint32_t)j.N * 128u;
-            for (int kb = 0; kb < j.nkb; ++kb, ++it) {
-              const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+            for (int kb = 0; kb < j.nkb; ++kb) {
               mbar_wait_relaxed(&w_empty[s], ph ^ 1, 2000);
               mbar_expect_tx(&w_full[s], kParts * part_bytes);
               const unsigned char* src = tb + j.w_off + (long long)kb * kParts * part_bytes;
               unsigned char* dst = w_ring + s * kStageBytes;
 #pragma unroll
               for (int q = 0; q < kParts; ++q) bulk_g2s(dst + q * kWPartBytes, src + (size_t)q * part_bytes, part_bytes, &w_full[s]);
+              if (++s == kStages) { s = 0; ph ^= 1; }
             }
           }
         }
@@ -474,79 +458,70 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
     // ===================== MMA issuer =====================
     // One warp walks the (warp-uniform) schedule and waits on the barriers; per K-block one elected lane issues
     // the MMAs back to back.  The two tile slots take turns job by job (slot 0's job j, slot 1's job j, slot 0's
-    // job j+1, ...): while one slot's MMAs occupy the tensor pipe the other slot's epilogue drains its
-    // accumulator, so in steady state the pipe never waits for an epilogue that is shorter than an MMA phase.
-    uint32_t it = 0;                 // weight stages consumed so far
+    // job j+1, ...): while one slot's MMAs occupy the tensor pipe the other slot's epilogue drains its accumulator.
+    // Dependencies of a job: a hidden layer (and the first last-layer chunk of a unit) waits for its A operand
+    // (a_ready: every thread of the slot has finished the previous epilogue, so the accumulator is drained as well);
+    // a later last-layer chunk waits until the previous chunk in ITS accumulator region has been consumed (acc_free).
+    uint32_t stage = 0, sphase = 0;  // ring position / phase of the next weight K-block to consume
     int trace_n = 0; (void)trace_n;
-    uint32_t jobctr[2] = {0, 0};     // accumulator uses per tile slot
-    uint32_t aph[2] = {0, 0};        // a_ready phases
+    uint32_t aph0 = 0, aph1 = 0;               // a_ready phases per slot
+    uint32_t nchunk0 = 0, nchunk1 = 0;         // last-layer chunks issued so far per region (both slots walk the same jobs)
+    const uint32_t tail_off = kFullBytes;
     for (long long p = blockIdx.x; p < n_pairs; p += gridDim.x) {
       const int nact = (2 * p + 1 < n_tiles) ? 2 : 1;  // odd tile count: slot 1 idles in the last pair
       for (int unit = 0; unit < n_units; ++unit) {
-        bool first_last = true;  // the first EXECUTED last-layer chunk of a unit waits for the last hidden activations
+        bool first_last = true;      // the first EXECUTED last-layer chunk of a unit waits for the last hidden activations
+        int in_unit0 = 0, in_unit1 = 0;  // chunks of this unit issued per region
         for (int ji = 0; ji < L.njobs; ++ji) {
           if (!job_live(unit, ji)) continue;
-          const TcJob& j = L.job[ji];
-          const uint32_t idesc = tc::make_idesc_f16(NSPLIT == 3 ? 0 : 1, 128, j.N);
-          const bool wait_a = j.last ? first_last : (j.needs_a != 0);
-          if (j.last) first_last = false;
+          // job constants -> registers (the parameter struct lives in the constant bank)
+          const int jN = L.job[ji].N, jks = L.job[ji].ksteps, jlast = L.job[ji].last, jreg = L.job[ji].region;
+          const uint32_t jcol = (uint32_t)L.job[ji].acc_col;
+          const uint32_t idesc = tc::make_idesc_f16(NSPLIT == 3 ? 0 : 1, 128, jN);
+          const bool wait_a = jlast ? first_last : true;
+          const bool wait_free = jlast && (jreg ? in_unit1 : in_unit0) > 0;
+          const uint32_t free_par = ((jreg ? nchunk1 : nchunk0) - 1) & 1;  // phase of the previous chunk of this region
+          if (jlast) {
+            first_last = false;
+            if (jreg) { ++in_unit1; ++nchunk1; } else { ++in_unit0; ++nchunk0; }
+          }
+          // ring slots of the job's (at most two) weight K-blocks; both must have landed before the batch is issued
+          const uint32_t s0 = stage, p0 = sphase;
+          uint32_t s1 = s0 + 1, p1 = p0;
+          if (s1 == kStages) { s1 = 0; p1 ^= 1; }
+          const bool two = jks > 4;
+          mbar_wait(&w_full[s0], p0);
+          if (two) mbar_wait(&w_full[s1], p1);
+          const uint32_t w_base0 = smem_u32(w_ring + s0 * kStageBytes), w_base1 = smem_u32(w_ring + s1 * kStageBytes);
           for (int t = 0; t < nact; ++t) {
-            const uint32_t d_tmem = tmem + (uint32_t)(t * 256);
-            const uint32_t a_tmem = d_tmem + 128;  // hi plane; lo plane 64 columns further
+            const uint32_t d_tmem = tmem + (uint32_t)(t * 256) + jcol;
+            const uint32_t a_tmem = tmem + (uint32_t)(t * 256) + 128;  // hi plane; lo plane 64 columns further
             const uint32_t a_base = smem_u32(a_buf + (size_t)t * kParts * kPlane);
-            if (wait_a) { mbar_wait(&a_ready[t], aph[t]); aph[t] ^= 1; }
-            if (jobctr[t] >= 1) mbar_wait(&acc_free[t], (jobctr[t] - 1) & 1);  // accumulator drained
+            if (wait_a) {
+              mbar_wait(&a_ready[t], t ? aph1 : aph0);
+              if (t) aph1 ^= 1; else aph0 ^= 1;
+            }
+            if (wait_free) mbar_wait(&acc_free[t][jreg], free_par);
             MF_TRACE(lane == 0, 100 + 10 * t + ji);
             tc::fence_after_thread_sync();
-            for (int kb = 0; kb < j.nkb; ++kb) {
-              const uint32_t s = (it + kb) % kStages, ph = ((it + kb) / kStages) & 1;
-              if (t == 0) mbar_wait(&w_full[s], ph);
-              tc::fence_after_thread_sync();
-              const uint32_t w_base = smem_u32(w_ring + s * kStageBytes);
-              const int ks_n = min(4, j.ksteps - kb * 4);
-              // measured: 75 clk per 128x128x16 MMA issued like this against ~120 when every MMA sits in its own
-              // elect / branch / reconverge region
-              if (tc::elect_one()) {
-                const uint64_t dbh = tc::make_smem_desc(w_base);
-                const uint64_t dbl = tc::make_smem_desc(w_base + kWPartBytes);
-                if (ji == 0) {  // layer 0: (x | ctx) operand from shared memory
-                  const bool full = kb < L.in0_full;
-                  const uint64_t dah = full ? tc::make_smem_desc(a_base + kb * kKBlockBytes) : tc::make_smem_desc_sw32(a_base + kFullBytes);
-                  const uint64_t dal = full ? tc::make_smem_desc(a_base + kPlane + kb * kKBlockBytes)
-                                            : tc::make_smem_desc_sw32(a_base + kPlane + kFullBytes);
-                  const uint64_t astep = full ? 2u : (kTailBytes >> 4);  // descriptor address units of 16 bytes
-#pragma unroll
-                  for (int ks = 0; ks < 4; ++ks) {
-                    if (ks < ks_n) {
-                      tc::mma_f16_ss(d_tmem, dah + ks * astep, dbh + ks * 2u, idesc, (kb | ks) ? 1u : 0u);
-                      if (NSPLIT == 3) {
-                        tc::mma_f16_ss(d_tmem, dah + ks * astep, dbl + ks * 2u, idesc, 1u);
-                        tc::mma_f16_ss(d_tmem, dal + ks * astep, dbh + ks * 2u, idesc, 1u);
-                      }
-                    }
-                  }
-                } else {        // hidden activations: operand planes in TMEM
-                  const uint32_t ah = a_tmem + (uint32_t)(kb * 4) * 8u;
-#pragma unroll
-                  for (int ks = 0; ks < 4; ++ks) {
-                    if (ks < ks_n) {
-                      tc::mma_f16_ts(d_tmem, ah + ks * 8u, dbh + ks * 2u, idesc, (kb | ks) ? 1u : 0u);
-                      if (NSPLIT == 3) {
-                        tc::mma_f16_ts(d_tmem, ah + ks * 8u, dbl + ks * 2u, idesc, 1u);
-                        tc::mma_f16_ts(d_tmem, ah + 64u + ks * 8u, dbh + ks * 2u, idesc, 1u);
-                      }
-                    }
-                  }
-                }
-                if (t == nact - 1) tc::mma_commit(&w_empty[s]);  // both slots are done with the stage
-                if (kb == j.nkb - 1) tc::mma_commit(&acc_full[t]);
-              }
-              __syncwarp();
+            if (tc::elect_one()) {
+              const bool release = (t == nact - 1);  // both slots are done with the stages
+              if (ji == 0)
+                issue_job_ss<NSPLIT>(d_tmem, a_base, a_base + kPlane, L.in0_full, tail_off, w_base0, w_base1, idesc, jks,
+                                     &w_empty[s0], &w_empty[s1], release, &acc_full[t][jreg]);
+              else
+                issue_job_ts<NSPLIT>(d_tmem, a_tmem, w_base0, w_base1, idesc, jks, &w_empty[s0], &w_empty[s1], release,
+                                     &acc_full[t][jreg]);
             }
+            __syncwarp();
             MF_TRACE(lane == 0, 200 + 10 * t + ji);
-            jobctr[t]++;
           }
-          it += j.nkb;
+          // advance the ring by the job's K-blocks (s1 / p1 already are the wrapped successor of s0 / p0)
+          stage = s1; sphase = p1;
+          if (two) {
+            ++stage;
+            if (stage == kStages) { stage = 0; sphase ^= 1; }
+          }
         }
       }
     }
@@ -554,12 +529,11 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
     // spare warp (keeps the epilogue warps aligned to the TMEM lane quarters: warp % 4)
   } else {
     // ===================== epilogue groups =====================
-    const int eset = (warp - 3) >> 3;         // warp set inside the tile's epilogue group (0 .. EW-1)
-    const int t = ((warp - 3) & 7) >> 2;      // tile slot
+    const int t = (warp - 3) >> 2;            // tile slot
     const int q = warp & 3;                   // TMEM lane quarter this warp may access (4 consecutive warps cover all)
     const int row = q * 32 + lane;            // object inside the tile
-    const int gt = eset * 128 + ((warp - 3) & 3) * 32 + lane;  // thread index inside the group (cooperative loops)
-    constexpr int GT = 128 * EW;              // threads per epilogue group
+    const int gt = ((warp - 3) & 3) * 32 + lane;  // thread index inside the group (cooperative loops)
+    constexpr int GT = 128;                   // threads per epilogue group
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     unsigned char* a_hi = a_buf + (size_t)t * kParts * kPlane;
     unsigned char* a_lo = a_hi + kPlane;
@@ -572,11 +546,12 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
     const float* gc = static_cast<const float*>(args.ctx);
     float* gz = static_cast<float*>(args.z);
     const int D = L.D, C = L.C, xcol0 = L.xcol0;
-    SplineCfg<float> cfg;
-    cfg.K = L.K; cfg.univariate = args.univariate; cfg.bound = (float)args.bound;
-    cfg.inv_ls2 = args.slope > 0.0 ? (float)(2.0 / log(args.slope)) : 0.f;
-    cfg.inv_ls1 = args.slope > 0.0 ? (float)(1.0 / log(args.slope)) : 0.f;
-    uint32_t jobctr = 0;
+    const RqsScaled cf = make_rqs_scaled(L.K, args.univariate, args.bound, args.slope);
+    // soft-clip scale of the bias of last-layer column gt (same column layout in every chunk): the spline works on
+    // logits pre-multiplied by 2 / ln(slope) (widths, heights) or 1 / ln(slope) (derivatives)
+    const float bscale_last = ((gt % L.PFt) / L.Kp == 2) ? cf.inv1 : cf.inv2;
+    uint32_t jobctr = 0;                      // bias double-buffer parity
+    uint32_t fullctr0 = 0, fullctr1 = 0;      // accumulator uses per region
     int trace_n = 2000 + 1000 * t; (void)trace_n;
 
     auto put1 = [&](int r, int k, float v) {
@@ -600,24 +575,23 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
       // working copy of x lives in the output buffer (each thread touches only its own row); when sampling,
       // gx holds the noise and the base sample a + b * noise is the starting point
       MF_TRACE(gt == 0, 950 + 10 * t);
-      if (eset == 0)
-        for (int f0 = 0; f0 < D; f0 += 8) {  // eight loads in flight
-          float xv[8];
+      for (int f0 = 0; f0 < D; f0 += 8) {  // eight loads in flight
+        float xv[8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) xv[u] = (valid && f0 + u < D) ? gx[g * D + f0 + u] : 0.f;
+        for (int u = 0; u < 8; ++u) xv[u] = (valid && f0 + u < D) ? gx[g * D + f0 + u] : 0.f;
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int f = f0 + u;
-            if (f < D) {
-              float v0 = xv[u];
-              if (inverse && valid)
-                v0 = (args.base == MF_BASE_DIAG_NORMAL) ? (float)bp.a[f] + (float)bp.b[f] * v0
-                                                       : (float)bp.a[f] + ((float)bp.b[f] - (float)bp.a[f]) * v0;
-              if (valid) gz[g * D + f] = v0;
-              put1(row, xcol0 + f, v0);  // x columns of the layer-0 operand
-            }
+        for (int u = 0; u < 8; ++u) {
+          const int f = f0 + u;
+          if (f < D) {
+            float v0 = xv[u];
+            if (inverse && valid)
+              v0 = (args.base == MF_BASE_DIAG_NORMAL) ? (float)bp.a[f] + (float)bp.b[f] * v0
+                                                     : (float)bp.a[f] + ((float)bp.b[f] - (float)bp.a[f]) * v0;
+            if (valid) gz[g * D + f] = v0;
+            put1(row, xcol0 + f, v0);  // x columns of the layer-0 operand
           }
         }
+      }
       float* gy = static_cast<float*>(args.work);  // sampling: target y of the transform being inverted
       float ladj = 0.f;
       MF_TRACE(gt == 0, 951 + 10 * t);
@@ -625,8 +599,7 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
       //      operand has retired (this group waited on the last accumulator of that tile)
       {
         const int kfill = L.in0_ksteps * 16;
-        if (eset == 0)
-          for (int k = xcol0 + D; k < kfill; ++k) put1(row, k, 0.f);
+        for (int k = xcol0 + D; k < kfill; ++k) put1(row, k, 0.f);
         // context: one 16-byte operand chunk (8 columns of one row) per thread and step, four chunks in flight;
         // consecutive threads take consecutive chunks, so a warp reads a contiguous stretch of global memory
         const int nchunk = xcol0 >> 3;  // chunks per row (the last one zero-padded when C % 8 != 0)
@@ -637,10 +610,10 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
           int rr[4], kc[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const int q = q0 + u * GT;
-            rr[u] = q / nchunk;
-            kc[u] = q - rr[u] * nchunk;
-            const bool live = (q < total) && (rr[u] < rows);
+            const int qq = q0 + u * GT;
+            rr[u] = qq / nchunk;
+            kc[u] = qq - rr[u] * nchunk;
+            const bool live = (qq < total) && (rr[u] < rows);
             const float* src = gct + (long long)rr[u] * C + kc[u] * 8;
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[u][e] = (live && kc[u] * 8 + e < C) ? __ldg(src + e) : 0.f;
@@ -680,7 +653,6 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
           for (long long o = (long long)gt * 128; o < cb; o += (long long)GT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + o));
         }
       }
-      if (EW > 1) group_bar(1 + t, GT);  // x written by warp set 0 is read by the other set below
       float lp_base = 0.f;               // base log-density, accumulated as the last transform's outputs appear
       float bias_next;
       {
@@ -690,7 +662,7 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
       MF_TRACE(gt == 0, 953 + 10 * t);
       for (int unit = 0; unit < n_units; ++unit) {
         const int tr = inverse ? (L.T - 1 - unit / sweeps) : unit;
-        if (inverse && (unit % sweeps) == 0 && eset == 0) {  // y <- x, x <- 0  (AutoregressiveTransform._inverse)
+        if (inverse && (unit % sweeps) == 0) {  // y <- x, x <- 0  (AutoregressiveTransform._inverse)
           for (int f = 0; f < D; ++f) {
             if (valid) { gy[g * D + f] = gz[g * D + f]; gz[g * D + f] = 0.f; }
             put1(row, xcol0 + f, 0.f);
@@ -707,7 +679,7 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
           ++jobctr;
           // this job's biases -> shared memory (double-buffered by job parity), overlapping the MMA
           float* sb = sbias[t][jpar];
-          if (gt < j.N) sb[gt] = bias_next;  // fetched one job ahead (global latency off the critical path)
+          if (gt < j.N) sb[gt] = j.last ? bias_next * bscale_last : bias_next;  // fetched one job ahead
           {
             int ju = unit, jn = ji + 1;
             if (jn == L.njobs) { jn = 0; ++ju; }
@@ -721,45 +693,47 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
             }
           }
           group_bar(1 + t, GT);
-          // inputs of this chunk's splines, fetched before the accumulator wait (at most 5 features per chunk)
+          // inputs of this chunk's splines, fetched before the accumulator wait
           const float* xsrc = (inverse ? gy : gz) + g * D + j.feat0;
-          float xnext = (j.last && eset < j.nfeat && valid) ? xsrc[eset] : 0.f;
+          float xnext = (j.last && valid) ? xsrc[0] : 0.f;
           MF_TRACE(gt == 0, 500 + 300 * t + ji);
-          mbar_wait(&acc_full[t], jpar);
+          mbar_wait(&acc_full[t][j.region], (j.region ? fullctr1 : fullctr0) & 1);
+          if (j.region) ++fullctr1; else ++fullctr0;
           MF_TRACE(gt == 0, 300 + 300 * t + ji);
           tc::fence_after_thread_sync();
           const uint32_t taddr = tmem + lane_off + (uint32_t)(t * 256);
           if (!j.last) {
             // hidden layer: TMEM -> +bias -> ReLU -> operand planes of the next layer (in place)
-            const int csplit = (EW == 1) ? j.N : min(j.N, ((j.N / 2 + 31) / 32) * 32);
-            const int cbeg = eset == 0 ? 0 : csplit, cend = eset == 0 ? csplit : j.N;
-            for (int c00 = cbeg; c00 < cend; c00 += 32) {
+            for (int c00 = 0; c00 < j.N; c00 += 32) {
               float vv[32];
               tc::tmem_ld16(taddr + c00, vv);
-              if (c00 + 16 < cend) tc::tmem_ld16(taddr + c00 + 16, vv + 16);
+              if (c00 + 16 < j.N) tc::tmem_ld16(taddr + c00 + 16, vv + 16);
               tc::tmem_ld_wait();
 #pragma unroll
               for (int half = 0; half < 2; ++half) {
                 const int c0 = c00 + half * 16;
-                if (c0 < cend) {
+                if (c0 < j.N) {
                   float* v = vv + half * 16;
+                  float2 w2[8];
 #pragma unroll
                   for (int i = 0; i < 16; i += 4) {
                     const float4 b4 = *reinterpret_cast<const float4*>(sb + c0 + i);
-                    v[i] = fmaxf(v[i] + b4.x, 0.f); v[i + 1] = fmaxf(v[i + 1] + b4.y, 0.f);
-                    v[i + 2] = fmaxf(v[i + 2] + b4.z, 0.f); v[i + 3] = fmaxf(v[i + 3] + b4.w, 0.f);
+                    float2 u0 = f2_add(make_float2(v[i], v[i + 1]), make_float2(b4.x, b4.y));
+                    float2 u1 = f2_add(make_float2(v[i + 2], v[i + 3]), make_float2(b4.z, b4.w));
+                    w2[i / 2] = make_float2(fmaxf(u0.x, 0.f), fmaxf(u0.y, 0.f));
+                    w2[i / 2 + 1] = make_float2(fmaxf(u1.x, 0.f), fmaxf(u1.y, 0.f));
                   }
                   // 16 values -> 8 packed 16-bit pairs per plane -> operand planes in TMEM
                   if (NSPLIT == 3) {
                     uint32_t hi[8], lo[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) tc::split_f16(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+                    for (int i = 0; i < 8; ++i) split_f16_pair(w2[i], hi[i], lo[i]);
                     tc::tmem_st8(taddr + 128 + c0 / 2, hi);
                     tc::tmem_st8(taddr + 192 + c0 / 2, lo);
                   } else {
                     uint32_t pk[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) pk[i] = tc::pack_bf16(v[2 * i], v[2 * i + 1]);
+                    for (int i = 0; i < 8; ++i) pk[i] = tc::pack_bf16(w2[i].x, w2[i].y);
                     tc::tmem_st8(taddr + 128 + c0 / 2, pk);
                   }
                 }
@@ -767,71 +741,40 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
             }
             tc::tmem_st_wait();
             tc::fence_before_thread_sync();
-            mbar_arrive(&acc_free[t]);
             mbar_arrive(&a_ready[t]);
             MF_TRACE(gt == 0, 400 + 300 * t + ji);
           } else {
             // last-layer chunk: splines of the chunk's features straight out of TMEM
             const unsigned long long fmask = sched ? sched[(size_t)tr * MF_MAX_FEATURES + (unit % sweeps)] : ~0ull;
 #pragma unroll 1
-            for (int fl = eset; fl < j.nfeat; fl += EW) {  // one copy of the spline code (instruction cache)
+            for (int fl = 0; fl < j.nfeat; ++fl) {  // one copy of the spline code (instruction cache)
               const int f = j.feat0 + fl;
               const float xv = xnext;
-              if (fl + EW < j.nfeat && valid) xnext = xsrc[fl + EW];  // next feature's input, in flight during this spline
+              if (fl + 1 < j.nfeat && valid) xnext = xsrc[fl + 1];  // next feature's input, in flight during this spline
               if (!((fmask >> f) & 1ull)) continue;  // sampling: provisional feature of this sweep, keeps its value
               float out, la;
               int bin;
               bool ins;
-              const uint32_t ta = taddr + fl * L.PFt;
-              const float* sbf = sb + fl * L.PFt;
-              switch (L.Kp) {
-                case 8: rqs_forward_tmem_reg<1>(ta, sbf, cfg, inverse, xv, out, la, bin, ins); break;
-#ifdef MF_TC_TRACE
-                case 16: {
-                  long long ts5[5];
-                  rqs_forward_tmem_reg<2>(ta, sbf, cfg, inverse, xv, out, la, bin, ins, ts5);
-                  if (gt == 0 && t == 0 && blockIdx.x == 0 && trace_n < 2900) {
-                    long long* tb_ = reinterpret_cast<long long*>(args.inside);
-                    for (int q5 = 0; q5 < 5; ++q5) { tb_[2 * trace_n] = ts5[q5]; tb_[2 * trace_n + 1] = 900 + q5; ++trace_n; }
-                  }
-                } break;
-#else
-                case 16: rqs_forward_tmem_reg<2>(ta, sbf, cfg, inverse, xv, out, la, bin, ins); break;
-#endif
-                case 24: rqs_forward_tmem_reg<3>(ta, sbf, cfg, inverse, xv, out, la, bin, ins); break;
-                case 32: rqs_forward_tmem_reg<4>(ta, sbf, cfg, inverse, xv, out, la, bin, ins); break;
-                default: rqs_forward_tmem(ta, sbf, cfg, L.Kp, xv, out, la, bin, ins); break;
-              }
+              spline_tmem<NCHK, INV>(taddr + j.acc_col + fl * L.PFt, sb + fl * L.PFt, cf, xv, out, la, bin, ins);
               put1(row, xcol0 + f, valid ? out : 0.f);  // next unit's layer-0 operand (its last reader, job 0, has retired)
               if (valid) {
                 gz[g * D + f] = out;
                 ladj += la;
-                if (EW == 1 && !inverse && unit == n_units - 1)
+                if (!inverse && unit == n_units - 1)
                   lp_base += base_log_prob_1<float>(args.base, out, (float)bp.a[f], (float)bp.b[f]);
                 if (!inverse && args.bins) args.bins[((size_t)tr * n + g) * D + f] = (int8_t)bin;
                 if (!inverse && args.inside) args.inside[((size_t)tr * n + g) * D + f] = ins ? 1 : 0;
               }
             }
             tc::fence_before_thread_sync();
-            mbar_arrive(&acc_free[t]);
+            mbar_arrive(&acc_free[t][j.region]);
             MF_TRACE(gt == 0, 400 + 300 * t + ji);
           }
         }
       }
-      if (EW > 1 && !inverse) {  // the other warp set's share of ladj travels through the workspace
-        float* wl = static_cast<float*>(args.work);
-        if (eset == 1 && valid) wl[g] = ladj;
-        group_bar(1 + t, GT);
-        if (eset == 0 && valid) ladj += wl[g];
-      }
-      if (valid && !inverse && eset == 0) {
+      if (valid && !inverse) {
         if (args.ladj) static_cast<float*>(args.ladj)[g] = ladj;
-        if (args.logprob) {
-          float lp = lp_base;
-          if (EW > 1)
-            for (int f = 0; f < D; ++f) lp += base_log_prob_1<float>(args.base, gz[g * D + f], (float)bp.a[f], (float)bp.b[f]);
-          static_cast<float*>(args.logprob)[g] = lp + ladj;
-        }
+        if (args.logprob) static_cast<float*>(args.logprob)[g] = lp_base + ladj;
       }
     }
   }
@@ -860,7 +803,7 @@ int flow_tc_sched_layout(const mf_flow_desc& d, int gemm, long long* offset, int
   int rc = make_tc_layout(d, gemm, &L);
   if (rc != MF_OK) return rc;
   *offset = tc_sched_offset(L);
-  *features_per_chunk = std::max(1, 128 / L.PFt);
+  *features_per_chunk = L.fpc;
   return MF_OK;
 }
 
@@ -891,18 +834,29 @@ int flow_tc_pack(const mf_flow_desc& d, const void* const* w, const void* const*
   return MF_OK;
 }
 
-int tc_epilogue_sets() {  // MF_TC_EW=2 selects the 16-epilogue-warp variant (measured: no gain, kept for A/B runs)
-  static const int ew = [] {
-    const char* e = getenv("MF_TC_EW");
-    return (e && e[0] == '2') ? 2 : 1;
-  }();
-  return ew;
-}
-
 long long flow_tc_workspace_bytes(const mf_flow_desc& d, long long n, int gemm, int op) {
   (void)gemm;
   if (op == MF_FLOW_OP_SAMPLE) return n * d.features * 4;  // y targets of the transform being inverted
-  return n * 4;                                            // ladj share of the second epilogue warp set
+  return 0;
+}
+
+template <int NS, int NCHK, bool INV>
+static int tc_launch(const TcLayout& L, const FlowKernelArgs& a, const BaseParams& bp, unsigned grid, size_t smem, cudaStream_t st) {
+  MF_CUDA_CHECK(cudaFuncSetAttribute(flow_tc_kernel<NS, NCHK, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  flow_tc_kernel<NS, NCHK, INV><<<grid, 11 * 32, smem, st>>>(L, a, bp);
+  return MF_OK;
+}
+template <int NS, bool INV>
+static int tc_launch_k(const TcLayout& L, const FlowKernelArgs& a, const BaseParams& bp, unsigned grid, size_t smem, cudaStream_t st) {
+  switch (L.Kp) {
+    case 8: return tc_launch<NS, 1, INV>(L, a, bp, grid, smem, st);
+    case 16: return tc_launch<NS, 2, INV>(L, a, bp, grid, smem, st);
+    case 24: return tc_launch<NS, 3, INV>(L, a, bp, grid, smem, st);
+    case 32: return tc_launch<NS, 4, INV>(L, a, bp, grid, smem, st);
+    case 40: return tc_launch<NS, 5, INV>(L, a, bp, grid, smem, st);
+  }
+  set_error("tensor-core flow path: unsupported bins (roundup(K,8) = %d)", L.Kp);
+  return MF_EUNSUPPORTED;
 }
 
 int flow_tc_run(const mf_flow_desc& d, const FlowKernelArgs& a, const BaseParams& bp, int gemm, cudaStream_t st) {
@@ -913,17 +867,16 @@ int flow_tc_run(const mf_flow_desc& d, const FlowKernelArgs& a, const BaseParams
   FlowKernelArgs a_run = a;
   if (a.mode == 1) a_run.sched = reinterpret_cast<const unsigned long long*>(static_cast<const char*>(a.blob) + tc_sched_offset(L));
   if (a.ctx_group > 1) {
-    set_error("context grouping (ctx_group=%d) is implemented on the MF_GEMM_EXACT path only", a.ctx_group);
+    set_error("context grouping (ctx_group=%d) is not implemented on the tcgen05 path; use MF_GEMM_MMA_3XF16 / MF_GEMM_EXACT", a.ctx_group);
     return MF_EUNSUPPORTED;
   }
-  if (a.mode == 1) {
-    if (L.Kp > 32) {
-      set_error("tensor-core sampling needs bins <= 32 (got %d); use MF_GEMM_EXACT", d.bins);
-      return MF_EUNSUPPORTED;
-    }
+  if (!(a.slope > 0.0)) {
+    set_error("the tcgen05 flow path needs the soft clip of the spline logits (slope > 0); use MF_GEMM_EXACT");
+    return MF_EUNSUPPORTED;
+  }
+  if (a.mode == 1)
     MF_REQUIRE(a.work != nullptr && a.work_bytes >= flow_tc_workspace_bytes(d, a.n, gemm, MF_FLOW_OP_SAMPLE),
                "tensor-core sampling needs a workspace of mf_flow_workspace_bytes() bytes");
-  }
   const int parts = (L.nsplit == 3) ? 2 : 1;
   MF_REQUIRE(L.stages >= 2, "layer-0 operand too large for the weight ring");
   const size_t smem = (size_t)2 * parts * L.in0_plane_bytes + (size_t)L.stages * parts * kWPartBytes;
@@ -932,19 +885,9 @@ int flow_tc_run(const mf_flow_desc& d, const FlowKernelArgs& a, const BaseParams
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const unsigned grid = (unsigned)std::min<long long>(n_pairs, sms);
-  if (a.mode == 0)
-    MF_REQUIRE(a.work != nullptr && a.work_bytes >= a.n * 4, "tensor-core log_prob needs a workspace of mf_flow_workspace_bytes() bytes");
-  const int ew = tc_epilogue_sets();
-#define MF_TC_LAUNCH2(NS, EWV, INVV)                                                                                  \
-  do {                                                                                                                \
-    MF_CUDA_CHECK(cudaFuncSetAttribute(flow_tc_kernel<NS, EWV, INVV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    flow_tc_kernel<NS, EWV, INVV><<<grid, (3 + 8 * EWV) * 32, smem, st>>>(L, a_run, bp);                              \
-  } while (0)
-#define MF_TC_LAUNCH(NS, EWV) do { if (a.mode == 1) MF_TC_LAUNCH2(NS, EWV, true); else MF_TC_LAUNCH2(NS, EWV, false); } while (0)
-  if (L.nsplit == 3) { if (ew == 2) MF_TC_LAUNCH(3, 2); else MF_TC_LAUNCH(3, 1); }
-  else               { if (ew == 2) MF_TC_LAUNCH(1, 2); else MF_TC_LAUNCH(1, 1); }
-#undef MF_TC_LAUNCH2
-#undef MF_TC_LAUNCH
+  if (L.nsplit == 3) rc = (a.mode == 1) ? tc_launch_k<3, true>(L, a_run, bp, grid, smem, st) : tc_launch_k<3, false>(L, a_run, bp, grid, smem, st);
+  else               rc = (a.mode == 1) ? tc_launch_k<1, true>(L, a_run, bp, grid, smem, st) : tc_launch_k<1, false>(L, a_run, bp, grid, smem, st);
+  if (rc != MF_OK) return rc;
   return post_launch("flow_tc_kernel");
 }
 

@@ -20,39 +20,48 @@ namespace {
 
 constexpr int kRqsRows = 256;
 
-// fp32 fast path: all logits of the element in registers (K <= 8 * NCH)
-template <int NCH>
-__device__ __forceinline__ void rqs_row_reg(const float* p, const SplineCfg<float>& cfg, bool inverse, float v,
-                                            float& out, float& la, int& bin, bool& ins) {
+// fp32 fast path: all logits of the element in registers (K <= 8 * NCH), masked-sum spline of spline_reg.cuh
+template <int NCH, bool INV>
+__device__ __forceinline__ void rqs_row_reg(const float* p, const RqsScaled& cf, float v, float& out, float& la, int& bin,
+                                            bool& ins) {
   constexpr int KP = 8 * NCH;
-  const int K = cfg.K;
+  const int K = cf.K;
   float lw[KP], lh[KP], ld[KP];
 #pragma unroll
   for (int j = 0; j < KP; ++j) {
     // clamped indices instead of guarded loads (a conditional load compiles to one branch per element); the
-    // duplicated entries beyond K are masked out inside the spline
+    // duplicated width / height entries beyond K are masked out inside the spline, derivative entries from K-1 on
+    // must be zero (boundary derivative exp(0) = 1)
     const int jw = min(j, K - 1), jd = max(min(j, K - 2), 0);
-    lw[j] = p[jw];
-    lh[j] = p[K + jw];
-    ld[j] = p[2 * K + jd];
+    lw[j] = p[jw] * cf.inv2;
+    lh[j] = p[K + jw] * cf.inv2;
+    ld[j] = (j < K - 1) ? p[2 * K + jd] * cf.inv1 : 0.f;
   }
-  rqs_eval_reg<NCH>(lw, lh, ld, cfg, inverse, v, out, la, bin, ins);
+  rqs_masked_sums<NCH, INV>(lw, lh, ld, cf, v, out, la, bin, ins);
 }
 
 template <typename T>
-__device__ __forceinline__ void rqs_row(T* p, const SplineCfg<T>& cfg, bool inverse, T v, T& out, T& la, int& bin,
-                                        bool& ins) {
+__device__ __forceinline__ void rqs_row(T* p, const SplineCfg<T>& cfg, double slope, bool inverse, T v, T& out, T& la,
+                                        int& bin, bool& ins) {
   rqs_univariate<T>(p, 1, cfg, inverse, v, out, la, bin, ins);
 }
 template <>
-__device__ __forceinline__ void rqs_row<float>(float* p, const SplineCfg<float>& cfg, bool inverse, float v, float& out,
-                                               float& la, int& bin, bool& ins) {
+__device__ __forceinline__ void rqs_row<float>(float* p, const SplineCfg<float>& cfg, double slope, bool inverse, float v,
+                                               float& out, float& la, int& bin, bool& ins) {
   const int K = cfg.K;
-  if (K <= 8) rqs_row_reg<1>(p, cfg, inverse, v, out, la, bin, ins);
-  else if (K <= 16) rqs_row_reg<2>(p, cfg, inverse, v, out, la, bin, ins);
-  else if (K <= 24) rqs_row_reg<3>(p, cfg, inverse, v, out, la, bin, ins);
-  else if (K <= 32) rqs_row_reg<4>(p, cfg, inverse, v, out, la, bin, ins);
-  else rqs_univariate<float>(p, 1, cfg, inverse, v, out, la, bin, ins);
+  if (K > 40 || !(slope > 0.0)) {  // no soft clip (unbounded logits) or more bins than the register path holds
+    rqs_univariate<float>(p, 1, cfg, inverse, v, out, la, bin, ins);
+    return;
+  }
+  const RqsScaled cf = make_rqs_scaled(K, cfg.univariate, (double)cfg.bound, slope);
+#define MF_RQS_CASE(NCH) \
+  { if (inverse) rqs_row_reg<NCH, true>(p, cf, v, out, la, bin, ins); else rqs_row_reg<NCH, false>(p, cf, v, out, la, bin, ins); }
+  if (K <= 8) MF_RQS_CASE(1)
+  else if (K <= 16) MF_RQS_CASE(2)
+  else if (K <= 24) MF_RQS_CASE(3)
+  else if (K <= 32) MF_RQS_CASE(4)
+  else MF_RQS_CASE(5)
+#undef MF_RQS_CASE
 }
 
 template <typename T>
@@ -89,7 +98,7 @@ __global__ void __launch_bounds__(kRqsRows, 2) rqs_kernel(const T* __restrict__ 
     T out, la;
     int bin;
     bool ins;
-    rqs_row<T>(s_par + (size_t)tid * P, cfg, inverse != 0, g_x[first + tid], out, la, bin, ins);
+    rqs_row<T>(s_par + (size_t)tid * P, cfg, slope, inverse != 0, g_x[first + tid], out, la, bin, ins);
     g_y[first + tid] = out;
     if (g_ladj) g_ladj[first + tid] = la;
     if (g_bins) g_bins[first + tid] = (int8_t)bin;

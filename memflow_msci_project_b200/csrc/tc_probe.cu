@@ -255,34 +255,27 @@ __global__ void __launch_bounds__(128, 1) tc_issue_probe_kernel(float* __restric
 }
 
 
-// Spline-scan throughput probe: every thread runs `iters` register splines (K = 16) back to back on one SM;
-// out[0] = cycles per spline seen by warp 0.  variant 0: knot scan only, 1: scan + finish (full spline).
+// Spline throughput probe: every thread runs `iters` register splines (K = 16, masked-sum form of spline_reg.cuh)
+// back to back on one SM; out[0] = cycles per spline seen by warp 0.  variant 0: forward, 1: inverse.
 __global__ void spline_probe_kernel(float* __restrict__ out, int iters, int variant, float seed) {
-  SplineCfg<float> cfg;
-  cfg.K = 16; cfg.univariate = MF_UNIV_RQS; cfg.bound = 1.f;
-  cfg.inv_ls2 = 2.f / logf(1e-3f); cfg.inv_ls1 = 1.f / logf(1e-3f);
+  const RqsScaled cf = make_rqs_scaled(16, MF_UNIV_RQS, 1.0, 1e-3);
   const float tf = seed * (float)(threadIdx.x % 29) * 0.01f;
 #define MF_PB(j) (tf + (float)(((j) * 13) % 31 - 15) * 0.1f)
   float v = 0.01f * (threadIdx.x % 64) - 0.3f, acc = 0.f;
   const long long t0 = clock64();
   for (int i = 0; i < iters; ++i) {
-    float lw[16], lh[16];
+    float lw[16], lh[16], ld[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) { lw[j] = MF_PB(j) + acc; lh[j] = MF_PB(16 + j) - acc; }
-    int k; bool inside; float x0, x1, y0, y1, l0;
-    float vv = v;
-    rqs_scan_reg<2>(lw, lh, cfg, false, vv, k, inside, x0, x1, y0, y1, l0);
-    if (variant == 1) {
-      float t0_, t1_, o, la;
-      float ld[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) ld[j] = MF_PB(32 + j) + acc;
-      select_pair<16>(ld, k, t0_, t1_);
-      rqs_finish(cfg, false, vv, k, inside, x0, x1, y0, y1, t0_, t1_, l0, o, la);
-      acc = 1e-6f * (o + la);
-    } else {
-      acc = 1e-6f * (x0 + y1 + (float)k);
+    for (int j = 0; j < 16; ++j) {
+      lw[j] = (MF_PB(j) + acc) * cf.inv2; lh[j] = (MF_PB(16 + j) - acc) * cf.inv2;
+      ld[j] = (j < 15) ? (MF_PB(32 + j) + acc) * cf.inv1 : 0.f;
     }
+    float o, la;
+    int k;
+    bool inside;
+    if (variant == 1) rqs_masked_sums<2, true>(lw, lh, ld, cf, v, o, la, k, inside);
+    else rqs_masked_sums<2, false>(lw, lh, ld, cf, v, o, la, k, inside);
+    acc = 1e-6f * (o + la + (float)k);
   }
   const long long t1 = clock64();
   if (threadIdx.x == 0) out[0] = (float)(t1 - t0) / (float)iters;
@@ -328,6 +321,7 @@ __global__ void mma_sync_probe_kernel(float* __restrict__ out, int iters, int f1
 
 using namespace mf;
 
+// test-only entry point of libmemflow_b200_probe.so (NOT part of the product ABI, not declared in include/memflow_b200.h)
 extern "C" int mf_tc_probe_gemm(const float* d_a, const float* d_w, float* d_out, int32_t k, int32_t n, int32_t mode,
                                 void* stream) {
   MF_REQUIRE(d_a && d_w && d_out, "mf_tc_probe_gemm: null argument");

@@ -198,12 +198,15 @@ class _FlowForwardFn(torch.autograd.Function):
     def forward(ctx, bound_flow, x, c, *params):
         m = bound_flow._m
         dtype = m.compute_dtype()
-        gemm = m.effective_gemm(dtype)
+        G = bound_flow._ctx_group
+        gemm = m.effective_gemm(dtype, ctx_group=G)
         desc, blob = m.packed(x.device, dtype, gemm=gemm)
+        desc = bound_flow._with_group(desc)   # ctx_group > 1: c has one row per G consecutive x rows
         z = torch.empty_like(x)
         ladj = torch.empty(x.shape[0], dtype=dtype, device=x.device)
         _cabi.flow_log_prob(desc, blob, x, c, None, z, ladj, None, None, gemm)
         ctx.module = m
+        ctx.group = G
         ctx.has_c = c is not None
         ctx.save_for_backward(x, c if c is not None else x.new_empty(0))
         return z, ladj
@@ -217,7 +220,9 @@ class _FlowForwardFn(torch.autograd.Function):
         with torch.enable_grad():
             xr = x.detach().requires_grad_(True)
             cr = c.detach().requires_grad_(True) if c is not None else None
-            z, ladj = eager_forward(m, xr, cr)
+            # grouped context: the recompute sees the context repeated per row; autograd sums the group's gradient
+            ce = cr.repeat_interleave(ctx.group, dim=0) if (cr is not None and ctx.group > 1) else cr
+            z, ladj = eager_forward(m, xr, ce)
             inputs = [xr] + ([cr] if cr is not None else []) + [p for p in params if p.requires_grad]
             grads = torch.autograd.grad([z, ladj], inputs, [gz, gladj], allow_unused=True)
         it = iter(grads)
@@ -253,11 +258,14 @@ class _FlowInverseFn(torch.autograd.Function):
     def forward(ctx, bound_flow, z, c, *params):
         m = bound_flow._m
         dtype = m.compute_dtype()
-        gemm = m.effective_gemm(dtype, sampling=True)
+        G = bound_flow._ctx_group
+        gemm = m.effective_gemm(dtype, sampling=True, ctx_group=G)
         desc, blob = m.packed(z.device, dtype, identity_base=True, gemm=gemm)
+        desc = bound_flow._with_group(desc)
         x = torch.empty_like(z)
         _cabi.flow_sample(desc, blob, z, c, x, gemm)
         ctx.module = m
+        ctx.group = G
         ctx.has_c = c is not None
         ctx.save_for_backward(z, c if c is not None else z.new_empty(0))
         return x
@@ -271,7 +279,8 @@ class _FlowInverseFn(torch.autograd.Function):
         with torch.enable_grad():
             zr = z.detach().requires_grad_(True)
             cr = c.detach().requires_grad_(True) if c is not None else None
-            x = eager_inverse(m, zr, cr)
+            ce = cr.repeat_interleave(ctx.group, dim=0) if (cr is not None and ctx.group > 1) else cr
+            x = eager_inverse(m, zr, ce)
             inputs = [zr] + ([cr] if cr is not None else []) + [p for p in params if p.requires_grad]
             grads = torch.autograd.grad([x], inputs, [gx], allow_unused=True)
         it = iter(grads)

