@@ -156,6 +156,19 @@ int mf_rambo_get_ps(const mf_rambo_desc* desc, const void* d_momenta, const void
                     const int32_t* perm, int64_t n_events, void* d_ps, uint8_t* d_mask,
                     int io_dtype, int compute, void* stream);
 
+/*
+ * Lab-frame get_PS: memflow/unfolding_flow/unfolding_flow.py:137-163 in ONE launch:
+ *   1. fix an unphysical regressed boost (:140-143): where sqrt(E^2 - pz^2) < m_min_tot the energy becomes
+ *      sqrt(pz^2 + m_min_tot^2 + 1e-3)                                        (m_min_tot <= 0: skipped)
+ *   2. momenta_cm = boost_tt(momenta_lab, -boostVector_t(boost))               (phasespace/utils.py:36-42, 121-147)
+ *   3. get_PS(momenta_cm, boost) as mf_rambo_get_ps
+ *   d_momenta_lab [N,4,4], d_boost [N,4] (E,px,py,pz)
+ *   d_momenta_cm [N,4,4] (may be NULL), d_boost_fixed [N,4] (may be NULL), d_ps [N,10], d_mask [N] (may be NULL)
+ */
+int mf_rambo_get_ps_lab(const mf_rambo_desc* desc, const void* d_momenta_lab, const void* d_boost,
+                        const int32_t* perm, int64_t n_events, double m_min_tot, void* d_momenta_cm,
+                        void* d_boost_fixed, void* d_ps, uint8_t* d_mask, int io_dtype, int compute, void* stream);
+
 /* ------------------------------------------------------------------------- */
 /* conditional RQ-spline masked autoregressive flow (zuko NSF / MAF family)  */
 
@@ -238,6 +251,35 @@ int mf_flow_log_prob(const mf_flow_desc* desc, const void* d_blob, const void* d
 int mf_flow_sample(const mf_flow_desc* desc, const void* d_blob, const void* d_noise,
                    const void* d_ctx, int64_t n, void* d_x, int dtype, int gemm, void* d_workspace,
                    int64_t workspace_bytes, void* stream);
+
+/*
+ * Element-wise maps of the flow's data side, fused into the kernels' load / store of x (a19 in SURVEY.md section 8:
+ * the logit / sigmoid bridge between the unit hypercube of the phase space and the flow's unbounded space):
+ *   MF_XMAP_SIGMOID_AFFINE  on the OUTPUT of mf_flow_sample:   x' = sigmoid(x * scale[f] + shift[f])
+ *                           (scripts/run_model_labframe_sampling.py:427: torch.sigmoid(flow_samples*scale_ps + mean_ps))
+ *   MF_XMAP_LOGIT_AFFINE    on the INPUT of mf_flow_log_prob:  x' = (logit(clamp(x, eps, 1-eps)) - shift[f]) / scale[f]
+ *                           (memflow/unfolding_flow/unfolding_flow.py:170-171: torch.logit(ps, eps=5e-5), then the
+ *                           (x - mean) / std scaling).  Like the reference, the map is a data transformation: it does not
+ *                           contribute to ladj / log_prob.
+ * A NULL map (or kind MF_XMAP_NONE) leaves the call identical to the unmapped entry points.
+ */
+#define MF_XMAP_NONE 0
+#define MF_XMAP_SIGMOID_AFFINE 1
+#define MF_XMAP_LOGIT_AFFINE 2
+typedef struct mf_flow_xmap {
+  int32_t kind; /* MF_XMAP_* */
+  int32_t reserved;
+  double eps;   /* clamp of the logit (torch.logit's eps); unused by the sigmoid */
+  double scale[MF_MAX_FEATURES];
+  double shift[MF_MAX_FEATURES];
+} mf_flow_xmap;
+int mf_flow_log_prob_mapped(const mf_flow_desc* desc, const void* d_blob, const void* d_x,
+                            const void* d_ctx, int64_t n, void* d_logprob, void* d_z, void* d_ladj,
+                            int8_t* d_bins, uint8_t* d_inside, int dtype, int gemm, void* d_workspace,
+                            int64_t workspace_bytes, const mf_flow_xmap* in_map, void* stream);
+int mf_flow_sample_mapped(const mf_flow_desc* desc, const void* d_blob, const void* d_noise,
+                          const void* d_ctx, int64_t n, void* d_x, int dtype, int gemm, void* d_workspace,
+                          int64_t workspace_bytes, const mf_flow_xmap* out_map, void* stream);
 
 /*
  * Scratch the two calls above need for (desc, n, dtype, gemm); op 0 = log_prob, 1 = sample.  The caller

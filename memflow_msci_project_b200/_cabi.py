@@ -102,6 +102,17 @@ def rambo_get_ps(desc: RamboDesc, momenta, boost, perm, ps, mask, compute):
     check(rc, "mf_rambo_get_ps")
 
 
+def rambo_get_ps_lab(desc: RamboDesc, momenta_lab, boost, perm, m_min_tot, momenta_cm, boost_fixed, ps, mask, compute):
+    """Fused boost fix-up + lab -> CM boost + get_PS (mf_rambo_get_ps_lab)."""
+    perm_arr = (ctypes.c_int32 * 4)(*perm) if perm is not None else None
+    with torch.cuda.device(momenta_lab.device):
+        rc = lib().mf_rambo_get_ps_lab(ctypes.byref(desc), _ptr(momenta_lab), _ptr(boost), perm_arr,
+                                       ctypes.c_int64(momenta_lab.shape[0]), ctypes.c_double(m_min_tot), _ptr(momenta_cm),
+                                       _ptr(boost_fixed), _ptr(ps), _ptr(mask), ctypes.c_int(io_dtype_of(momenta_lab)),
+                                       ctypes.c_int(compute), _stream(momenta_lab.device))
+    check(rc, "mf_rambo_get_ps_lab")
+
+
 # ---- conditional spline flows ---------------------------------------------------------------------
 def _dtype_code(dtype):
     return {torch.float32: MF_F32, torch.float64: MF_F64}[dtype]
@@ -158,24 +169,50 @@ def _flow_workspace(desc, n, dtype, gemm, op, device):
     return torch.empty(int(nb), dtype=torch.uint8, device=device) if nb > 0 else None
 
 
-def flow_log_prob(desc, blob, x, ctx, logprob, z, ladj, bins, inside, gemm):
+MF_MAX_FEATURES = 64
+MF_XMAP_NONE, MF_XMAP_SIGMOID_AFFINE, MF_XMAP_LOGIT_AFFINE = 0, 1, 2
+
+
+class FlowXmap(ctypes.Structure):
+    """ctypes mirror of ``struct mf_flow_xmap`` (element-wise map fused into the x load / store of the flow kernels)."""
+
+    _fields_ = [("kind", ctypes.c_int32), ("reserved", ctypes.c_int32), ("eps", ctypes.c_double),
+                ("scale", ctypes.c_double * MF_MAX_FEATURES), ("shift", ctypes.c_double * MF_MAX_FEATURES)]
+
+
+def make_xmap(kind, scale, shift, features, eps=0.0):
+    m = FlowXmap()
+    m.kind, m.eps = kind, float(eps)
+    sc = [float(v) for v in torch.as_tensor(scale, dtype=torch.float64).reshape(-1).expand(features).tolist()] \
+        if torch.as_tensor(scale).numel() in (1, features) else None
+    sh = [float(v) for v in torch.as_tensor(shift, dtype=torch.float64).reshape(-1).expand(features).tolist()] \
+        if torch.as_tensor(shift).numel() in (1, features) else None
+    if sc is None or sh is None:
+        raise ValueError(f"x-map scale / shift must be scalars or have {features} entries")
+    for f in range(features):
+        m.scale[f], m.shift[f] = sc[f], sh[f]
+    return m
+
+
+def flow_log_prob(desc, blob, x, ctx, logprob, z, ladj, bins, inside, gemm, xmap=None):
     ws = _flow_workspace(desc, x.shape[0], x.dtype, gemm, 0, x.device)
     with torch.cuda.device(x.device):
-        rc = lib().mf_flow_log_prob(ctypes.byref(desc), _ptr(blob), _ptr(x), _ptr(ctx),
-                                    ctypes.c_int64(x.shape[0]), _ptr(logprob), _ptr(z), _ptr(ladj),
-                                    _ptr(bins), _ptr(inside), ctypes.c_int(_dtype_code(x.dtype)),
-                                    ctypes.c_int(gemm), _ptr(ws), ctypes.c_int64(ws.numel() if ws is not None else 0),
-                                    _stream(x.device))
+        rc = lib().mf_flow_log_prob_mapped(ctypes.byref(desc), _ptr(blob), _ptr(x), _ptr(ctx),
+                                           ctypes.c_int64(x.shape[0]), _ptr(logprob), _ptr(z), _ptr(ladj),
+                                           _ptr(bins), _ptr(inside), ctypes.c_int(_dtype_code(x.dtype)),
+                                           ctypes.c_int(gemm), _ptr(ws), ctypes.c_int64(ws.numel() if ws is not None else 0),
+                                           ctypes.byref(xmap) if xmap is not None else None, _stream(x.device))
     check(rc, "mf_flow_log_prob")
 
 
-def flow_sample(desc, blob, noise, ctx, x, gemm):
+def flow_sample(desc, blob, noise, ctx, x, gemm, xmap=None):
     ws = _flow_workspace(desc, noise.shape[0], noise.dtype, gemm, 1, noise.device)
     with torch.cuda.device(noise.device):
-        rc = lib().mf_flow_sample(ctypes.byref(desc), _ptr(blob), _ptr(noise), _ptr(ctx),
-                                  ctypes.c_int64(noise.shape[0]), _ptr(x),
-                                  ctypes.c_int(_dtype_code(noise.dtype)), ctypes.c_int(gemm), _ptr(ws),
-                                  ctypes.c_int64(ws.numel() if ws is not None else 0), _stream(noise.device))
+        rc = lib().mf_flow_sample_mapped(ctypes.byref(desc), _ptr(blob), _ptr(noise), _ptr(ctx),
+                                         ctypes.c_int64(noise.shape[0]), _ptr(x),
+                                         ctypes.c_int(_dtype_code(noise.dtype)), ctypes.c_int(gemm), _ptr(ws),
+                                         ctypes.c_int64(ws.numel() if ws is not None else 0),
+                                         ctypes.byref(xmap) if xmap is not None else None, _stream(noise.device))
     check(rc, "mf_flow_sample")
 
 

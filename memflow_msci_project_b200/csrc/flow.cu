@@ -215,6 +215,8 @@ flow_kernel(const __grid_constant__ FlowLayout L, const __grid_constant__ FlowKe
           if (args.mode == 1) {  // base sample from caller-supplied noise
             v = (args.base == MF_BASE_DIAG_NORMAL) ? (T)bp.a[c] + (T)bp.b[c] * v
                                                   : (T)bp.a[c] + ((T)bp.b[c] - (T)bp.a[c]) * v;
+          } else if (bp.xmap_kind != MF_XMAP_NONE) {
+            v = xmap_apply<T>(bp, v, c);   // input map of log_prob (logit bridge)
           }
         } else if (c < D + C) {
           v = gc[((tile0 + m) / args.ctx_group) * C + (c - D)];
@@ -334,7 +336,11 @@ flow_kernel(const __grid_constant__ FlowLayout L, const __grid_constant__ FlowKe
       }
     } else {
       T* gz = static_cast<T*>(args.z);
-      for (int i = tid; i < rows * D; i += kThreads) gz[tile0 * D + i] = in0[(size_t)(i / D) * L.in0_ld + (i % D)];
+      for (int i = tid; i < rows * D; i += kThreads) {
+        T v = in0[(size_t)(i / D) * L.in0_ld + (i % D)];
+        if (bp.xmap_kind != MF_XMAP_NONE) v = xmap_apply<T>(bp, v, i % D);   // output map of sample (sigmoid bridge)
+        gz[tile0 * D + i] = v;
+      }
     }
     __syncthreads();
   }
@@ -462,7 +468,22 @@ int mf_flow_pack_weights(const mf_flow_desc* desc, const void* const* d_weights,
   return MF_OK;
 }
 
-static int flow_run(const mf_flow_desc* desc, const FlowKernelArgs& a, int dtype, int gemm, void* stream) {
+static int fill_xmap(BaseParams* bp, const mf_flow_xmap* map, int mode, int features) {
+  bp->xmap_kind = MF_XMAP_NONE; bp->xmap_eps = 0.0;
+  for (int f = 0; f < MF_MAX_FEATURES; ++f) { bp->xmap_scale[f] = 1.0; bp->xmap_shift[f] = 0.0; }
+  if (map == nullptr || map->kind == MF_XMAP_NONE) return MF_OK;
+  MF_REQUIRE((mode == 0 && map->kind == MF_XMAP_LOGIT_AFFINE) || (mode == 1 && map->kind == MF_XMAP_SIGMOID_AFFINE),
+             "mf_flow_xmap kind %d does not apply to this call (log_prob takes MF_XMAP_LOGIT_AFFINE on its input, sample "
+             "MF_XMAP_SIGMOID_AFFINE on its output)", map->kind);
+  bp->xmap_kind = map->kind; bp->xmap_eps = map->eps;
+  for (int f = 0; f < features; ++f) {
+    MF_REQUIRE(map->kind != MF_XMAP_LOGIT_AFFINE || map->scale[f] != 0.0, "mf_flow_xmap: zero scale for feature %d", f);
+    bp->xmap_scale[f] = map->scale[f]; bp->xmap_shift[f] = map->shift[f];
+  }
+  return MF_OK;
+}
+
+static int flow_run(const mf_flow_desc* desc, const FlowKernelArgs& a, int dtype, int gemm, const mf_flow_xmap* map, void* stream) {
   int rc = check_flow_common(desc, dtype, gemm);
   if (rc != MF_OK) return rc;
   FlowLayout L;
@@ -474,6 +495,8 @@ static int flow_run(const mf_flow_desc* desc, const FlowKernelArgs& a, int dtype
     if (a.n == 0) return MF_OK;
     BaseParams bpt;
     for (int f = 0; f < MF_MAX_FEATURES; ++f) { bpt.a[f] = desc->base_a[f]; bpt.b[f] = desc->base_b[f]; }
+    rc = fill_xmap(&bpt, map, a.mode, desc->features);
+    if (rc != MF_OK) return rc;
     return flow_tc_run(*desc, a, bpt, gemm, static_cast<cudaStream_t>(stream));
   }
   MF_REQUIRE(desc->context == 0 || a.ctx != nullptr || a.n == 0, "context pointer is null but context=%d", desc->context);
@@ -481,6 +504,8 @@ static int flow_run(const mf_flow_desc* desc, const FlowKernelArgs& a, int dtype
   if (a.n == 0) return MF_OK;
   BaseParams bp;
   for (int f = 0; f < MF_MAX_FEATURES; ++f) { bp.a[f] = desc->base_a[f]; bp.b[f] = desc->base_b[f]; }
+  rc = fill_xmap(&bp, map, a.mode, desc->features);
+  if (rc != MF_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   FlowKernelArgs as = a;
   if (a.mode == 1)
@@ -492,10 +517,10 @@ static int flow_run(const mf_flow_desc* desc, const FlowKernelArgs& a, int dtype
   return dtype == MF_F32 ? launch_flow<float>(L, as, bp, st) : launch_flow<double>(L, as, bp, st);
 }
 
-int mf_flow_log_prob(const mf_flow_desc* desc, const void* d_blob, const void* d_x, const void* d_ctx,
-                     int64_t n, void* d_logprob, void* d_z, void* d_ladj, int8_t* d_bins,
-                     uint8_t* d_inside, int dtype, int gemm, void* d_workspace, int64_t workspace_bytes,
-                     void* stream) {
+int mf_flow_log_prob_mapped(const mf_flow_desc* desc, const void* d_blob, const void* d_x, const void* d_ctx,
+                            int64_t n, void* d_logprob, void* d_z, void* d_ladj, int8_t* d_bins,
+                            uint8_t* d_inside, int dtype, int gemm, void* d_workspace, int64_t workspace_bytes,
+                            const mf_flow_xmap* in_map, void* stream) {
   MF_REQUIRE(n >= 0, "mf_flow_log_prob: negative count");
   MF_REQUIRE(desc && d_blob && (d_x || n == 0), "mf_flow_log_prob: null argument");
   FlowKernelArgs a{};
@@ -505,7 +530,15 @@ int mf_flow_log_prob(const mf_flow_desc* desc, const void* d_blob, const void* d
   a.ctx_group = desc->ctx_group > 1 ? desc->ctx_group : 1;
   a.mode = 0; a.passes = desc->passes; a.base = desc->base; a.univariate = desc->univariate;
   a.bound = desc->bound; a.slope = desc->slope;
-  return flow_run(desc, a, dtype, gemm, stream);
+  return flow_run(desc, a, dtype, gemm, in_map, stream);
+}
+
+int mf_flow_log_prob(const mf_flow_desc* desc, const void* d_blob, const void* d_x, const void* d_ctx,
+                     int64_t n, void* d_logprob, void* d_z, void* d_ladj, int8_t* d_bins,
+                     uint8_t* d_inside, int dtype, int gemm, void* d_workspace, int64_t workspace_bytes,
+                     void* stream) {
+  return mf_flow_log_prob_mapped(desc, d_blob, d_x, d_ctx, n, d_logprob, d_z, d_ladj, d_bins, d_inside, dtype, gemm,
+                                 d_workspace, workspace_bytes, nullptr, stream);
 }
 
 int64_t mf_flow_workspace_bytes(const mf_flow_desc* desc, int64_t n, int dtype, int gemm, int op) {
@@ -514,9 +547,9 @@ int64_t mf_flow_workspace_bytes(const mf_flow_desc* desc, int64_t n, int dtype, 
   return flow_tc_workspace_bytes(*desc, n, gemm, op);
 }
 
-int mf_flow_sample(const mf_flow_desc* desc, const void* d_blob, const void* d_noise, const void* d_ctx,
-                   int64_t n, void* d_x, int dtype, int gemm, void* d_workspace, int64_t workspace_bytes,
-                   void* stream) {
+int mf_flow_sample_mapped(const mf_flow_desc* desc, const void* d_blob, const void* d_noise, const void* d_ctx,
+                          int64_t n, void* d_x, int dtype, int gemm, void* d_workspace, int64_t workspace_bytes,
+                          const mf_flow_xmap* out_map, void* stream) {
   MF_REQUIRE(n >= 0, "mf_flow_sample: negative count");
   MF_REQUIRE(desc && d_blob && ((d_noise && d_x) || n == 0), "mf_flow_sample: null argument");
   MF_REQUIRE(desc->passes >= 1 && desc->passes <= desc->features, "passes=%d outside 1..features", desc->passes);
@@ -527,7 +560,14 @@ int mf_flow_sample(const mf_flow_desc* desc, const void* d_blob, const void* d_n
   a.ctx_group = desc->ctx_group > 1 ? desc->ctx_group : 1;
   a.mode = 1; a.passes = desc->passes; a.base = desc->base; a.univariate = desc->univariate;
   a.bound = desc->bound; a.slope = desc->slope;
-  return flow_run(desc, a, dtype, gemm, stream);
+  return flow_run(desc, a, dtype, gemm, out_map, stream);
+}
+
+int mf_flow_sample(const mf_flow_desc* desc, const void* d_blob, const void* d_noise, const void* d_ctx,
+                   int64_t n, void* d_x, int dtype, int gemm, void* d_workspace, int64_t workspace_bytes,
+                   void* stream) {
+  return mf_flow_sample_mapped(desc, d_blob, d_noise, d_ctx, n, d_x, dtype, gemm, d_workspace, workspace_bytes, nullptr,
+                               stream);
 }
 
 int64_t mf_flow_sched_offset(const mf_flow_desc* desc, int dtype, int gemm) {

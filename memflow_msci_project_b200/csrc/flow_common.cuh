@@ -90,6 +90,7 @@ struct FlowKernelArgs {
   uint8_t* inside;
   const unsigned short* klim;        // mma mode: k-step limits per 128-column block (NULL: full K)
   const unsigned long long* sched;  // sampling: [T][MF_MAX_FEATURES] chunk bitmasks per sweep (NULL: every chunk every sweep)
+  const unsigned long long* skip;   // tcgen05 path: zero-block table [T][jobs] (flow_tc_skip_kernel)
   void* work;         // caller-provided scratch (mf_flow_workspace_bytes)
   long long work_bytes;
   int ctx_group;      // x rows per context row (>= 1)
@@ -103,6 +104,11 @@ struct FlowKernelArgs {
 struct BaseParams {
   double a[MF_MAX_FEATURES];
   double b[MF_MAX_FEATURES];
+  // element-wise map of the data side (mf_flow_xmap): applied to x when it is loaded (log_prob) / stored (sample)
+  int xmap_kind;
+  double xmap_eps;
+  double xmap_scale[MF_MAX_FEATURES];
+  double xmap_shift[MF_MAX_FEATURES];
 };
 
 
@@ -252,6 +258,22 @@ __device__ __forceinline__ void rqs_univariate(T* p, int ps, const SplineCfg<T>&
     out = x;
     ladj = T(0);
   }
+}
+
+// mf_flow_xmap on one value of feature f (see include/memflow_b200.h)
+template <typename T>
+__device__ __forceinline__ T xmap_apply(const BaseParams& bp, T v, int f) {
+  if (bp.xmap_kind == MF_XMAP_SIGMOID_AFFINE) {
+    const T t = v * (T)bp.xmap_scale[f] + (T)bp.xmap_shift[f];
+    return T(1) / (T(1) + FM<T>::exp_(-t));
+  }
+  if (bp.xmap_kind == MF_XMAP_LOGIT_AFFINE) {
+    const T e = (T)bp.xmap_eps;
+    T c = v < e ? e : (v > T(1) - e ? T(1) - e : v);   // torch.logit(x, eps): clamp to [eps, 1 - eps]
+    const T l = FM<T>::log_(c / (T(1) - c));
+    return (l - (T)bp.xmap_shift[f]) / (T)bp.xmap_scale[f];
+  }
+  return v;
 }
 
 // base.log_prob contribution of one feature

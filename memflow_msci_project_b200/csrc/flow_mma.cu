@@ -351,6 +351,8 @@ flow_mma_kernel(const __grid_constant__ FlowLayout L, const __grid_constant__ Fl
         if (args.mode == 1)  // base sample from caller-supplied noise
           v = (args.base == MF_BASE_DIAG_NORMAL) ? (float)bp.a[c] + (float)bp.b[c] * v
                                                  : (float)bp.a[c] + ((float)bp.b[c] - (float)bp.a[c]) * v;
+        else if (bp.xmap_kind != MF_XMAP_NONE)
+          v = xmap_apply<float>(bp, v, c);  // input map of log_prob (logit bridge)
       }
       xcur[i] = v;
     }
@@ -453,7 +455,11 @@ flow_mma_kernel(const __grid_constant__ FlowLayout L, const __grid_constant__ Fl
     // ---- outputs
     float* gz = static_cast<float*>(args.z);
     if (gz)
-      for (int i = tid; i < rows * D; i += kWThreads) gz[tile0 * D + i] = xcur[i];
+      for (int i = tid; i < rows * D; i += kWThreads) {
+        float v = xcur[i];
+        if (args.mode == 1 && bp.xmap_kind != MF_XMAP_NONE) v = xmap_apply<float>(bp, v, i % D);  // output map of sample
+        gz[tile0 * D + i] = v;
+      }
     if (args.mode == 0) {
       for (int m = tid; m < rows; m += kWThreads) {
         const float la = ladj_s[m];

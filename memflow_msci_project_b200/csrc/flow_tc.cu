@@ -1,15 +1,17 @@
 // flow_tc.cu -- fused conditional RQ-spline MAF log_prob / sample with the conditioner GEMMs on tcgen05.
 //
-// One persistent CTA per SM works on PAIRS of 128-object tiles (two "tile slots").  Warp roles (352 threads):
-//   warp 0        weight loader: streams the packed, pre-swizzled weight K-blocks from L2 into a shared-memory ring
+// One persistent CTA per SM works on PAIRS of 128-object tiles (two "tile slots").  Warp roles (320 threads):
+//   warps 0-3     epilogue group of tile slot 0 (thread = object = TMEM lane; warp % 4 = TMEM lane quarter)
+//   warps 4-7     epilogue group of tile slot 1
+//   warp 8        weight loader: streams the packed, pre-swizzled weight K-blocks from L2 into a shared-memory ring
 //                 (as many 32 KB stages as fit next to the layer-0 operands) with 1-D bulk async copies (TMA engine)
 //                 completing on mbarriers
-//   warp 1        MMA issuer: walks the job schedule, the two tile slots take turns job by job; per weight K-block ONE
-//                 elected lane issues the tcgen05.mma (M=128, N<=128, K=16, kind::f16, fp32 accumulate in TMEM) back to
-//                 back and commits the stage / accumulator mbarriers
-//   warp 2        spare (keeps the epilogue warps aligned to the TMEM lane quarters, warp % 4)
-//   warps 3-6     epilogue group of tile slot 0 (thread = object = TMEM lane)
-//   warps 7-10    epilogue group of tile slot 1
+//   warp 9        MMA issuer: walks the job schedule, the two tile slots take turns job by job; per job ONE elected lane
+//                 issues the tcgen05.mma (M=128, N<=128, K=16, kind::f16, fp32 accumulate in TMEM) of the whole job back
+//                 to back and commits the stage / accumulator mbarriers
+// The control warps carry the HIGHEST warp ids of their scheduler on purpose: the sub-partition arbiter prefers the
+// highest warp id, and with the issuer as warp 1 it lost the issue slot to the epilogue warps of its scheduler for
+// ~1000 cycles per job (per-warp trace profiles/trace_flow_tc_r2f.txt: dependencies met at t, batch issued at t + 1000).
 // While the tensor core works on one slot's job, the other slot's epilogue (TMEM accumulator -> registers -> bias +
 // ReLU -> fp16 hi/lo operand planes -> back into TMEM with tcgen05.st) runs on the CUDA cores.  Hidden activations never
 // leave TMEM: layer l+1 takes its A operand straight from TMEM (tcgen05.mma, TS form); only the layer-0 operand
@@ -35,27 +37,30 @@
 namespace mf {
 namespace {
 
-// Optional cycle-level trace of CTA 0 / first tile pair (build with -DMF_TC_TRACE): events are written as
-// (clock64, id) pairs into the `inside` debug buffer.  ids: 100+ji MMA sees a_ready, 200+ji MMA issued,
-// 300+ji epilogue sees acc_full, 400+ji epilogue done (tile slot 0 only).
+// Optional cycle-level trace of CTA 0 (build with -DMF_TC_TRACE): every traced warp writes (clock64, id) pairs into its
+// own region of the `inside` debug buffer; id = warp * 1000 + code * 20 + job.  Codes: issuer 1 = weights landed,
+// 2 = operand / accumulator dependencies met, 3 = batch issued; epilogue warps 5 = waiting for the accumulator,
+// 6 = accumulator complete, 7 = done (arrived on the next barrier); 8/9 = tile start / tile staged.  tools/trace_tc.py.
 #ifdef MF_TC_TRACE
-#define MF_TRACE(cond, id)                                                          \
-  do {                                                                              \
-    if ((cond) && blockIdx.x == 0 && trace_n < 4000) {                              \
-      long long* tb_ = reinterpret_cast<long long*>(args.inside);                   \
-      tb_[2 * trace_n] = clock64(); tb_[2 * trace_n + 1] = (id); ++trace_n;         \
-    }                                                                               \
+#define MF_TRACE(cond, code, job)                                                    \
+  do {                                                                               \
+    if ((cond) && blockIdx.x == 0 && trace_n < trace_end) {                          \
+      long long* tb_ = reinterpret_cast<long long*>(args.inside);                    \
+      tb_[2 * trace_n] = clock64(); tb_[2 * trace_n + 1] = (threadIdx.x >> 5) * 1000 + (code) * 20 + (job); ++trace_n; \
+    }                                                                                \
   } while (0)
 #else
-#define MF_TRACE(cond, id) do { } while (0)
+#define MF_TRACE(cond, code, job) do { } while (0)
 #endif
 
+constexpr int kTcThreads = 10 * 32;              // 8 epilogue warps + loader + MMA issuer
+constexpr int kLoaderWarp = 8, kIssuerWarp = 9;
 constexpr int kMaxStages = 8;                   // weight ring depth: as many as fit next to the layer-0 operands
 constexpr int kMaxJobs = 40;
 constexpr uint32_t kWPartBytes = 128 * 128;     // one [<=128 rows x 64] 16-bit weight K-block
 constexpr uint32_t kKBlockBytes = 128 * 128;    // one [128 x 64] 16-bit SWIZZLE_128B K-block of the layer-0 operand
 constexpr uint32_t kTailBytes = 128 * 32;       // one [128 x 16] 16-bit SWIZZLE_32B k-step of the layer-0 operand
-constexpr size_t kStaticSmem = 4096;            // barriers, bias slots (static __shared__), alignment slack
+constexpr size_t kStaticSmem = 10240;           // barriers, per-warp bias slots (static __shared__), alignment slack
 
 struct TcJob {
   int N;        // MMA N (multiple of 16, <= 128)
@@ -69,6 +74,7 @@ struct TcJob {
   int in_dim, out_dim;
   long long w_off;  // bytes from the transform base to K-block 0 ([hi block][lo block] per K-block)
   int b_off;        // floats from the transform bias base
+  int nstages;      // weight ring stages of the job: both K-blocks of a narrow job (N <= 64) share one stage
   int region;       // accumulator region (barrier pair) of a last-layer chunk; hidden layers use region 0 and all columns
   int acc_col;      // first accumulator column of the job (0 or 64)
 };
@@ -124,6 +130,7 @@ int make_tc_layout(const mf_flow_desc& d, int gemm, TcLayout* L) {
     j.ksteps = round_up(l == 0 ? L->xcol0 + d.features : j.in_dim, 16) / 16;
     j.nkb = (j.ksteps + 3) / 4;
     j.needs_a = 1; j.last = 0; j.feat0 = 0; j.nfeat = 0; j.layer = l; j.row0 = 0; j.region = 0; j.acc_col = 0;
+    j.nstages = (j.nkb == 1 || j.N <= 64) ? 1 : 2;
     j.w_off = woff; woff += (long long)j.nkb * parts * j.N * 128;
     j.b_off = boff; boff += j.N;
   }
@@ -153,6 +160,7 @@ int make_tc_layout(const mf_flow_desc& d, int gemm, TcLayout* L) {
     j.nkb = (j.ksteps + 3) / 4;
     j.needs_a = (f0 == 0) ? 1 : 0; j.last = 1; j.layer = d.n_hidden; j.row0 = f0 * (3 * d.bins - 1);
     j.region = (L->nregions == 2) ? (ci & 1) : 0; j.acc_col = j.region * 64;
+    j.nstages = (j.nkb == 1 || j.N <= 64) ? 1 : 2;
     j.w_off = woff; woff += (long long)j.nkb * parts * j.N * 128;
     j.b_off = boff; boff += j.N;
   }
@@ -172,34 +180,43 @@ struct TcPackArgs {
   const uint8_t* m[kMaxLayers];
 };
 
+// masked weight of packed row n, operand column k of job j (0 for padding) and the zuko row it comes from
+template <typename T>
+__device__ __forceinline__ float tc_packed_weight(const TcLayout& L, const TcPackArgs<T>& a, const TcJob& j, int ji, int n, int k,
+                                                  int* src_row_out) {
+  const int P = 3 * L.K - 1;
+  int src_row = -1;
+  if (!j.last) {
+    if (n < j.out_dim) src_row = n;
+  } else {
+    const int fl = n / L.PFt, c = n % L.PFt;
+    if (fl < j.nfeat) {
+      const int seg = c / L.Kp, jj = c % L.Kp;  // 0 widths, 1 heights, 2 derivatives
+      const int len = (seg == 2) ? L.K - 1 : L.K;
+      if (jj < len) src_row = (j.feat0 + fl) * P + seg * L.K + jj;
+    }
+  }
+  float v = 0.f;
+  int src_col = k;  // layer 0: operand column -> zuko input column (x | context)
+  if (ji == 0) src_col = (k < L.C) ? L.D + k : ((k >= L.xcol0 && k < L.xcol0 + L.D) ? k - L.xcol0 : -1);
+  if (src_row >= 0 && src_col >= 0 && src_col < j.in_dim) {
+    const long long s = (long long)src_row * j.in_dim + src_col;
+    v = a.m[j.layer][s] ? (float)a.w[j.layer][s] : 0.f;
+  }
+  if (src_row_out) *src_row_out = src_row;
+  return v;
+}
+
 template <typename T>
 __global__ void flow_tc_pack_kernel(TcLayout L, TcPackArgs<T> a, unsigned char* blob_t, float* bias_t) {
   const int parts = (L.nsplit == 3) ? 2 : 1;
-  const int P = 3 * L.K - 1;
   for (int ji = 0; ji < L.njobs; ++ji) {
     const TcJob j = L.job[ji];
     const int kdim = j.nkb * 64;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < j.N * kdim; i += gridDim.x * blockDim.x) {
       const int n = i / kdim, k = i % kdim;
-      // source row in zuko layout
-      int src_row = -1;
-      if (!j.last) {
-        if (n < j.out_dim) src_row = n;
-      } else {
-        const int fl = n / L.PFt, c = n % L.PFt;
-        if (fl < j.nfeat) {
-          const int seg = c / L.Kp, jj = c % L.Kp;  // 0 widths, 1 heights, 2 derivatives
-          const int len = (seg == 2) ? L.K - 1 : L.K;
-          if (jj < len) src_row = (j.feat0 + fl) * P + seg * L.K + jj;
-        }
-      }
-      float v = 0.f;
-      int src_col = k;  // layer 0: operand column -> zuko input column (x | context)
-      if (ji == 0) src_col = (k < L.C) ? L.D + k : ((k >= L.xcol0 && k < L.xcol0 + L.D) ? k - L.xcol0 : -1);
-      if (src_row >= 0 && src_col >= 0 && src_col < j.in_dim) {
-        const long long s = (long long)src_row * j.in_dim + src_col;
-        v = a.m[j.layer][s] ? (float)a.w[j.layer][s] : 0.f;
-      }
+      int src_row;
+      const float v = tc_packed_weight(L, a, j, ji, n, k, &src_row);
       const int kb = k >> 6;
       unsigned char* blk = blob_t + j.w_off + (long long)kb * parts * j.N * 128;
       const uint32_t off = tc::sw128_offset(n, k & 63, j.N);
@@ -219,12 +236,57 @@ __global__ void flow_tc_pack_kernel(TcLayout L, TcPackArgs<T> a, unsigned char* 
   }
 }
 
+// Zero-block table: for job ji and k-step ks (16 operand columns) byte ks of word [ji] = (number of LEADING packed rows
+// whose weights in these columns are all exactly zero) / 16, i.e. the MMA of that k-step only has to produce the
+// accumulator columns from 16 * byte on (byte = N / 16: the whole k-step is skipped).  With the hidden units sorted by
+// autoregressive degree (host mirror, _sort_hidden_units) the masked weight matrices are block-triangular and ~1/4 of
+// the tensor work falls away; the skipped products are exact zeros, so the results do not change.  k-step 0 always
+// covers every column (it initialises the accumulator).
+template <typename T>
+__global__ void flow_tc_skip_kernel(TcLayout L, TcPackArgs<T> a, unsigned long long* skip_t) {
+  const int ji = blockIdx.x, ks = threadIdx.x;  // 8 threads per job
+  if (ji >= L.njobs) return;
+  const TcJob j = L.job[ji];
+  int n0 = 0;
+  if (ks > 0 && ks < j.ksteps) {
+    for (; n0 < j.N; ++n0) {
+      bool nz = false;
+      for (int k = ks * 16; k < ks * 16 + 16; ++k) nz |= (tc_packed_weight(L, a, j, ji, n0, k, nullptr) != 0.f);
+      if (nz) break;
+    }
+  }
+  const unsigned long long byte = (unsigned long long)(n0 / 16) << (8 * ks);
+  // combine the 8 bytes of the job (threads 0..7 of the block)
+  __shared__ unsigned long long w[8];
+  w[ks] = byte;
+  __syncthreads();
+  if (ks == 0) skip_t[ji] = w[0] | w[1] | w[2] | w[3] | w[4] | w[5] | w[6] | w[7];
+}
+
 // ------------------------------------------------------------------------------------------------
+// non-suspending wait (mbarrier.test_wait poll): for the MMA issuer, whose wake-up from a suspended try_wait on a
+// barrier completed by plain thread arrivals took ~1000 cycles in the per-warp traces
+__device__ __forceinline__ void mbar_poll(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+// one arrival per WARP: every lane has finished (and fenced) its part, the warp converges, one lane arrives
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar, int lane) {
+  __syncwarp();
+  if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void group_bar(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 // Spline of one feature with its 3K-1 unconstrained parameters in TMEM (this thread's lane): columns [0,K) widths,
@@ -328,34 +390,42 @@ __device__ __forceinline__ void mma_ss_p(uint32_t tmem_d, uint64_t desc_a, uint6
 // tensor pipe is fed back to back (measured: bookkeeping between the K-blocks of a job used to cost ~500 cycles of an
 // idle pipe per K-block -- an MMA "cost" 85-105 cycles whatever its N was).
 //   hidden layers / last-layer chunks: A operand planes in TMEM (hi at a_tmem, lo 64 columns further)
+// skipw: zero-block word of the job (flow_tc_skip_kernel): k-step ks only produces accumulator columns >= 16 * byte ks
 template <int NSPLIT>
 __device__ __forceinline__ void issue_job_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t w_base0, uint32_t w_base1, uint32_t idesc,
-                                             int ksteps, uint64_t* empty0, uint64_t* empty1, bool release, uint64_t* full) {
-  const uint64_t b0h = tc::make_smem_desc(w_base0), b0l = tc::make_smem_desc(w_base0 + kWPartBytes);
-  const uint64_t b1h = tc::make_smem_desc(w_base1), b1l = tc::make_smem_desc(w_base1 + kWPartBytes);
+                                             int ksteps, int N, unsigned long long skipw, uint64_t* empty0, uint64_t* empty1,
+                                             uint64_t* full) {
+  const uint32_t part_bytes = (uint32_t)N * 128u;  // [hi][lo] planes of a K-block are dense in the stage
+  const uint64_t b0h = tc::make_smem_desc(w_base0), b0l = tc::make_smem_desc(w_base0 + part_bytes);
+  const uint64_t b1h = tc::make_smem_desc(w_base1), b1l = tc::make_smem_desc(w_base1 + part_bytes);
 #pragma unroll
   for (int ks = 0; ks < 8; ++ks) {
-    const uint32_t en = ks < ksteps ? 1u : 0u;
-    const uint64_t bh = (ks < 4 ? b0h : b1h) + (uint64_t)((ks & 3) * 2), bl = (ks < 4 ? b0l : b1l) + (uint64_t)((ks & 3) * 2);
+    const uint32_t n0 = ((uint32_t)(skipw >> (8 * ks)) & 0xFFu) << 4;  // leading all-zero weight rows of this k-step
+    const uint32_t en = (ks < ksteps && (int)n0 < N) ? 1u : 0u;
+    const uint32_t idk = idesc - ((n0 >> 3) << 17);                    // N - n0 columns
+    const uint32_t d = d_tmem + n0;
+    const uint64_t roff = (uint64_t)(n0 * 8u) + (uint64_t)((ks & 3) * 2);  // 128-byte weight rows, 32-byte k-steps (16-byte units)
+    const uint64_t bh = (ks < 4 ? b0h : b1h) + roff, bl = (ks < 4 ? b0l : b1l) + roff;
     const uint32_t a = a_tmem + (uint32_t)ks * 8u;
-    mma_ts_p(d_tmem, a, bh, idesc, ks ? 1u : 0u, en);
+    mma_ts_p(d, a, bh, idk, ks ? 1u : 0u, en);
     if (NSPLIT == 3) {
-      mma_ts_p(d_tmem, a, bl, idesc, 1u, en);
-      mma_ts_p(d_tmem, a + 64u, bh, idesc, 1u, en);
+      mma_ts_p(d, a, bl, idk, 1u, en);
+      mma_ts_p(d, a + 64u, bh, idk, 1u, en);
     }
-    if (ks == 3 && release) tc::mma_commit(empty0);  // K-block 0 consumed by both slots
+    if (ks == 3 && empty0) tc::mma_commit(empty0);  // first stage consumed by both slots
   }
-  if (release && ksteps > 4) tc::mma_commit(empty1);
+  if (empty1) tc::mma_commit(empty1);
   tc::mma_commit(full);
 }
 //   layer 0: (ctx | x) operand planes in shared memory: `nfull` 64-wide SWIZZLE_128B K-blocks, then single k-steps in
 //   SWIZZLE_32B blocks (a_hi / a_lo: plane bases, tail_off: byte offset of the first tail k-step inside a plane)
 template <int NSPLIT>
 __device__ __forceinline__ void issue_job_ss(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, int nfull, uint32_t tail_off,
-                                             uint32_t w_base0, uint32_t w_base1, uint32_t idesc, int ksteps, uint64_t* empty0,
-                                             uint64_t* empty1, bool release, uint64_t* full) {
-  const uint64_t b0h = tc::make_smem_desc(w_base0), b0l = tc::make_smem_desc(w_base0 + kWPartBytes);
-  const uint64_t b1h = tc::make_smem_desc(w_base1), b1l = tc::make_smem_desc(w_base1 + kWPartBytes);
+                                             uint32_t w_base0, uint32_t w_base1, uint32_t idesc, int ksteps, int N,
+                                             uint64_t* empty0, uint64_t* empty1, uint64_t* full) {
+  const uint32_t part_bytes = (uint32_t)N * 128u;
+  const uint64_t b0h = tc::make_smem_desc(w_base0), b0l = tc::make_smem_desc(w_base0 + part_bytes);
+  const uint64_t b1h = tc::make_smem_desc(w_base1), b1l = tc::make_smem_desc(w_base1 + part_bytes);
   const uint64_t fh0 = tc::make_smem_desc(a_hi), fl0 = tc::make_smem_desc(a_lo);
   const uint64_t fh1 = tc::make_smem_desc(a_hi + kKBlockBytes), fl1 = tc::make_smem_desc(a_lo + kKBlockBytes);
   const uint64_t th = tc::make_smem_desc_sw32(a_hi + tail_off), tl = tc::make_smem_desc_sw32(a_lo + tail_off);
@@ -372,16 +442,16 @@ __device__ __forceinline__ void issue_job_ss(uint32_t d_tmem, uint32_t a_hi, uin
       mma_ss_p(d_tmem, ah, bl, idesc, 1u, en);
       mma_ss_p(d_tmem, al, bh, idesc, 1u, en);
     }
-    if (ks == 3 && release) tc::mma_commit(empty0);
+    if (ks == 3 && empty0) tc::mma_commit(empty0);
   }
-  if (release && ksteps > 4) tc::mma_commit(empty1);
+  if (empty1) tc::mma_commit(empty1);
   tc::mma_commit(full);
 }
 
 // INV: sampling (transforms in reverse, `passes` sweeps each) -- a compile-time flag so that the log_prob kernel carries
 // none of the sweep / schedule logic.  NCHK = roundup(K, 8) / 8 (spline logits held in registers).
 template <int NSPLIT, int NCHK, bool INV>
-__global__ void __launch_bounds__(11 * 32, 1)
+__global__ void __launch_bounds__(kTcThreads, 1)
 flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowKernelArgs args,
                const __grid_constant__ BaseParams bp) {
   constexpr int kParts = (NSPLIT == 3) ? 2 : 1;           // operand planes (hi, lo)
@@ -395,7 +465,7 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
   const uint32_t kStages = (uint32_t)L.stages;
   __shared__ __align__(8) uint64_t w_full[kMaxStages], w_empty[kMaxStages], a_ready[2], acc_full[2][2], acc_free[2][2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ __align__(16) float sbias[2][2][128];  // [tile slot][job parity][column]
+  __shared__ __align__(16) float sbias[8][2][128];  // [epilogue warp][job parity][column]: every warp stages its own copy
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long n = args.n;
@@ -418,18 +488,18 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
   if (tid == 0) {
     for (int s = 0; s < kMaxStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     for (int t = 0; t < 2; ++t) {
-      mbar_init(&a_ready[t], 128);
-      for (int r = 0; r < 2; ++r) { mbar_init(&acc_full[t][r], 1); mbar_init(&acc_free[t][r], 128); }
+      mbar_init(&a_ready[t], 4);  // one arrival per epilogue warp of the slot
+      for (int r = 0; r < 2; ++r) { mbar_init(&acc_full[t][r], 1); mbar_init(&acc_free[t][r], 4); }
     }
     fence_mbar_init();
   }
-  if (warp == 1) tc::tmem_alloc(&tmem_base_s, 512);
+  if (warp == kIssuerWarp) tc::tmem_alloc(&tmem_base_s, 512);
   tc::fence_before_thread_sync();
   __syncthreads();
   tc::fence_after_thread_sync();
   const uint32_t tmem = tmem_base_s;
 
-  if (warp == 0) {
+  if (warp == kLoaderWarp) {
     // ===================== weight loader =====================
     if (lane == 0) {
       uint32_t s = 0, ph = 0;  // ring position / phase of the next stage to fill
@@ -440,21 +510,21 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
           for (int ji = 0; ji < L.njobs; ++ji) {
             if (!job_live(unit, ji)) continue;
             const TcJob& j = L.job[ji];
-            const uint32_t part_bytes = (uint32_t)j.N * 128u;
-            for (int kb = 0; kb < j.nkb; ++kb) {
+            // one bulk copy per ring stage: the K-blocks of a job are contiguous in the blob ([hi][lo] per K-block) and keep
+            // that dense layout in the stage; a narrow job (N <= 64) brings both of its K-blocks into ONE stage
+            const uint32_t kb_bytes = kParts * (uint32_t)j.N * 128u;
+            const uint32_t st_bytes = (j.nstages == 1) ? kb_bytes * (uint32_t)j.nkb : kb_bytes;
+            for (int q = 0; q < j.nstages; ++q) {
               mbar_wait_relaxed(&w_empty[s], ph ^ 1, 2000);
-              mbar_expect_tx(&w_full[s], kParts * part_bytes);
-              const unsigned char* src = tb + j.w_off + (long long)kb * kParts * part_bytes;
-              unsigned char* dst = w_ring + s * kStageBytes;
-#pragma unroll
-              for (int q = 0; q < kParts; ++q) bulk_g2s(dst + q * kWPartBytes, src + (size_t)q * part_bytes, part_bytes, &w_full[s]);
+              mbar_expect_tx(&w_full[s], st_bytes);
+              bulk_g2s(w_ring + s * kStageBytes, tb + j.w_off + (long long)q * kb_bytes, st_bytes, &w_full[s]);
               if (++s == kStages) { s = 0; ph ^= 1; }
             }
           }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kIssuerWarp) {
     // ===================== MMA issuer =====================
     // One warp walks the (warp-uniform) schedule and waits on the barriers; per K-block one elected lane issues
     // the MMAs back to back.  The two tile slots take turns job by job (slot 0's job j, slot 1's job j, slot 0's
@@ -463,10 +533,11 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
     // (a_ready: every thread of the slot has finished the previous epilogue, so the accumulator is drained as well);
     // a later last-layer chunk waits until the previous chunk in ITS accumulator region has been consumed (acc_free).
     uint32_t stage = 0, sphase = 0;  // ring position / phase of the next weight K-block to consume
-    int trace_n = 0; (void)trace_n;
+    int trace_n = 0, trace_end = 1500; (void)trace_n; (void)trace_end;
     uint32_t aph0 = 0, aph1 = 0;               // a_ready phases per slot
     uint32_t nchunk0 = 0, nchunk1 = 0;         // last-layer chunks issued so far per region (both slots walk the same jobs)
     const uint32_t tail_off = kFullBytes;
+    unsigned long long skip_next = args.skip ? __ldg(args.skip + (size_t)(inverse ? L.T - 1 : 0) * kMaxJobs) : 0ull;
     for (long long p = blockIdx.x; p < n_pairs; p += gridDim.x) {
       const int nact = (2 * p + 1 < n_tiles) ? 2 : 1;  // odd tile count: slot 1 idles in the last pair
       for (int unit = 0; unit < n_units; ++unit) {
@@ -478,6 +549,18 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
           const int jN = L.job[ji].N, jks = L.job[ji].ksteps, jlast = L.job[ji].last, jreg = L.job[ji].region;
           const uint32_t jcol = (uint32_t)L.job[ji].acc_col;
           const uint32_t idesc = tc::make_idesc_f16(NSPLIT == 3 ? 0 : 1, 128, jN);
+          // zero-block word of (transform, job): fetched one job ahead (an L2 round trip is ~500 cycles of an idle pipe)
+          const unsigned long long skipw = skip_next;
+          {
+            int ju = unit, jn = ji + 1;
+            if (jn == L.njobs) { jn = 0; ++ju; }
+            while (ju < n_units && !job_live(ju, jn)) {
+              if (++jn == L.njobs) { jn = 0; ++ju; }
+            }
+            if (ju >= n_units) { ju = 0; jn = 0; }  // first job of the next tile pair (job 0 is always live)
+            const int trn = inverse ? (L.T - 1 - ju / sweeps) : ju;
+            skip_next = args.skip ? __ldg(args.skip + (size_t)trn * kMaxJobs + jn) : 0ull;
+          }
           const bool wait_a = jlast ? first_last : true;
           const bool wait_free = jlast && (jreg ? in_unit1 : in_unit0) > 0;
           const uint32_t free_par = ((jreg ? nchunk1 : nchunk0) - 1) & 1;  // phase of the previous chunk of this region
@@ -485,36 +568,41 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
             first_last = false;
             if (jreg) { ++in_unit1; ++nchunk1; } else { ++in_unit0; ++nchunk0; }
           }
-          // ring slots of the job's (at most two) weight K-blocks; both must have landed before the batch is issued
+          // ring stages of the job's (at most two) weight K-blocks; everything must have landed before the batch is issued
+          const int jnst = L.job[ji].nstages;
           const uint32_t s0 = stage, p0 = sphase;
           uint32_t s1 = s0 + 1, p1 = p0;
           if (s1 == kStages) { s1 = 0; p1 ^= 1; }
-          const bool two = jks > 4;
+          const bool two = jnst > 1;
           mbar_wait(&w_full[s0], p0);
           if (two) mbar_wait(&w_full[s1], p1);
-          const uint32_t w_base0 = smem_u32(w_ring + s0 * kStageBytes), w_base1 = smem_u32(w_ring + s1 * kStageBytes);
+          MF_TRACE(lane == 0, 1, 2 * ji);
+          const uint32_t w_base0 = smem_u32(w_ring + s0 * kStageBytes);
+          const uint32_t w_base1 = two ? smem_u32(w_ring + s1 * kStageBytes) : w_base0 + kParts * (uint32_t)jN * 128u;
           for (int t = 0; t < nact; ++t) {
             const uint32_t d_tmem = tmem + (uint32_t)(t * 256) + jcol;
             const uint32_t a_tmem = tmem + (uint32_t)(t * 256) + 128;  // hi plane; lo plane 64 columns further
             const uint32_t a_base = smem_u32(a_buf + (size_t)t * kParts * kPlane);
             if (wait_a) {
-              mbar_wait(&a_ready[t], t ? aph1 : aph0);
+              mbar_poll(&a_ready[t], t ? aph1 : aph0);
               if (t) aph1 ^= 1; else aph0 ^= 1;
             }
-            if (wait_free) mbar_wait(&acc_free[t][jreg], free_par);
-            MF_TRACE(lane == 0, 100 + 10 * t + ji);
+            if (wait_free) mbar_poll(&acc_free[t][jreg], free_par);
+            MF_TRACE(lane == 0, 2, 2 * ji + t);
             tc::fence_after_thread_sync();
             if (tc::elect_one()) {
-              const bool release = (t == nact - 1);  // both slots are done with the stages
+              // the last slot releases the stages: the first one right after its k-steps when the job spans two stages
+              const bool release = (t == nact - 1);
+              uint64_t* e0 = (release && two) ? &w_empty[s0] : nullptr;
+              uint64_t* e1 = release ? (two ? &w_empty[s1] : &w_empty[s0]) : nullptr;
               if (ji == 0)
-                issue_job_ss<NSPLIT>(d_tmem, a_base, a_base + kPlane, L.in0_full, tail_off, w_base0, w_base1, idesc, jks,
-                                     &w_empty[s0], &w_empty[s1], release, &acc_full[t][jreg]);
+                issue_job_ss<NSPLIT>(d_tmem, a_base, a_base + kPlane, L.in0_full, tail_off, w_base0, w_base1, idesc, jks, jN,
+                                     e0, e1, &acc_full[t][jreg]);
               else
-                issue_job_ts<NSPLIT>(d_tmem, a_tmem, w_base0, w_base1, idesc, jks, &w_empty[s0], &w_empty[s1], release,
-                                     &acc_full[t][jreg]);
+                issue_job_ts<NSPLIT>(d_tmem, a_tmem, w_base0, w_base1, idesc, jks, jN, skipw, e0, e1, &acc_full[t][jreg]);
             }
             __syncwarp();
-            MF_TRACE(lane == 0, 200 + 10 * t + ji);
+            MF_TRACE(lane == 0, 3, 2 * ji + t);
           }
           // advance the ring by the job's K-blocks (s1 / p1 already are the wrapped successor of s0 / p0)
           stage = s1; sphase = p1;
@@ -525,14 +613,12 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
         }
       }
     }
-  } else if (warp == 2) {
-    // spare warp (keeps the epilogue warps aligned to the TMEM lane quarters: warp % 4)
   } else {
     // ===================== epilogue groups =====================
-    const int t = (warp - 3) >> 2;            // tile slot
+    const int t = warp >> 2;                  // tile slot
     const int q = warp & 3;                   // TMEM lane quarter this warp may access (4 consecutive warps cover all)
     const int row = q * 32 + lane;            // object inside the tile
-    const int gt = ((warp - 3) & 3) * 32 + lane;  // thread index inside the group (cooperative loops)
+    const int gt = (warp & 3) * 32 + lane;    // thread index inside the group (cooperative loops)
     constexpr int GT = 128;                   // threads per epilogue group
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     unsigned char* a_hi = a_buf + (size_t)t * kParts * kPlane;
@@ -547,12 +633,16 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
     float* gz = static_cast<float*>(args.z);
     const int D = L.D, C = L.C, xcol0 = L.xcol0;
     const RqsScaled cf = make_rqs_scaled(L.K, args.univariate, args.bound, args.slope);
-    // soft-clip scale of the bias of last-layer column gt (same column layout in every chunk): the spline works on
-    // logits pre-multiplied by 2 / ln(slope) (widths, heights) or 1 / ln(slope) (derivatives)
-    const float bscale_last = ((gt % L.PFt) / L.Kp == 2) ? cf.inv1 : cf.inv2;
+    // Biases: every warp keeps its own copy in shared memory (lane l stages columns 4l .. 4l+3 with one 16-byte load,
+    // fetched one job ahead), so the four warps of a slot never wait for each other outside the mbarriers.
+    // Soft-clip scale of the last-layer columns (same column layout in every chunk): the spline works on logits
+    // pre-multiplied by 2 / ln(slope) (widths, heights) or 1 / ln(slope) (derivatives); a 4-aligned group of columns
+    // never straddles a segment (segments are multiples of 8 columns wide).
+    const float bscale_last = (((4 * lane) % L.PFt) / L.Kp == 2) ? cf.inv1 : cf.inv2;
+    float* const sb_warp = &sbias[warp][0][0];
     uint32_t jobctr = 0;                      // bias double-buffer parity
     uint32_t fullctr0 = 0, fullctr1 = 0;      // accumulator uses per region
-    int trace_n = 2000 + 1000 * t; (void)trace_n;
+    int trace_n = 1500 + warp * 300, trace_end = trace_n + 300; (void)trace_n; (void)trace_end;
 
     auto put1 = [&](int r, int k, float v) {
       const uint32_t off = in0_offset(r, k);
@@ -574,7 +664,7 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
       const long long g = tile0 + row;
       // working copy of x lives in the output buffer (each thread touches only its own row); when sampling,
       // gx holds the noise and the base sample a + b * noise is the starting point
-      MF_TRACE(gt == 0, 950 + 10 * t);
+      MF_TRACE(lane == 0, 8, 0);
       for (int f0 = 0; f0 < D; f0 += 8) {  // eight loads in flight
         float xv[8];
 #pragma unroll
@@ -587,6 +677,7 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
             if (inverse && valid)
               v0 = (args.base == MF_BASE_DIAG_NORMAL) ? (float)bp.a[f] + (float)bp.b[f] * v0
                                                      : (float)bp.a[f] + ((float)bp.b[f] - (float)bp.a[f]) * v0;
+            if (!inverse && valid && bp.xmap_kind != MF_XMAP_NONE) v0 = xmap_apply<float>(bp, v0, f);  // logit bridge
             if (valid) gz[g * D + f] = v0;
             put1(row, xcol0 + f, v0);  // x columns of the layer-0 operand
           }
@@ -594,7 +685,6 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
       }
       float* gy = static_cast<float*>(args.work);  // sampling: target y of the transform being inverted
       float ladj = 0.f;
-      MF_TRACE(gt == 0, 951 + 10 * t);
       // ---- stage (ctx | 0) of the layer-0 operand once per tile; every MMA that read the previous tile's
       //      operand has retired (this group waited on the last accumulator of that tile)
       {
@@ -641,7 +731,6 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
           }
         }
       }
-      MF_TRACE(gt == 0, 952 + 10 * t);
       {  // pull this slot's next tile (x rows and context rows) into L2 while this one is being processed
         const long long nt0 = (tile + 2 * (long long)gridDim.x) * 128;
         if (nt0 < n) {
@@ -654,12 +743,13 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
         }
       }
       float lp_base = 0.f;               // base log-density, accumulated as the last transform's outputs appear
-      float bias_next;
+      float4 bias_next = make_float4(0.f, 0.f, 0.f, 0.f);
       {
         const int tr0 = inverse ? (L.T - 1) : 0;
-        bias_next = (gt < L.job[0].N) ? __ldg(bias_all + (size_t)tr0 * L.bias_stride + L.job[0].b_off + gt) : 0.f;
+        if (4 * lane < L.job[0].N)
+          bias_next = __ldg(reinterpret_cast<const float4*>(bias_all + (size_t)tr0 * L.bias_stride + L.job[0].b_off) + lane);
       }
-      MF_TRACE(gt == 0, 953 + 10 * t);
+      MF_TRACE(lane == 0, 9, 0);
       for (int unit = 0; unit < n_units; ++unit) {
         const int tr = inverse ? (L.T - 1 - unit / sweeps) : unit;
         if (inverse && (unit % sweeps) == 0) {  // y <- x, x <- 0  (AutoregressiveTransform._inverse)
@@ -671,15 +761,19 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
         // ---- layer-0 operand: the context part was staged at the tile start, the D columns of x were written
         //      by this thread when it produced them (tile start / spline output of the previous unit)
         fence_proxy_async_smem();
-        mbar_arrive(&a_ready[t]);
+        mbar_arrive_warp(&a_ready[t], lane);
         for (int ji = 0; ji < L.njobs; ++ji) {
           if (!job_live(unit, ji)) continue;
           const TcJob& j = L.job[ji];
           const uint32_t jpar = jobctr & 1;
           ++jobctr;
-          // this job's biases -> shared memory (double-buffered by job parity), overlapping the MMA
-          float* sb = sbias[t][jpar];
-          if (gt < j.N) sb[gt] = j.last ? bias_next * bscale_last : bias_next;  // fetched one job ahead
+          // this job's biases -> the warp's shared-memory slot (double-buffered by job parity), overlapping the MMA
+          float* sb = sb_warp + jpar * 128;
+          if (4 * lane < j.N) {
+            float4 bv = bias_next;
+            if (j.last) { bv.x *= bscale_last; bv.y *= bscale_last; bv.z *= bscale_last; bv.w *= bscale_last; }
+            reinterpret_cast<float4*>(sb)[lane] = bv;
+          }
           {
             int ju = unit, jn = ji + 1;
             if (jn == L.njobs) { jn = 0; ++ju; }
@@ -689,17 +783,18 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
             if (ju < n_units) {
               const int trn = inverse ? (L.T - 1 - ju / sweeps) : ju;
               const TcJob& nj = L.job[jn];
-              bias_next = (gt < nj.N) ? __ldg(bias_all + (size_t)trn * L.bias_stride + nj.b_off + gt) : 0.f;
+              if (4 * lane < nj.N)
+                bias_next = __ldg(reinterpret_cast<const float4*>(bias_all + (size_t)trn * L.bias_stride + nj.b_off) + lane);
             }
           }
-          group_bar(1 + t, GT);
+          __syncwarp();
           // inputs of this chunk's splines, fetched before the accumulator wait
           const float* xsrc = (inverse ? gy : gz) + g * D + j.feat0;
           float xnext = (j.last && valid) ? xsrc[0] : 0.f;
-          MF_TRACE(gt == 0, 500 + 300 * t + ji);
+          MF_TRACE(lane == 0, 5, ji);
           mbar_wait(&acc_full[t][j.region], (j.region ? fullctr1 : fullctr0) & 1);
           if (j.region) ++fullctr1; else ++fullctr0;
-          MF_TRACE(gt == 0, 300 + 300 * t + ji);
+          MF_TRACE(lane == 0, 6, ji);
           tc::fence_after_thread_sync();
           const uint32_t taddr = tmem + lane_off + (uint32_t)(t * 256);
           if (!j.last) {
@@ -708,6 +803,9 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
               float vv[32];
               tc::tmem_ld16(taddr + c00, vv);
               if (c00 + 16 < j.N) tc::tmem_ld16(taddr + c00 + 16, vv + 16);
+              float4 bb[8];  // the biases travel from shared memory while the TMEM loads are in flight
+#pragma unroll
+              for (int i = 0; i < 8; ++i) bb[i] = *reinterpret_cast<const float4*>(sb + c00 + 4 * i);
               tc::tmem_ld_wait();
 #pragma unroll
               for (int half = 0; half < 2; ++half) {
@@ -717,7 +815,7 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
                   float2 w2[8];
 #pragma unroll
                   for (int i = 0; i < 16; i += 4) {
-                    const float4 b4 = *reinterpret_cast<const float4*>(sb + c0 + i);
+                    const float4 b4 = bb[half * 4 + i / 4];
                     float2 u0 = f2_add(make_float2(v[i], v[i + 1]), make_float2(b4.x, b4.y));
                     float2 u1 = f2_add(make_float2(v[i + 2], v[i + 3]), make_float2(b4.z, b4.w));
                     w2[i / 2] = make_float2(fmaxf(u0.x, 0.f), fmaxf(u0.y, 0.f));
@@ -741,8 +839,8 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
             }
             tc::tmem_st_wait();
             tc::fence_before_thread_sync();
-            mbar_arrive(&a_ready[t]);
-            MF_TRACE(gt == 0, 400 + 300 * t + ji);
+            mbar_arrive_warp(&a_ready[t], lane);
+            MF_TRACE(lane == 0, 7, ji);
           } else {
             // last-layer chunk: splines of the chunk's features straight out of TMEM
             const unsigned long long fmask = sched ? sched[(size_t)tr * MF_MAX_FEATURES + (unit % sweeps)] : ~0ull;
@@ -767,8 +865,8 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
               }
             }
             tc::fence_before_thread_sync();
-            mbar_arrive(&acc_free[t][j.region]);
-            MF_TRACE(gt == 0, 400 + 300 * t + ji);
+            mbar_arrive_warp(&acc_free[t][j.region], lane);
+            MF_TRACE(lane == 0, 7, ji);
           }
         }
       }
@@ -776,11 +874,13 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
         if (args.ladj) static_cast<float*>(args.ladj)[g] = ladj;
         if (args.logprob) static_cast<float*>(args.logprob)[g] = lp_base + ladj;
       }
+      if (valid && inverse && bp.xmap_kind != MF_XMAP_NONE)  // output map of sample (sigmoid bridge) on the thread's own row
+        for (int f = 0; f < D; ++f) gz[g * D + f] = xmap_apply<float>(bp, gz[g * D + f], f);
     }
   }
   tc::fence_before_thread_sync();
   __syncthreads();
-  if (warp == 1) tc::tmem_dealloc(tmem, 512);
+  if (warp == kIssuerWarp) tc::tmem_dealloc(tmem, 512);
 }
 
 }  // namespace
@@ -790,11 +890,15 @@ static long long tc_sched_offset(const TcLayout& L) {  // sampling schedule afte
   return (L.bias_off + (long long)L.bias_stride * L.T * 4 + 7) / 8 * 8;
 }
 
+// zero-block table [T][kMaxJobs] uint64 after the schedule
+static long long tc_skip_offset(const TcLayout& L) { return tc_sched_offset(L) + kSchedBytes; }
+static long long tc_blob_total(const TcLayout& L) { return tc_skip_offset(L) + (long long)L.T * kMaxJobs * 8; }
+
 int flow_tc_blob_bytes(const mf_flow_desc& d, int gemm, long long* bytes) {
   TcLayout L;
   int rc = make_tc_layout(d, gemm, &L);
   if (rc != MF_OK) return rc;
-  *bytes = tc_sched_offset(L) + kSchedBytes;
+  *bytes = tc_blob_total(L);
   return MF_OK;
 }
 
@@ -813,7 +917,7 @@ int flow_tc_pack(const mf_flow_desc& d, const void* const* w, const void* const*
   TcLayout L;
   int rc = make_tc_layout(d, gemm, &L);
   if (rc != MF_OK) return rc;
-  const long long need = tc_sched_offset(L) + kSchedBytes;
+  const long long need = tc_blob_total(L);
   MF_REQUIRE(blob_bytes >= need, "blob too small: %lld < %lld bytes", blob_bytes, need);
   const int nl = d.n_hidden + 1;
   for (int t = 0; t < L.T; ++t) {
@@ -829,6 +933,10 @@ int flow_tc_pack(const mf_flow_desc& d, const void* const* w, const void* const*
                                                        (size_t)t * L.bias_stride);
     rc = post_launch("flow_tc_pack_kernel");
     if (rc != MF_OK) return rc;
+    flow_tc_skip_kernel<float><<<L.njobs, 8, 0, st>>>(
+        L, a, reinterpret_cast<unsigned long long*>((unsigned char*)blob + tc_skip_offset(L)) + (size_t)t * kMaxJobs);
+    rc = post_launch("flow_tc_skip_kernel");
+    if (rc != MF_OK) return rc;
   }
   MF_CUDA_CHECK(cudaMemsetAsync((char*)blob + tc_sched_offset(L), 0xFF, kSchedBytes, st));
   return MF_OK;
@@ -843,7 +951,7 @@ long long flow_tc_workspace_bytes(const mf_flow_desc& d, long long n, int gemm, 
 template <int NS, int NCHK, bool INV>
 static int tc_launch(const TcLayout& L, const FlowKernelArgs& a, const BaseParams& bp, unsigned grid, size_t smem, cudaStream_t st) {
   MF_CUDA_CHECK(cudaFuncSetAttribute(flow_tc_kernel<NS, NCHK, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  flow_tc_kernel<NS, NCHK, INV><<<grid, 11 * 32, smem, st>>>(L, a, bp);
+  flow_tc_kernel<NS, NCHK, INV><<<grid, kTcThreads, smem, st>>>(L, a, bp);
   return MF_OK;
 }
 template <int NS, bool INV>
@@ -866,6 +974,7 @@ int flow_tc_run(const mf_flow_desc& d, const FlowKernelArgs& a, const BaseParams
   MF_REQUIRE(a.z != nullptr, "tensor-core flow path needs the z / x output buffer (it is the working copy of x)");
   FlowKernelArgs a_run = a;
   if (a.mode == 1) a_run.sched = reinterpret_cast<const unsigned long long*>(static_cast<const char*>(a.blob) + tc_sched_offset(L));
+  a_run.skip = reinterpret_cast<const unsigned long long*>(static_cast<const char*>(a.blob) + tc_skip_offset(L));
   if (a.ctx_group > 1) {
     set_error("context grouping (ctx_group=%d) is not implemented on the tcgen05 path; use MF_GEMM_MMA_3XF16 / MF_GEMM_EXACT", a.ctx_group);
     return MF_EUNSUPPORTED;

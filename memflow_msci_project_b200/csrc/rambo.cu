@@ -26,6 +26,7 @@ namespace mf {
 namespace {
 
 constexpr int kEPB = 128;  // events per CTA (one per thread)
+__device__ __forceinline__ bool aligned16_dev(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 template <typename T>
 struct Mth;
@@ -142,6 +143,10 @@ struct RamboAux {
   double vol_scale;         // vol_coef / vol_fact
   int cuts_on;
   int perm[MF_MAX_FINAL];
+  // lab-frame get_PS (mf_rambo_get_ps_lab, inverse kernel mode 2)
+  double m_min_tot;      // boost fix-up threshold (<= 0: no fix-up)
+  void* lab_mom_cm;      // optional output: momenta boosted to the CM frame [N,n,4]
+  void* lab_boost_out;   // optional output: the boost four-vectors after the fix-up [N,4]
 };
 
 __device__ __forceinline__ double pseudo_rap_d(double px, double py, double pz) {
@@ -493,27 +498,31 @@ __device__ __forceinline__ void rambo_inverse_event(const mf_rambo_desc& d, cons
     const int j = n - 1 - jj;  // j = n-1 .. 1
     if (jj < n - 1) {
       const int i = j + 1;     // reference's 1-based loop index
-      TC u = K[j] / K[j - 1];
+      TC u = fast_div(K[j], K[j - 1]);
       const int e = n - i;
       TC rm = TC(e + 1) * ipow(u, e) - TC(e) * ipow(u, e + 1);  // :672-674
       const TIO* p = pin + 4 * (aux.perm[j - 1] ^ swz);
       TC pE = (TC)p[0], px = (TC)p[1], py = (TC)p[2], pz = (TC)p[3];
       SE += pE; Sx += px; Sy += py; Sz += pz;  // Q_{j-1}
       // boost_t(P_{j-1}, -Q_vec/Q_E) (:678, phasespace/utils.py:88-118)
-      TC bx = -(Sx / SE), by = -(Sy / SE), bz = -(Sz / SE);
+      const TC iSE = fast_div(TC(1), SE);
+      TC bx = -(Sx * iSE), by = -(Sy * iSE), bz = -(Sz * iSE);
       TC b2 = bx * bx + by * by + bz * bz;
-      TC gamma = TC(1) / M::sqrt_(TC(1) - b2);
+      TC gamma = fast_div(TC(1), M::sqrt_(TC(1) - b2));
       TC bp = px * bx + py * by + pz * bz;
-      TC gamma2 = b2 > TC(0) ? (gamma - TC(1)) / b2 : TC(0);
+      TC gamma2 = b2 > TC(0) ? fast_div(gamma - TC(1), b2) : TC(0);
       TC f = gamma2 * bp + gamma * pE;
       px += f * bx; py += f * by; pz += f * bz;
-      TC rcos = ((pz / M::sqrt_(px * px + py * py + pz * pz)) + TC(1)) / TC(2);  // :681-683
-      TC phi = M::atan_(py / px);                                                 // :687
+      TC rcos = (fast_div(pz, M::sqrt_(px * px + py * py + pz * pz)) + TC(1)) * TC(0.5);  // :681-683
+      // fp32 outputs: the angle is stored as an fp32 uniform, an fp32-accurate arctangent of the fp64 ratio is enough
+      // (|d phi| <= 1.2e-7 -> 2e-8 of the unit interval, below the fp32 rounding of r); fp64 outputs keep the fp64 atan
+      const TC ratio = fast_div(py, px);
+      TC phi = (sizeof(TIO) == 4) ? (TC)atanf((float)ratio) : M::atan_(ratio);                // :687
       const TC pi = TC(3.14159265358979323846);
       TC dphi = (py < TC(0) && px > TC(0)) ? TC(2) * pi : TC(0);
       dphi += (px < TC(0)) ? pi : TC(0);
       phi += dphi;
-      TC rphi = phi / (TC(2) * pi);
+      TC rphi = phi * TC(0.15915494309189533577);  // / (2 pi)
       // the reference keeps r in an fp32 tensor (:663): round there for the range test
       float f0 = (float)rm, f1 = (float)rcos, f2 = (float)rphi;
       r_out_of_range |= (f0 < 0.f) | (f0 > 1.f) | (f1 < 0.f) | (f1 > 1.f) | (f2 < 0.f) | (f2 > 1.f);
@@ -524,17 +533,17 @@ __device__ __forceinline__ void rambo_inverse_event(const mf_rambo_desc& d, cons
   }
   // x1, x2 -> uniforms (get_uniform_from_x1x2, phasespace/utils.py:287-309)
   TC l1 = -M::log_(x1), l2 = -M::log_(x2);
-  TC u1 = (TC(-0.5) * (l1 * l1) + (TC)d.x_q * l1) / (TC)d.x_A;
-  TC u2 = l2 / (-l1 + (TC)d.x_q);
+  TC u1 = fast_div(TC(-0.5) * (l1 * l1) + (TC)d.x_q * l1, (TC)d.x_A);
+  TC u2 = fast_div(l2, -l1 + (TC)d.x_q);
   rout[3 * n - 4] = (TIO)u1;
   rout[3 * n - 3] = (TIO)u2;
   prob_out = TC(0);
   if (want_prob) {
-    TC jac = TC(1) / ((TC)d.x_A * x1 * x2);
+    TC jac = fast_div(TC(1), (TC)d.x_A * x1 * x2);
     TC E_cm = M::sqrt_(x1 * x2) * (TC)d.sqrt_s;  // :700
-    TC w = (TC)d.vol_coef * ipow(E_cm * E_cm, n - 2) / (TC)d.vol_fact;
+    TC w = fast_div((TC)d.vol_coef * ipow(E_cm * E_cm, n - 2), (TC)d.vol_fact);
     const TC Msq = Mi[n - 2] * Mi[n - 2];
-    w *= M::sqrt_((Msq - (TC)d.last_plus_sq) * (Msq - (TC)d.last_minus_sq)) / Msq;  // 8 rho, :709-713
+    w *= fast_div(M::sqrt_((Msq - (TC)d.last_plus_sq) * (Msq - (TC)d.last_minus_sq)), Msq);  // 8 rho, :709-713
 #pragma unroll UNR
     for (int i = 0; i < NMAX - 2; ++i) {
       if (i < n - 2) {
@@ -542,14 +551,15 @@ __device__ __forceinline__ void rambo_inverse_event(const mf_rambo_desc& d, cons
         const TC Ms = Mi[i] * Mi[i];
         TC a = Ms - (Mi[i + 1] + m) * (Mi[i + 1] + m);
         TC b = Ms - (Mi[i + 1] - m) * (Mi[i + 1] - m);
-        TC rhoM = M::sqrt_(a * b) / (TC(8) * Ms);
+        // (rhoM / rhoK) * (M_{i+1} / K_{i+1}) with rhoM = sqrt(ab) / 8 Ms, rhoK = (Ks - K1^2) / 8 Ks: one division
         TC Ks = K[i] * K[i];
-        TC rhoK = (Ks - K[i + 1] * K[i + 1]) / (TC(8) * Ks);
-        w *= (rhoM / rhoK) * (Mi[i + 1] / K[i + 1]);  // :714-725
+        TC num = M::sqrt_(a * b) * Ks * Mi[i + 1];
+        TC den = Ms * (Ks - K[i + 1] * K[i + 1]) * K[i + 1];
+        w *= fast_div(num, den);  // :714-725
       }
     }
-    w *= ipow(K[0] / Mi[0], 2 * n - 4);  // :727
-    TC prob = jac / w;
+    w *= ipow(fast_div(K[0], Mi[0]), 2 * n - 4);  // :727
+    TC prob = fast_div(jac, w);
     if (d.quirks & MF_QUIRK_F32_VOLUME) {
       float Ef = (float)E_cm;
       double p = 1.0, e2 = (double)(Ef * Ef);
@@ -569,6 +579,7 @@ rambo_inverse_kernel(const __grid_constant__ mf_rambo_desc d, const __grid_const
                      long long n_events, TIO* __restrict__ g_r, TIO* __restrict__ g_prob,
                      int* __restrict__ g_flags, unsigned char* __restrict__ g_mask, int mode,
                      int use_tma, int vec_ok) {
+  using M = Mth<TC>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int n = NF ? NF : d.n_final;
   const int ndim = 3 * n - 2, mdim = 4 * n;
@@ -624,6 +635,34 @@ rambo_inverse_kernel(const __grid_constant__ mf_rambo_desc d, const __grid_const
       // unfolding_flow/utils.py:1066-1071
       const TIO* b = g_boost + 4 * e;
       TC bE = (TC)b[0], bz = (TC)b[3];
+      if (mode == 2) {
+        // memflow/unfolding_flow/unfolding_flow.py:137-148 in front of get_PS: fix an unphysical regressed boost, then
+        // move the lab-frame momenta to the CM frame with boost_tt(p, -boostVector_t(boost)) (phasespace/utils.py:36-42,
+        // :121-147).  The CM momenta go back into the tile in the I/O dtype (the reference's tensors keep the model dtype).
+        TC bx = (TC)b[1], by = (TC)b[2];
+        if (aux.m_min_tot > 0.0) {
+          const TC mm = M::sqrt_(bE * bE - bz * bz);   // NaN for a space-like boost: comparison false, like torch
+          if (mm < (TC)aux.m_min_tot) bE = M::sqrt_(bz * bz + (TC)(aux.m_min_tot * aux.m_min_tot) + TC(1e-3));
+        }
+        if (aux.lab_boost_out) {
+          TIO* bo = static_cast<TIO*>(aux.lab_boost_out) + 4 * e;
+          bo[0] = (TIO)bE; bo[1] = (TIO)bx; bo[2] = (TIO)by; bo[3] = (TIO)bz;
+        }
+        bE = (TC)(TIO)bE;   // the reference reads the fixed value back from the tensor
+        const TC ibE = fast_div(TC(1), bE);
+        const TC vx = -(bx * ibE), vy = -(by * ibE), vz = -(bz * ibE);   // -beta
+        const TC b2 = vx * vx + vy * vy + vz * vz;
+        const TC gamma = fast_div(TC(1), M::sqrt_(TC(1) - b2));
+        const TC gamma2 = b2 > TC(0) ? fast_div(gamma - TC(1), b2) : TC(0);
+        for (int k = 0; k < n; ++k) {
+          TIO* p = s_in + tid * mdim + 4 * (k ^ swz);
+          const TC pE = (TC)p[0], px = (TC)p[1], py = (TC)p[2], pz = (TC)p[3];
+          const TC bp = px * vx + py * vy + pz * vz;
+          const TC f = gamma2 * bp + gamma * pE;
+          p[0] = (TIO)(gamma * (pE + bp));
+          p[1] = (TIO)(px + f * vx); p[2] = (TIO)(py + f * vy); p[3] = (TIO)(pz + f * vz);
+        }
+      }
       x1 = (bE + bz) / (TC)d.sqrt_s;
       x2 = (bE - bz) / (TC)d.sqrt_s;
       problem = (x1 > TC(1)) | (x1 < TC(0)) | (x2 < TC(0)) | (x1 > TC(1));  // sic, :1069
@@ -654,12 +693,24 @@ rambo_inverse_kernel(const __grid_constant__ mf_rambo_desc d, const __grid_const
     __syncthreads();
     if (tid == 0) {
       bulk_s2g(g_r + first * ndim, s_out, (uint32_t)(kEPB * ndim * sizeof(TIO)));
+      if (mode == 2 && aux.lab_mom_cm)
+        bulk_s2g(static_cast<TIO*>(aux.lab_mom_cm) + first * mdim, s_in, (uint32_t)(kEPB * mdim * sizeof(TIO)));
       bulk_commit();
       bulk_wait_read0();
     }
   } else {
     __syncthreads();
     tile_store(g_r + first * ndim, s_out, tile * ndim, vec_ok != 0);
+    if (mode == 2 && aux.lab_mom_cm) {
+      TIO* dst = static_cast<TIO*>(aux.lab_mom_cm) + first * mdim;
+      if (swizzled) {   // undo the 16-byte-chunk swizzle of the staged tile
+        const float4* src = reinterpret_cast<const float4*>(s_in);
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        for (int i = tid; i < tile * 8; i += kEPB) { const int row = i >> 3, c = i & 7; d4[i] = src[row * 8 + (c ^ (row & 7))]; }
+      } else {
+        tile_store(dst, s_in, tile * mdim, vec_ok != 0 && aligned16_dev(dst));
+      }
+    }
   }
 }
 
@@ -680,6 +731,7 @@ int fill_aux(const mf_rambo_desc* d, const int32_t* perm, RamboAux* aux) {
   for (int i = 0; i + 1 < n; ++i)
     aux->dS[i] = d->tail_sum_fwd[i] - d->tail_sum_fwd[i + 1] - d->mass[i];
   aux->cuts_on = (d->pt_min_cut > 0.0 || d->delr_min_cut > 0.0 || d->rap_max_cut > 0.0) ? 1 : 0;
+  aux->m_min_tot = 0.0; aux->lab_mom_cm = nullptr; aux->lab_boost_out = nullptr;
   if (perm) {
     unsigned seen = 0;
     for (int i = 0; i < n; ++i) {
@@ -801,10 +853,12 @@ int mf_rambo_forward_f64(const mf_rambo_desc* desc, const double* d_r, int64_t n
 static int inverse_dispatch(const mf_rambo_desc* desc, const void* mom, const void* x1,
                             const void* x2, const void* boost, const int32_t* perm, int64_t N,
                             void* r, void* prob, int32_t* flags, uint8_t* mask, int mode,
-                            int io_dtype, int compute, void* stream) {
+                            int io_dtype, int compute, void* stream, double m_min_tot = 0.0,
+                            void* mom_cm = nullptr, void* boost_out = nullptr) {
   RamboAux aux;
   int rc = fill_aux(desc, perm, &aux);
   if (rc != MF_OK) return rc;
+  aux.m_min_tot = m_min_tot; aux.lab_mom_cm = mom_cm; aux.lab_boost_out = boost_out;
   if (N == 0) return MF_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (io_dtype == MF_F32 && compute == MF_COMPUTE_F64)
@@ -855,6 +909,16 @@ int mf_rambo_get_ps(const mf_rambo_desc* desc, const void* d_momenta, const void
   MF_REQUIRE(n_events >= 0, "mf_rambo_get_ps: negative event count");
   return inverse_dispatch(desc, d_momenta, nullptr, nullptr, d_boost, perm, n_events, d_ps, nullptr,
                           nullptr, d_mask, 1, io_dtype, compute, stream);
+}
+
+int mf_rambo_get_ps_lab(const mf_rambo_desc* desc, const void* d_momenta_lab, const void* d_boost,
+                        const int32_t* perm, int64_t n_events, double m_min_tot, void* d_momenta_cm,
+                        void* d_boost_fixed, void* d_ps, uint8_t* d_mask, int io_dtype, int compute, void* stream) {
+  MF_REQUIRE(desc && ((d_momenta_lab && d_boost && d_ps) || n_events == 0), "mf_rambo_get_ps_lab: null argument");
+  MF_REQUIRE(desc->n_final == 4, "mf_rambo_get_ps_lab: the reference hard-codes n = 4 (got %d)", desc->n_final);
+  MF_REQUIRE(n_events >= 0, "mf_rambo_get_ps_lab: negative event count");
+  return inverse_dispatch(desc, d_momenta_lab, nullptr, nullptr, d_boost, perm, n_events, d_ps, nullptr,
+                          nullptr, d_mask, 2, io_dtype, compute, stream, m_min_tot, d_momenta_cm, d_boost_fixed);
 }
 
 }  // extern "C"

@@ -283,6 +283,99 @@ __global__ void spline_probe_kernel(float* __restrict__ out, int iters, int vari
 }
 
 
+// TMEM bandwidth probe: warps 0-3 (one per lane quarter) run `iters` passes over a 128-column fp32 accumulator like the
+// hidden-layer epilogue of the flow kernel.  variant bits: 1 = tcgen05.ld of the 128 columns, 2 = tcgen05.st of the two
+// 64-column operand planes, 4 = the bias / ReLU / fp16 hi-lo split arithmetic in between, 8 = warp 4 issues TS-form MMAs
+// (M=128, N=128, K=16) back to back into the OTHER half of TMEM during the measurement.
+// out[w] = cycles per pass seen by warp w, out[8] = cycles per MMA of warp 4.
+__global__ void __launch_bounds__(160, 1) tmem_bw_probe_kernel(float* __restrict__ out, int iters, int variant) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ volatile int stop_flag;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 32768 / 4; i += 160) reinterpret_cast<uint32_t*>(smem)[i] = 0x34003400u;
+  if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_mbar_init(); stop_flag = 0; }
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
+  fence_proxy_async_smem();
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  const uint32_t tmem = tmem_base_s;
+  if (warp < 4) {
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+    float acc = 0.f;
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      for (int c00 = 0; c00 < 128; c00 += 32) {
+        float vv[32];
+        if (variant & 1) {
+          tc::tmem_ld16(taddr + c00, vv);
+          tc::tmem_ld16(taddr + c00 + 16, vv + 16);
+          tc::tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) vv[i] = acc + (float)(i + c00);
+        }
+        uint32_t hi[16], lo[16];
+        if (variant & 4) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float a = fmaxf(vv[2 * i] + 0.25f, 0.f), b = fmaxf(vv[2 * i + 1] - 0.125f, 0.f);
+            tc::split_f16(a, b, hi[i], lo[i]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { hi[i] = __float_as_uint(vv[2 * i]); lo[i] = __float_as_uint(vv[2 * i + 1]); }
+        }
+        if (variant & 2) {
+          tc::tmem_st8(taddr + 128 + c00 / 2, hi);
+          tc::tmem_st8(taddr + 128 + c00 / 2 + 8, hi + 8);
+          tc::tmem_st8(taddr + 192 + c00 / 2, lo);
+          tc::tmem_st8(taddr + 192 + c00 / 2 + 8, lo + 8);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc += __uint_as_float(hi[i] ^ lo[i]) * 1e-30f;
+        }
+      }
+      if (variant & 2) tc::tmem_st_wait();
+    }
+    const long long t1 = clock64();
+    if (lane == 0) out[warp] = (float)(t1 - t0) / (float)iters;
+    if (acc == 12345.f) out[15] = acc;
+    __syncwarp();
+    if (warp == 0 && lane == 0) stop_flag = 1;
+  } else if (variant & 8) {
+    const uint32_t idesc = tc::make_idesc_f16(0, 128, 128);
+    const uint32_t b_s = smem_u32(smem);
+    const uint32_t d_tmem = tmem + 256, a_tmem = d_tmem + 128;
+    long long n_mma = 0;
+    const long long t0 = clock64();
+    while (!stop_flag) {
+      if (tc::elect_one()) {
+        const uint64_t db = tc::make_smem_desc(b_s);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          tc::mma_f16_ts(d_tmem, a_tmem + (ks & 7) * 8u, db + (uint64_t)((ks & 3) * 2), idesc, 1u);
+          tc::mma_f16_ts(d_tmem, a_tmem + (ks & 7) * 8u, db + (uint64_t)((ks & 3) * 2), idesc, 1u);
+          tc::mma_f16_ts(d_tmem, a_tmem + 64u + (ks & 7) * 8u, db + (uint64_t)((ks & 3) * 2), idesc, 1u);
+        }
+      }
+      __syncwarp();
+      n_mma += 24;
+    }
+    if (tc::elect_one()) tc::mma_commit(&bar[0]);
+    __syncwarp();
+    mbar_wait(&bar[0], 0);
+    const long long t1 = clock64();
+    if (lane == 0) { out[8] = (float)(t1 - t0) / (float)n_mma; out[9] = (float)n_mma; }
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+
 // Legacy warp-level MMA rate probe: every warp issues `iters` x 8 independent mma.sync.m16n8k8 TF32 (fp32 accumulate).
 // out[0] = cycles per MMA per scheduler.  f16 = 1: m16n8k16 fp16 instead.
 __global__ void mma_sync_probe_kernel(float* __restrict__ out, int iters, int f16) {
@@ -329,6 +422,12 @@ extern "C" int mf_tc_probe_gemm(const float* d_a, const float* d_w, float* d_out
   MF_REQUIRE(n >= 16 && n % 16 == 0 && n <= 256, "mf_tc_probe_gemm: N=%d must be a multiple of 16 in 16..256", n);
   int all_sms = 0;
   if (mode >= 1000) { all_sms = 1; mode -= 1000; }
+  if (mode >= 400) {  // TMEM bandwidth: mode = 400 + variant bits (1 ld, 2 st, 4 split arithmetic, 8 concurrent MMAs); k = passes
+    MF_REQUIRE(d_out && mode - 400 < 16 && k >= 1, "mf_tc_probe_gemm: bad TMEM probe mode");
+    MF_CUDA_CHECK(cudaFuncSetAttribute(tmem_bw_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768));
+    tmem_bw_probe_kernel<<<all_sms ? 148 : 1, 160, 32768, static_cast<cudaStream_t>(stream)>>>(d_out, k, mode - 400);
+    return post_launch("tmem_bw_probe_kernel");
+  }
   if (mode >= 300) {  // legacy mma.sync rate: mode = 300 + warps per scheduler; k = iterations
     const int wps = (mode - 300) % 10, f16 = (mode - 300) / 10;
     MF_REQUIRE(d_out && wps >= 1 && wps <= 8 && f16 <= 1, "mf_tc_probe_gemm: bad mma.sync probe mode");

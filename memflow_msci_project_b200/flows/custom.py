@@ -2,6 +2,7 @@
 
   NCSF_gaussian         memflow/transfer_flow/periodicNSF_gaussian.py:24-58
   Custom_spline_flow_ps memflow/unfolding_flow/custom_spline_flow_ps.py:37-81
+  Custom_spline_flow_eta memflow/unfolding_flow/custom_spline_flow_eta.py:15-57
   UniformNCSF / UniformNSF / PSNSF   memflow/ttH/transfer_flow/custom_flows.py:58-127
                                      (memflow/models/custom_flows.py has the same classes)
 """
@@ -29,6 +30,16 @@ class Custom_spline_flow_ps(MAF):
                          **kwargs)
         self.base = Unconditional(DiagNormal, mean_gaussian * torch.ones((features,)),
                                   std_gaussian * torch.ones((features,)), buffer=True)
+
+
+class Custom_spline_flow_eta(MAF):
+    """RQS(bound=3.5) univariates (``RQSTransform_custom``, custom_spline_flow_eta.py:15-21) on MAF's default
+    DiagNormal(0, 1) base -- the pseudorapidity flow."""
+
+    def __init__(self, features, context=0, bins=8, **kwargs):
+        kwargs.pop("univariate", None)
+        kwargs.pop("bound", None)
+        super().__init__(features=features, context=context, bins=bins, univariate=UNIV_RQS, bound=3.5, **kwargs)
 
 
 class UniformNCSF(MAF):

@@ -27,6 +27,9 @@ MF_MAX_FEATURES = 64
 UNIV_RQS, UNIV_CIRCULAR_RQS, UNIV_PS_RQS = 0, 1, 2
 BASE_DIAG_NORMAL, BASE_BOX_UNIFORM = 0, 1
 GEMM_EXACT, GEMM_TC_3XF16, GEMM_TC_BF16, GEMM_MMA_3XF16 = 0, 1, 2, 3
+# tensor paths pack the hidden units sorted by autoregressive degree (block-triangular masked weights: the kernels skip
+# the all-zero blocks); the function computed is unchanged
+SORTED_GEMMS = (GEMM_TC_3XF16, GEMM_TC_BF16, GEMM_MMA_3XF16)
 GEMM_AUTO = -1  # resolved per call: tcgen05 3xFP16 when the shape fits, mma.sync 3xFP16 up to width 512, else exact
 
 
@@ -167,6 +170,35 @@ class SimpleAffineTransform(nn.Module):
 
 
 # ------------------------------------------------------------------------------------------------
+class SigmoidAffine:
+    """``torch.sigmoid(x * scale + shift)`` applied to the samples INSIDE the sampling kernel (a19):
+    ``flow(c).rsample((1,), post=SigmoidAffine(scale_ps, mean_ps))`` replaces the reference's
+    ``torch.sigmoid(flow(c).rsample((1,)) * scale_ps + mean_ps)`` (scripts/run_model_labframe_sampling.py:426-427)."""
+
+    def __init__(self, scale=1.0, shift=0.0):
+        self.scale, self.shift = scale, shift
+
+    def torch(self, x):
+        return torch.sigmoid(x * torch.as_tensor(self.scale).to(x) + torch.as_tensor(self.shift).to(x))
+
+    def xmap(self, features):
+        return _cabi.make_xmap(_cabi.MF_XMAP_SIGMOID_AFFINE, self.scale, self.shift, features)
+
+
+class LogitAffine:
+    """``(torch.logit(x, eps) - mean) / std`` applied to the data INSIDE the log_prob kernel (a19): the bridge of
+    memflow/unfolding_flow/unfolding_flow.py:170-171.  Like there it is a data transformation (no ladj term)."""
+
+    def __init__(self, mean=0.0, std=1.0, eps=5e-5):
+        self.mean, self.std, self.eps = mean, std, eps
+
+    def torch(self, x):
+        return (torch.logit(x, eps=self.eps) - torch.as_tensor(self.mean).to(x)) / torch.as_tensor(self.std).to(x)
+
+    def xmap(self, features):
+        return _cabi.make_xmap(_cabi.MF_XMAP_LOGIT_AFFINE, self.std, self.mean, features, eps=self.eps)
+
+
 class _Transform:
     """What ``flow(c).transform`` returns: callable forward map with ``.inv`` and ``.call_and_ladj``."""
 
@@ -243,14 +275,18 @@ class NormalizingFlow:
         cb = c.expand(*batch, c.shape[-1]).reshape(-1, c.shape[-1])
         return xb, cb, batch
 
-    def _forward(self, x, want_logprob, debug=False):
+    def _forward(self, x, want_logprob, debug=False, xmap=None):
         m = self._m
         pre, core, post = self._split()
         _cabi.require_cuda(x, "x")
         if torch.is_grad_enabled() and (x.requires_grad or (self._c is not None and self._c.requires_grad)
                                         or any(p.requires_grad for p in m.parameters())):
             from ._autograd import flow_log_prob_autograd
+            if xmap is not None:   # under autograd the bridge is differentiable torch in front of the fused kernel
+                x = xmap.torch(x)
             return flow_log_prob_autograd(self, x, want_logprob)
+        if xmap is not None and pre:
+            x, xmap = xmap.torch(x), None   # element-wise prefix transforms come after the bridge: apply it eagerly
         dtype = m.compute_dtype()
         ladj_pre = None
         x = x.to(dtype)
@@ -272,7 +308,8 @@ class NormalizingFlow:
         if debug:
             bins = torch.empty((len(core), N, D), dtype=torch.int8, device=xb.device)
             inside = torch.empty((len(core), N, D), dtype=torch.uint8, device=xb.device)
-        _cabi.flow_log_prob(desc, blob, xb, cb, logprob, z, ladj, bins, inside, gemm)
+        _cabi.flow_log_prob(desc, blob, xb, cb, logprob, z, ladj, bins, inside, gemm,
+                            xmap=xmap.xmap(D) if xmap is not None else None)
         z = z.reshape(*batch, D)
         ladj = ladj.reshape(batch)
         if ladj_pre is not None:
@@ -290,7 +327,7 @@ class NormalizingFlow:
             return z, ladj, logprob, bins.reshape(len(core), *batch, D), inside.reshape(len(core), *batch, D).bool()
         return z, ladj, logprob
 
-    def _inverse(self, z, noise_is_base_sample=True):
+    def _inverse(self, z, noise_is_base_sample=True, xmap=None):
         """x = T^-1(z) for z already distributed like the base."""
         m = self._m
         pre, core, post = self._split()
@@ -306,32 +343,38 @@ class NormalizingFlow:
         desc, blob = m.packed(zb.device, dtype, identity_base=True, gemm=gemm)
         desc = self._with_group(desc)
         x = torch.empty_like(zb)
-        _cabi.flow_sample(desc, blob, zb, cb, x, gemm)
+        fuse = xmap is not None and not pre
+        _cabi.flow_sample(desc, blob, zb, cb, x, gemm, xmap=xmap.xmap(m.features) if fuse else None)
         x = x.reshape(*batch, m.features)
         for t in reversed(pre):
             x = t.inv(x)
+        if xmap is not None and not fuse:
+            x = xmap.torch(x)
         return x
 
     # -- distribution API
-    def log_prob(self, x):
-        return self._forward(x, want_logprob=True)[2]
+    def log_prob(self, x, pre=None):
+        """``pre``: optional LogitAffine bridge evaluated inside the kernel on the data (extension, a19)."""
+        return self._forward(x, want_logprob=True, xmap=pre)[2]
 
-    def rsample(self, shape=()):
+    def rsample(self, shape=(), post=None):
+        """``post``: optional SigmoidAffine bridge evaluated inside the kernel on the samples (extension, a19)."""
         base = self.base
         z = base.rsample(torch.Size(shape)) if base.has_rsample else base.sample(torch.Size(shape))
         if torch.is_grad_enabled() and (z.requires_grad or (self._c is not None and self._c.requires_grad)
                                         or any(p.requires_grad for p in self._m.parameters())):
             from ._autograd import flow_rsample_autograd
-            return flow_rsample_autograd(self, z)
-        return self._inverse(z)
+            x = flow_rsample_autograd(self, z)
+            return post.torch(x) if post is not None else x
+        return self._inverse(z, xmap=post)
 
-    def sample(self, shape=()):
+    def sample(self, shape=(), post=None):
         with torch.no_grad():
             base = self.base
             z = base.sample(torch.Size(shape))
-            return self._inverse(z)
+            return self._inverse(z, xmap=post)
 
-    def sample_from_noise(self, noise):
+    def sample_from_noise(self, noise, post=None):
         """Deterministic sampling from caller-supplied noise [..., D] (standard normals for a
         DiagNormal base, uniforms in [0,1) for BoxUniform): the identical-noise parity protocol."""
         m = self._m
@@ -339,7 +382,7 @@ class NormalizingFlow:
         a, b = a.to(noise), b.to(noise)
         z = a + b * noise if m.base_kind() == BASE_DIAG_NORMAL else a + (b - a) * noise
         with torch.no_grad():
-            return self._inverse(z)
+            return self._inverse(z, xmap=post)
 
     def log_prob_debug(self, x):
         """(log_prob, z, ladj, bin indices [T,...,D] int8, in-range masks [T,...,D] bool)."""
@@ -516,7 +559,7 @@ class MAF(nn.Module):
             ws = [p.detach().to(dtype).contiguous() for p in params[0::3]]
             bs = [p.detach().to(dtype).contiguous() for p in params[1::3]]
             ms = [p.detach().to(torch.uint8).contiguous() for p in params[2::3]]
-            if gemm == GEMM_MMA_3XF16:
+            if gemm in SORTED_GEMMS:
                 ws, bs, ms = _sort_hidden_units(ws, bs, ms, len(core))
             nbytes = _cabi.flow_blob_bytes(desc, dtype, gemm)
             blob = torch.empty(nbytes, dtype=torch.uint8, device=device)
@@ -541,8 +584,9 @@ def _sort_hidden_units(ws, bs, ms, n_transforms):
 
     The order of hidden units is free (rows of W_l, b_l and the matching columns of W_{l+1} move together; the
     function computed is the same up to the summation order inside a dot product).  zuko assigns autoregressive
-    degrees round-robin; sorted by degree the masked weight matrices become block-triangular, and the warp-level MMA
-    kernel stops streaming a 128-column block at its last nonzero weight row (flow_mma_klimit_kernel)."""
+    degrees round-robin; sorted by degree the masked weight matrices become block-triangular: the warp-level MMA
+    kernel stops streaming a 128-column block at its last nonzero weight row (flow_mma_klimit_kernel) and the tcgen05
+    kernel issues every k-step only for the accumulator columns that can be nonzero (flow_tc_skip_kernel)."""
     nl = len(ws) // n_transforms
     ws, bs, ms = list(ws), list(bs), list(ms)
     for t in range(n_transforms):

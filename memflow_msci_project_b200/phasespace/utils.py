@@ -106,19 +106,22 @@ def uniform_distr(r, minv, maxv):
 
 
 def get_x1x2_from_uniform(unif, final_state_mass, E_cm):
-    """Uniform pair -> (x1, x2, weight) (:260-284); kept in torch for callers outside the kernels."""
+    """Uniform pair -> (x1, x2, weight) (:260-284); kept in torch for callers outside the kernels.  Same order of
+    operations as the reference (its constants q, A take the dtype of ``final_state_mass``, an fp32 tensor in PhaseSpace)."""
+    m = -1
     q = -torch.log((final_state_mass / E_cm) ** 2)
-    A = 0.5 * q ** 2
-    l1 = q * (1 - torch.sqrt(1 - unif[:, 0]))
-    l2 = (q - l1) * unif[:, 1]
+    A = (m / 2) * q ** 2 + q ** 2
+    l1 = (-q / A + torch.sqrt((-q / A) ** 2 + 2 * m * unif[:, 0] / A)) / (m / A)
+    l2 = (m * l1 + q) * unif[:, 1]
     x1, x2 = torch.exp(-l1), torch.exp(-l2)
-    return x1, x2, A * x1 * x2
+    return x1, x2, 1 / (1 / (A * x1 * x2))
 
 
 def get_uniform_from_x1x2(x1, x2, final_state_mass, E_cm):
     """(x1, x2) -> uniform pair and its Jacobian (:287-309)."""
+    m = -1
     q = -torch.log((final_state_mass / E_cm) ** 2)
-    A = 0.5 * q ** 2
+    A = (m / 2) * q ** 2 + q ** 2
     l1, l2 = -torch.log(x1), -torch.log(x2)
-    u = torch.stack(((-0.5 * l1 ** 2 + q * l1) / A, l2 / (q - l1)), dim=1)
+    u = torch.cat(((((m / 2) * l1 ** 2 + q * l1) / A).unsqueeze(1), (l2 / (m * l1 + q)).unsqueeze(1)), axis=1)
     return u, 1 / (A * x1 * x2)

@@ -53,6 +53,8 @@ CONFIGS = {
                                base=flows.DiagNormal, base_args=[torch.zeros(3), 0.35 * torch.ones(3)],
                                univariate_kwargs={"bound": 1.1}, passes=2)),
     "NCSF": (flows.NCSF_gaussian, dict(features=2, context=8, bins=8, transforms=3, hidden_features=[64] * 2)),
+    # memflow/unfolding_flow/custom_spline_flow_eta.py:37-57 (RQS bound 3.5, DiagNormal(0,1) base)
+    "eta": (flows.Custom_spline_flow_eta, dict(features=2, context=6, bins=10, transforms=3, hidden_features=[64] * 2)),
     "UniformNCSF": (flows.UniformNCSF, dict(features=1, context=5, bins=10, bound=3.14159, transforms=2,
                                             hidden_features=[32] * 2)),
     "PSNSF": (flows.PSNSF, dict(features=2, context=4, bins=12, transforms=2, hidden_features=[48] * 2)),
@@ -684,10 +686,44 @@ def test_sample_schedule_equals_literal_sweeps(cuda, name, gemm, dtype):
     ws = [p[0].detach().to(dtype).contiguous() for p in params]
     bs = [p[1].detach().to(dtype).contiguous() for p in params]
     ms = [p[2].detach().to(torch.uint8).contiguous() for p in params]
-    if gemm == flows.modules.GEMM_MMA_3XF16:   # the host mirror packs this mode with hidden units sorted by degree
+    if gemm in flows.modules.SORTED_GEMMS:   # the host mirror packs the tensor modes with hidden units sorted by degree
         ws, bs, ms = flows.modules._sort_hidden_units(ws, bs, ms, len(flow.core_transforms()))
     blob2 = torch.empty_like(blob)
     _cabi.flow_pack_weights(desc, ws, bs, ms, dtype, gemm, blob2)  # schedule = all chunks, all sweeps
     x2 = torch.empty_like(noise)
     _cabi.flow_sample(desc, blob2, noise.contiguous(), c.contiguous(), x2, gemm)
     assert torch.equal(xs, x2)
+
+
+# ------------------------------------------------------------------------------------------------
+# a19: the logit / sigmoid bridge fused into the kernels' x load / store == the reference's torch composition
+@pytest.mark.parametrize("name,gemm,dtype", [("TF-B", flows.modules.GEMM_TC_3XF16, torch.float32), ("UF", flows.modules.GEMM_MMA_3XF16, torch.float32),
+                                             ("TF-B", flows.modules.GEMM_EXACT, torch.float32), ("UF", flows.modules.GEMM_EXACT, torch.float64)])
+def test_fused_sigmoid_logit_bridges(cuda, name, gemm, dtype):
+    flow = build(name, cuda, dtype, mode="bias")
+    flow.gemm = gemm
+    D = flow.features
+    N = 1537
+    _, c = inputs(flow, N, 9, cuda, dtype)
+    g = torch.Generator().manual_seed(4)
+    noise = torch.randn(N, D, generator=g).to(cuda, dtype)
+    scale = (0.5 + torch.rand(D, generator=g)).to(cuda, dtype)
+    mean = (0.3 * torch.randn(D, generator=g)).to(cuda, dtype)
+    tol = 2e-6 if dtype == torch.float32 else 1e-12
+    # scripts/run_model_labframe_sampling.py:426-427: torch.sigmoid(flow_samples * scale_ps + mean_ps)
+    ref = torch.sigmoid(flow(c).sample_from_noise(noise) * scale + mean)
+    fused = flow(c).sample_from_noise(noise, post=flows.SigmoidAffine(scale, mean))
+    assert (fused - ref).abs().max().item() < tol
+    assert (fused > 0).all() and (fused < 1).all()
+    # memflow/unfolding_flow/unfolding_flow.py:170-171: (torch.logit(ps, eps=5e-5) - mean) / std, then the flow
+    u = torch.rand(N, D, generator=g).to(cuda, dtype)
+    u[:7] = 0.0
+    u[7:13] = 1.0                                  # the eps clamp of torch.logit
+    std = (0.8 + torch.rand(D, generator=g)).to(cuda, dtype)
+    with torch.no_grad():
+        ref_lp = flow(c).log_prob((torch.logit(u, eps=5e-5) - mean) / std)
+        fused_lp = flow(c).log_prob(u, pre=flows.LogitAffine(mean, std, eps=5e-5))
+    fin = torch.isfinite(ref_lp)
+    assert torch.equal(torch.isfinite(fused_lp), fin)
+    err = ((fused_lp[fin] - ref_lp[fin]).abs() / ref_lp[fin].abs().clamp_min(1.0)).max().item()
+    assert err < (5e-5 if dtype == torch.float32 else 1e-10), err   # fp32: logit of the kernel vs torch differ by rounding, amplified by the flow

