@@ -27,7 +27,7 @@
 // accuracy (measured 4e-7 of sum|terms|, tests/test_tc_probe_gpu.py).  MF_GEMM_TC_BF16: single bf16 MMA.
 //
 // Supported shapes (others are served by flow_mma.cu / flow.cu): roundup(C,8) + D <= 128, every hidden width <= 128,
-// 3 * roundup(K, 8) <= 128 (K <= 40), soft clip enabled (slope > 0), ctx_group = 1.
+// 3 * roundup(K, 8) <= 128 (K <= 40), soft clip enabled (slope > 0).
 #include <algorithm>
 
 #include "flow_common.cuh"
@@ -60,7 +60,8 @@ constexpr int kMaxJobs = 40;
 constexpr uint32_t kWPartBytes = 128 * 128;     // one [<=128 rows x 64] 16-bit weight K-block
 constexpr uint32_t kKBlockBytes = 128 * 128;    // one [128 x 64] 16-bit SWIZZLE_128B K-block of the layer-0 operand
 constexpr uint32_t kTailBytes = 128 * 32;       // one [128 x 16] 16-bit SWIZZLE_32B k-step of the layer-0 operand
-constexpr size_t kStaticSmem = 10240;           // barriers, per-warp bias slots (static __shared__), alignment slack
+constexpr size_t kStaticSmem = 10240;
+constexpr int kPktWords = 40;                   // 32-bit words of one job packet (struct JobPkt)           // barriers, per-warp bias slots (static __shared__), alignment slack
 
 struct TcJob {
   int N;        // MMA N (multiple of 16, <= 128)
@@ -90,6 +91,7 @@ struct TcLayout {
   int in0_tail;          // ... followed by this many single k-steps in SWIZZLE_32B blocks
   int in0_plane_bytes;   // bytes of one operand plane of one tile
   int stages;            // weight ring depth
+  int pkt_table;         // 1: the job packets of all (transform, job) pairs are prepared once per CTA in shared memory
   int fpc;               // features per last-layer chunk
   int nregions;          // 2: last-layer chunks alternate between the accumulator halves
   long long t_stride;    // bytes per transform (weights)
@@ -138,10 +140,7 @@ int make_tc_layout(const mf_flow_desc& d, int gemm, TcLayout* L) {
   L->in0_full = L->in0_ksteps / 4;
   L->in0_tail = L->in0_ksteps % 4;
   L->in0_plane_bytes = L->in0_full * (int)kKBlockBytes + L->in0_tail * (int)kTailBytes;
-  {
-    const size_t avail = 232448 - kStaticSmem - (size_t)2 * parts * L->in0_plane_bytes;
-    L->stages = (int)std::min<size_t>(kMaxStages, avail / ((size_t)parts * kWPartBytes));
-  }
+  L->stages = 0;  // fixed below, once the number of jobs (packet table size) is known
   // features per last-layer chunk: as many as fit the 128 accumulator columns; when that takes more than one chunk
   // and a feature fits 64 columns, chunks of <= 64 columns alternate between the two accumulator halves instead
   int fpc = std::max(1, 128 / L->PFt);
@@ -165,6 +164,16 @@ int make_tc_layout(const mf_flow_desc& d, int gemm, TcLayout* L) {
     j.b_off = boff; boff += j.N;
   }
   L->njobs = nj;
+  {
+    // shared memory: layer-0 operands | weight ring | job-packet table [T][njobs] (when it fits next to >= 4 stages)
+    const size_t avail = 232448 - kStaticSmem - (size_t)2 * parts * L->in0_plane_bytes;
+    const size_t stage_bytes = (size_t)parts * kWPartBytes, table = (size_t)d.transforms * nj * kPktWords * 4;
+    int st = (int)std::min<size_t>(kMaxStages, avail / stage_bytes);
+    L->pkt_table = 0;
+    if (st >= 2 && avail - (size_t)st * stage_bytes >= table) L->pkt_table = 1;
+    else if (st > 4 && avail - (size_t)(st - 1) * stage_bytes >= table) { --st; L->pkt_table = 1; }
+    L->stages = st;
+  }
   L->t_stride = woff;
   L->bias_off = woff * d.transforms;
   L->bias_stride = boff;
@@ -280,12 +289,9 @@ __device__ __forceinline__ void mbar_poll(uint64_t* bar, uint32_t parity) {
         : "memory");
   }
 }
-// one arrival per WARP: every lane has finished (and fenced) its part, the warp converges, one lane arrives
+// arrival of every thread of an epilogue warp (barrier count 128)
 __device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar, int lane) {
-  __syncwarp();
-  if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  (void)lane;  // every thread arrives (count 128): measured 1 % faster than one elected arrival per warp behind a __syncwarp
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
@@ -359,88 +365,107 @@ __device__ __forceinline__ void split_f16_pair(float2 v, uint32_t& hi, uint32_t&
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-// tcgen05.mma under a (uniform) enable predicate: the tail k-steps of a job are switched off without branches
-__device__ __forceinline__ void mma_ts_p(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate,
-                                         uint32_t enable) {
+// tcgen05.mma under a (uniform) enable predicate: the tail k-steps of a job are switched off without branches.
+// Shared-memory descriptors travel as (low word, high word): only the 14-bit start-address field of the LOW word
+// changes from MMA to MMA and it cannot carry (shared-memory addresses are < 2^18 bytes = 2^14 sixteen-byte units), so
+// all per-MMA address arithmetic is 32-bit -- with 64-bit descriptors the compiler emitted ~300 carry-propagating
+// instructions per job in front of the first MMA (~900 cycles of an idle tensor pipe per job, per-warp trace r2h).
+__device__ __forceinline__ void mma_ts_p(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                         uint32_t accumulate, uint32_t enable) {
   asm volatile(
       "{\n"
       ".reg .pred p, q;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "setp.ne.b32 q, %5, 0;\n"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      ".reg .b64 db;\n"
+      "mov.b64 db, {%2, %3};\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "setp.ne.b32 q, %6, 0;\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n"
       "}\n" ::"r"(tmem_d),
-      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(enable)
+      "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(enable)
       : "memory");
 }
-__device__ __forceinline__ void mma_ss_p(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate,
-                                         uint32_t enable) {
+__device__ __forceinline__ void mma_ss_p(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                         uint32_t idesc, uint32_t accumulate, uint32_t enable) {
   asm volatile(
       "{\n"
       ".reg .pred p, q;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "setp.ne.b32 q, %5, 0;\n"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      ".reg .b64 da, db;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "setp.ne.b32 q, %7, 0;\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
       "}\n" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(enable)
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(enable)
       : "memory");
 }
+__device__ __forceinline__ uint32_t desc_lo(uint64_t d) { return (uint32_t)d; }
+__device__ __forceinline__ uint32_t desc_hi(uint64_t d) { return (uint32_t)(d >> 32); }
+
+// Everything the MMA batch of one job needs that does not depend on the tile slot, prepared ONE JOB AHEAD by the
+// issuer (while the previous job's MMAs execute): the per-job scalar work (parameter-bank loads, zero-block word,
+// per-k-step operand offsets) is ~400 dependent integer instructions = ~1500 cycles of a single warp, which used to sit
+// between "dependencies met" and "first MMA issued" of every job (per-warp traces profiles/trace_flow_tc_r2h.txt, r2k).
+struct JobPkt {
+  uint32_t kd[8];   // accumulator column offset of k-step ks (its leading all-zero weight rows, flow_tc_skip_kernel)
+  uint32_t kb[8];   // weight descriptor offset of k-step ks inside its K-block (16-byte units): rows skipped + k offset
+  uint32_t ki[8];   // instruction descriptor of k-step ks (N reduced by the skipped columns)
+  uint32_t ka[8];   // layer 0: A descriptor offset of k-step ks (16-byte units); bit 31: SWIZZLE_32B tail k-step
+  uint32_t en;      // bit ks: k-step ks is issued (inside K and not an all-zero weight block)
+  int N, last, reg, nst;
+  uint32_t col;     // first accumulator column
+  int ji, pad;      // 40 words = 160 bytes: one entry of the shared-memory packet table [transform][job]
+};
+static_assert(sizeof(JobPkt) == kPktWords * 4, "JobPkt layout");
 
 // One job of one tile slot, issued by ONE thread as a single straight-line batch (up to 8 k-steps = 2 weight K-blocks,
-// 3 MMAs per k-step in the 3xFP16 mode): everything the MMAs need is computed before the first one is issued, so the
-// tensor pipe is fed back to back (measured: bookkeeping between the K-blocks of a job used to cost ~500 cycles of an
-// idle pipe per K-block -- an MMA "cost" 85-105 cycles whatever its N was).
+// 3 MMAs per k-step in the 3xFP16 mode), so the tensor pipe is fed back to back (bookkeeping between the K-blocks of a
+// job used to cost ~500 cycles of an idle pipe per K-block).
 //   hidden layers / last-layer chunks: A operand planes in TMEM (hi at a_tmem, lo 64 columns further)
-// skipw: zero-block word of the job (flow_tc_skip_kernel): k-step ks only produces accumulator columns >= 16 * byte ks
 template <int NSPLIT>
-__device__ __forceinline__ void issue_job_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t w_base0, uint32_t w_base1, uint32_t idesc,
-                                             int ksteps, int N, unsigned long long skipw, uint64_t* empty0, uint64_t* empty1,
-                                             uint64_t* full) {
-  const uint32_t part_bytes = (uint32_t)N * 128u;  // [hi][lo] planes of a K-block are dense in the stage
-  const uint64_t b0h = tc::make_smem_desc(w_base0), b0l = tc::make_smem_desc(w_base0 + part_bytes);
-  const uint64_t b1h = tc::make_smem_desc(w_base1), b1l = tc::make_smem_desc(w_base1 + part_bytes);
+__device__ __forceinline__ void issue_job_ts(const JobPkt& q, uint32_t d_tmem, uint32_t a_tmem, uint32_t w_base0, uint32_t w_base1,
+                                             uint64_t* empty0, uint64_t* empty1, uint64_t* full) {
+  const uint32_t part16 = (uint32_t)q.N * 8u;  // [hi][lo] planes of a K-block are dense in the stage (16-byte units)
+  const uint64_t d0 = tc::make_smem_desc(w_base0), d1 = tc::make_smem_desc(w_base1);
+  const uint32_t bhi = desc_hi(d0), b0 = desc_lo(d0), b1 = desc_lo(d1);
 #pragma unroll
   for (int ks = 0; ks < 8; ++ks) {
-    const uint32_t n0 = ((uint32_t)(skipw >> (8 * ks)) & 0xFFu) << 4;  // leading all-zero weight rows of this k-step
-    const uint32_t en = (ks < ksteps && (int)n0 < N) ? 1u : 0u;
-    const uint32_t idk = idesc - ((n0 >> 3) << 17);                    // N - n0 columns
-    const uint32_t d = d_tmem + n0;
-    const uint64_t roff = (uint64_t)(n0 * 8u) + (uint64_t)((ks & 3) * 2);  // 128-byte weight rows, 32-byte k-steps (16-byte units)
-    const uint64_t bh = (ks < 4 ? b0h : b1h) + roff, bl = (ks < 4 ? b0l : b1l) + roff;
+    const uint32_t en = (q.en >> ks) & 1u;
+    const uint32_t d = d_tmem + q.kd[ks];
+    const uint32_t bh = (ks < 4 ? b0 : b1) + q.kb[ks], bl = bh + part16;
     const uint32_t a = a_tmem + (uint32_t)ks * 8u;
-    mma_ts_p(d, a, bh, idk, ks ? 1u : 0u, en);
+    mma_ts_p(d, a, bh, bhi, q.ki[ks], ks ? 1u : 0u, en);
     if (NSPLIT == 3) {
-      mma_ts_p(d, a, bl, idk, 1u, en);
-      mma_ts_p(d, a + 64u, bh, idk, 1u, en);
+      mma_ts_p(d, a, bl, bhi, q.ki[ks], 1u, en);
+      mma_ts_p(d, a + 64u, bh, bhi, q.ki[ks], 1u, en);
     }
     if (ks == 3 && empty0) tc::mma_commit(empty0);  // first stage consumed by both slots
   }
   if (empty1) tc::mma_commit(empty1);
   tc::mma_commit(full);
 }
-//   layer 0: (ctx | x) operand planes in shared memory: `nfull` 64-wide SWIZZLE_128B K-blocks, then single k-steps in
-//   SWIZZLE_32B blocks (a_hi / a_lo: plane bases, tail_off: byte offset of the first tail k-step inside a plane)
+//   layer 0: (ctx | x) operand planes in shared memory (a_hi / a_lo: plane bases): 64-wide SWIZZLE_128B K-blocks, then
+//   single k-steps in SWIZZLE_32B blocks; the offsets come prepared in q.ka
 template <int NSPLIT>
-__device__ __forceinline__ void issue_job_ss(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, int nfull, uint32_t tail_off,
-                                             uint32_t w_base0, uint32_t w_base1, uint32_t idesc, int ksteps, int N,
-                                             uint64_t* empty0, uint64_t* empty1, uint64_t* full) {
-  const uint32_t part_bytes = (uint32_t)N * 128u;
-  const uint64_t b0h = tc::make_smem_desc(w_base0), b0l = tc::make_smem_desc(w_base0 + part_bytes);
-  const uint64_t b1h = tc::make_smem_desc(w_base1), b1l = tc::make_smem_desc(w_base1 + part_bytes);
-  const uint64_t fh0 = tc::make_smem_desc(a_hi), fl0 = tc::make_smem_desc(a_lo);
-  const uint64_t fh1 = tc::make_smem_desc(a_hi + kKBlockBytes), fl1 = tc::make_smem_desc(a_lo + kKBlockBytes);
-  const uint64_t th = tc::make_smem_desc_sw32(a_hi + tail_off), tl = tc::make_smem_desc_sw32(a_lo + tail_off);
+__device__ __forceinline__ void issue_job_ss(const JobPkt& q, uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t w_base0,
+                                             uint32_t w_base1, uint64_t* empty0, uint64_t* empty1, uint64_t* full) {
+  const uint32_t part16 = (uint32_t)q.N * 8u;
+  const uint64_t d0 = tc::make_smem_desc(w_base0), d1 = tc::make_smem_desc(w_base1);
+  const uint32_t bhi = desc_hi(d0), b0 = desc_lo(d0), b1 = desc_lo(d1);
+  const uint64_t fh = tc::make_smem_desc(a_hi), fl = tc::make_smem_desc(a_lo);
+  const uint64_t th = tc::make_smem_desc_sw32(a_hi), tl = tc::make_smem_desc_sw32(a_lo);
 #pragma unroll
   for (int ks = 0; ks < 8; ++ks) {
-    const uint32_t en = ks < ksteps ? 1u : 0u;
-    const uint64_t bh = (ks < 4 ? b0h : b1h) + (uint64_t)((ks & 3) * 2), bl = (ks < 4 ? b0l : b1l) + (uint64_t)((ks & 3) * 2);
-    const bool isfull = (ks >> 2) < nfull;
-    const int kt = ks - 4 * nfull;  // tail k-step index
-    const uint64_t ah = isfull ? (ks < 4 ? fh0 : fh1) + (uint64_t)((ks & 3) * 2) : th + (uint64_t)kt * (kTailBytes >> 4);
-    const uint64_t al = isfull ? (ks < 4 ? fl0 : fl1) + (uint64_t)((ks & 3) * 2) : tl + (uint64_t)kt * (kTailBytes >> 4);
-    mma_ss_p(d_tmem, ah, bh, idesc, ks ? 1u : 0u, en);
+    const uint32_t en = (q.en >> ks) & 1u;
+    const uint32_t bh = (ks < 4 ? b0 : b1) + q.kb[ks], bl = bh + part16;
+    const bool tail = (q.ka[ks] >> 31) != 0u;
+    const uint32_t off = q.ka[ks] & 0x7fffffffu;
+    const uint32_t ah = (tail ? desc_lo(th) : desc_lo(fh)) + off, al = (tail ? desc_lo(tl) : desc_lo(fl)) + off;
+    const uint32_t ahi = tail ? desc_hi(th) : desc_hi(fh);
+    mma_ss_p(d_tmem, ah, ahi, bh, bhi, q.ki[ks], ks ? 1u : 0u, en);
     if (NSPLIT == 3) {
-      mma_ss_p(d_tmem, ah, bl, idesc, 1u, en);
-      mma_ss_p(d_tmem, al, bh, idesc, 1u, en);
+      mma_ss_p(d_tmem, ah, ahi, bl, bhi, q.ki[ks], 1u, en);
+      mma_ss_p(d_tmem, al, ahi, bh, bhi, q.ki[ks], 1u, en);
     }
     if (ks == 3 && empty0) tc::mma_commit(empty0);
   }
@@ -463,7 +488,7 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
   const uint32_t kFullBytes = (uint32_t)L.in0_full * kKBlockBytes;  // tail k-steps start here inside a plane
   unsigned char* w_ring = smem + 2 * kParts * kPlane;
   const uint32_t kStages = (uint32_t)L.stages;
-  __shared__ __align__(8) uint64_t w_full[kMaxStages], w_empty[kMaxStages], a_ready[2], acc_full[2][2], acc_free[2][2];
+  __shared__ __align__(8) uint64_t w_full[kMaxStages], w_empty[kMaxStages], a_ready[2], acc_full[2][2], acc_free[2][2], acc_hid[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float sbias[8][2][128];  // [epilogue warp][job parity][column]: every warp stages its own copy
 
@@ -488,12 +513,43 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
   if (tid == 0) {
     for (int s = 0; s < kMaxStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     for (int t = 0; t < 2; ++t) {
-      mbar_init(&a_ready[t], 4);  // one arrival per epilogue warp of the slot
-      for (int r = 0; r < 2; ++r) { mbar_init(&acc_full[t][r], 1); mbar_init(&acc_free[t][r], 4); }
+      mbar_init(&a_ready[t], 128);
+      for (int r = 0; r < 2; ++r) { mbar_init(&acc_full[t][r], 1); mbar_init(&acc_free[t][r], 128); }
+      // hidden-layer accumulators complete on their own barrier: all eight epilogue warps wait for EVERY completion of
+      // it (a warp that skipped completions of a barrier would be released early by parity aliasing)
+      mbar_init(&acc_hid[t], 1);
     }
     fence_mbar_init();
   }
   if (warp == kIssuerWarp) tc::tmem_alloc(&tmem_base_s, 512);
+  // job packets of every (transform, job), built once per CTA by all threads (the tensor pipe idles for ~1000 cycles per
+  // job when the issuer derives them on the fly)
+  JobPkt* pkt_s = reinterpret_cast<JobPkt*>(w_ring + (size_t)kStages * kStageBytes);
+  auto build_pkt = [&](JobPkt& q, int tr, int ji_) {
+    const int ksteps = L.job[ji_].ksteps;
+    q.ji = ji_; q.pad = 0;
+    q.N = L.job[ji_].N; q.last = L.job[ji_].last; q.reg = L.job[ji_].region; q.nst = L.job[ji_].nstages;
+    q.col = (uint32_t)L.job[ji_].acc_col;
+    const uint32_t idesc = tc::make_idesc_f16(NSPLIT == 3 ? 0 : 1, 128, q.N);
+    unsigned long long skipw = 0ull;
+    if (ji_ != 0 && args.skip) skipw = __ldg(args.skip + (size_t)tr * kMaxJobs + ji_);
+    const uint32_t slo = (uint32_t)skipw, shi = (uint32_t)(skipw >> 32);
+    uint32_t en = 0u;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      const uint32_t byte = ((ks < 4 ? slo : shi) >> (8 * (ks & 3))) & 0xFFu;  // leading all-zero weight rows / 16
+      q.kd[ks] = byte << 4;
+      q.kb[ks] = (byte << 7) + (uint32_t)((ks & 3) * 2);   // 128-byte weight rows, 32-byte k-steps (16-byte units)
+      q.ki[ks] = idesc - (byte << 18);                     // N - 16 * byte columns (N field = N >> 3 at bit 17)
+      en |= ((ks < ksteps && (int)(byte << 4) < q.N) ? 1u : 0u) << ks;
+      const bool isfull = (ks >> 2) < L.in0_full;           // layer-0 operand: 64-wide K-blocks, then 32-byte tail k-steps
+      q.ka[ks] = isfull ? (uint32_t)(ks >> 2) * (kKBlockBytes >> 4) + (uint32_t)((ks & 3) * 2)
+                        : (0x80000000u | ((kFullBytes >> 4) + (uint32_t)(ks - 4 * L.in0_full) * (kTailBytes >> 4)));
+    }
+    q.en = en;
+  };
+  if (L.pkt_table)
+    for (int i = tid; i < L.T * L.njobs; i += kTcThreads) build_pkt(pkt_s[i], i / L.njobs, i % L.njobs);
   tc::fence_before_thread_sync();
   __syncthreads();
   tc::fence_after_thread_sync();
@@ -536,82 +592,127 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
     int trace_n = 0, trace_end = 1500; (void)trace_n; (void)trace_end;
     uint32_t aph0 = 0, aph1 = 0;               // a_ready phases per slot
     uint32_t nchunk0 = 0, nchunk1 = 0;         // last-layer chunks issued so far per region (both slots walk the same jobs)
-    const uint32_t tail_off = kFullBytes;
-    unsigned long long skip_next = args.skip ? __ldg(args.skip + (size_t)(inverse ? L.T - 1 : 0) * kMaxJobs) : 0ull;
-    for (long long p = blockIdx.x; p < n_pairs; p += gridDim.x) {
-      const int nact = (2 * p + 1 < n_tiles) ? 2 : 1;  // odd tile count: slot 1 idles in the last pair
-      for (int unit = 0; unit < n_units; ++unit) {
-        bool first_last = true;      // the first EXECUTED last-layer chunk of a unit waits for the last hidden activations
-        int in_unit0 = 0, in_unit1 = 0;  // chunks of this unit issued per region
-        for (int ji = 0; ji < L.njobs; ++ji) {
-          if (!job_live(unit, ji)) continue;
-          // job constants -> registers (the parameter struct lives in the constant bank)
-          const int jN = L.job[ji].N, jks = L.job[ji].ksteps, jlast = L.job[ji].last, jreg = L.job[ji].region;
-          const uint32_t jcol = (uint32_t)L.job[ji].acc_col;
-          const uint32_t idesc = tc::make_idesc_f16(NSPLIT == 3 ? 0 : 1, 128, jN);
-          // zero-block word of (transform, job): fetched one job ahead (an L2 round trip is ~500 cycles of an idle pipe)
-          const unsigned long long skipw = skip_next;
-          {
-            int ju = unit, jn = ji + 1;
-            if (jn == L.njobs) { jn = 0; ++ju; }
-            while (ju < n_units && !job_live(ju, jn)) {
-              if (++jn == L.njobs) { jn = 0; ++ju; }
-            }
-            if (ju >= n_units) { ju = 0; jn = 0; }  // first job of the next tile pair (job 0 is always live)
-            const int trn = inverse ? (L.T - 1 - ju / sweeps) : ju;
-            skip_next = args.skip ? __ldg(args.skip + (size_t)trn * kMaxJobs + jn) : 0ull;
-          }
-          const bool wait_a = jlast ? first_last : true;
-          const bool wait_free = jlast && (jreg ? in_unit1 : in_unit0) > 0;
-          const uint32_t free_par = ((jreg ? nchunk1 : nchunk0) - 1) & 1;  // phase of the previous chunk of this region
-          if (jlast) {
-            first_last = false;
-            if (jreg) { ++in_unit1; ++nchunk1; } else { ++in_unit0; ++nchunk0; }
-          }
-          // ring stages of the job's (at most two) weight K-blocks; everything must have landed before the batch is issued
-          const int jnst = L.job[ji].nstages;
-          const uint32_t s0 = stage, p0 = sphase;
-          uint32_t s1 = s0 + 1, p1 = p0;
-          if (s1 == kStages) { s1 = 0; p1 ^= 1; }
-          const bool two = jnst > 1;
-          mbar_wait(&w_full[s0], p0);
-          if (two) mbar_wait(&w_full[s1], p1);
-          MF_TRACE(lane == 0, 1, 2 * ji);
-          const uint32_t w_base0 = smem_u32(w_ring + s0 * kStageBytes);
-          const uint32_t w_base1 = two ? smem_u32(w_ring + s1 * kStageBytes) : w_base0 + kParts * (uint32_t)jN * 128u;
-          for (int t = 0; t < nact; ++t) {
-            const uint32_t d_tmem = tmem + (uint32_t)(t * 256) + jcol;
-            const uint32_t a_tmem = tmem + (uint32_t)(t * 256) + 128;  // hi plane; lo plane 64 columns further
-            const uint32_t a_base = smem_u32(a_buf + (size_t)t * kParts * kPlane);
-            if (wait_a) {
-              mbar_poll(&a_ready[t], t ? aph1 : aph0);
-              if (t) aph1 ^= 1; else aph0 ^= 1;
-            }
-            if (wait_free) mbar_poll(&acc_free[t][jreg], free_par);
-            MF_TRACE(lane == 0, 2, 2 * ji + t);
-            tc::fence_after_thread_sync();
-            if (tc::elect_one()) {
-              // the last slot releases the stages: the first one right after its k-steps when the job spans two stages
-              const bool release = (t == nact - 1);
-              uint64_t* e0 = (release && two) ? &w_empty[s0] : nullptr;
-              uint64_t* e1 = release ? (two ? &w_empty[s1] : &w_empty[s0]) : nullptr;
-              if (ji == 0)
-                issue_job_ss<NSPLIT>(d_tmem, a_base, a_base + kPlane, L.in0_full, tail_off, w_base0, w_base1, idesc, jks, jN,
-                                     e0, e1, &acc_full[t][jreg]);
-              else
-                issue_job_ts<NSPLIT>(d_tmem, a_tmem, w_base0, w_base1, idesc, jks, jN, skipw, e0, e1, &acc_full[t][jreg]);
-            }
-            __syncwarp();
-            MF_TRACE(lane == 0, 3, 2 * ji + t);
-          }
-          // advance the ring by the job's K-blocks (s1 / p1 already are the wrapped successor of s0 / p0)
-          stage = s1; sphase = p1;
-          if (two) {
-            ++stage;
-            if (stage == kStages) { stage = 0; sphase ^= 1; }
+    struct JobRef { long long p; int unit, nact; };
+    // advance (p, unit, ji) to the next job that is executed; false after the last one of this CTA
+    auto next_job = [&](long long& p_, int& unit_, int& ji_) -> bool {
+      for (;;) {
+        if (++ji_ == L.njobs) {
+          ji_ = 0;
+          if (++unit_ == n_units) { unit_ = 0; p_ += gridDim.x; }
+        }
+        if (p_ >= n_pairs) return false;
+        if (job_live(unit_, ji_)) return true;
+      }
+    };
+    auto prepare = [&](JobPkt& q, JobRef& r, long long p_, int unit_, int ji_) {
+      r.p = p_; r.unit = unit_;
+      r.nact = (2 * p_ + 1 < n_tiles) ? 2 : 1;  // odd tile count: slot 1 idles in the last pair
+      const int tr = inverse ? (L.T - 1 - unit_ / sweeps) : unit_;
+      if (L.pkt_table) {
+        const uint4* src = reinterpret_cast<const uint4*>(pkt_s + tr * L.njobs + ji_);
+        uint4* dst = reinterpret_cast<uint4*>(&q);
+#pragma unroll
+        for (int i = 0; i < kPktWords / 4; ++i) dst[i] = src[i];
+      } else {
+        build_pkt(q, tr, ji_);
+      }
+    };
+    // pins a prepared packet in front of the next volatile statement (the compiler must not sink the preparation into
+    // the critical path behind the barrier waits)
+    auto pin = [&](JobPkt& q) {
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) asm volatile("" : "+r"(q.kd[ks]), "+r"(q.kb[ks]), "+r"(q.ki[ks]), "+r"(q.ka[ks]));
+      asm volatile("" : "+r"(q.en), "+r"(q.N), "+r"(q.col));
+    };
+
+    JobPkt cur, nxt;
+    JobRef rcur, rnxt;
+    long long jp = blockIdx.x;
+    int junit = 0, jji = -1;
+    bool have = (jp < n_pairs) && next_job(jp, junit, jji);
+    if (have) prepare(cur, rcur, jp, junit, jji);
+    bool first_last = true;          // the first EXECUTED last-layer chunk of a unit waits for the last hidden activations
+    int in_unit0 = 0, in_unit1 = 0;  // chunks of the current unit issued per region
+    long long key_p = -1;
+    int key_unit = -1;
+    // ring stages of a job's (at most two) weight K-blocks: wait until they have landed, return their addresses and
+    // advance the ring position
+    uint32_t wb0 = 0, wb1 = 0, cs0 = 0, cs1 = 0;  // current job: stage addresses and stage indices
+    auto take_stages = [&](const JobPkt& q, uint32_t& b0_, uint32_t& b1_, uint32_t& s0_, uint32_t& s1_) {
+      s0_ = stage;
+      const uint32_t ph0 = sphase;
+      if (++stage == kStages) { stage = 0; sphase ^= 1; }
+      s1_ = stage;
+      mbar_wait(&w_full[s0_], ph0);
+      b0_ = smem_u32(w_ring + s0_ * kStageBytes);
+      if (q.nst > 1) {
+        mbar_wait(&w_full[s1_], sphase);
+        if (++stage == kStages) { stage = 0; sphase ^= 1; }
+        b1_ = smem_u32(w_ring + s1_ * kStageBytes);
+      } else {
+        b1_ = b0_ + kParts * (uint32_t)q.N * 128u;  // both K-blocks of a narrow job share the stage
+      }
+    };
+    if (have) take_stages(cur, wb0, wb1, cs0, cs1);
+    while (have) {
+      if (rcur.p != key_p || rcur.unit != key_unit) {  // a new unit starts
+        key_p = rcur.p; key_unit = rcur.unit;
+        first_last = true; in_unit0 = 0; in_unit1 = 0;
+      }
+      const int ji = cur.ji;
+      const int jreg = cur.reg;
+      const bool two = cur.nst > 1;
+      const bool wait_a = cur.last ? first_last : true;
+      const bool wait_free = cur.last && (jreg ? in_unit1 : in_unit0) > 0;
+      const uint32_t free_par = ((jreg ? nchunk1 : nchunk0) - 1) & 1;  // phase of the previous chunk of this region
+      if (cur.last) {
+        first_last = false;
+        if (jreg) { ++in_unit1; ++nchunk1; } else { ++in_unit0; ++nchunk0; }
+      }
+      MF_TRACE(lane == 0, 1, 2 * ji);
+      bool have_next = false, early_take = false;
+      uint32_t nb0 = 0, nb1 = 0, ns0 = 0, ns1 = 0;
+      for (int t = 0; t < rcur.nact; ++t) {
+        const uint32_t d_tmem = tmem + (uint32_t)(t * 256) + cur.col;
+        const uint32_t a_tmem = tmem + (uint32_t)(t * 256) + 128;  // hi plane; lo plane 64 columns further
+        const uint32_t a_base = smem_u32(a_buf + (size_t)t * kParts * kPlane);
+        if (wait_a) {
+          mbar_wait(&a_ready[t], t ? aph1 : aph0);
+          if (t) aph1 ^= 1; else aph0 ^= 1;
+        }
+        if (wait_free) mbar_wait(&acc_free[t][jreg], free_par);
+        MF_TRACE(lane == 0, 2, 2 * ji + t);
+        tc::fence_after_thread_sync();
+        if (tc::elect_one()) {
+          // the last slot releases the stages: the first one right after its k-steps when the job spans two stages
+          const bool release = (t == rcur.nact - 1);
+          uint64_t* e0 = (release && two) ? &w_empty[cs0] : nullptr;
+          uint64_t* e1 = release ? (two ? &w_empty[cs1] : &w_empty[cs0]) : nullptr;
+          if (ji == 0)
+            issue_job_ss<NSPLIT>(cur, d_tmem, a_base, a_base + kPlane, wb0, wb1, e0, e1, &acc_hid[t]);
+          else
+            issue_job_ts<NSPLIT>(cur, d_tmem, a_tmem, wb0, wb1, e0, e1, cur.last ? &acc_full[t][jreg] : &acc_hid[t]);
+        }
+        __syncwarp();
+        MF_TRACE(lane == 0, 3, 2 * ji + t);
+        if (t == 0) {
+          // everything of the NEXT job that does not depend on the epilogues happens here, while the MMAs just issued
+          // execute (a dozen of them sit in the tensor core's queue): its packet, the wait for its weight stages
+          have_next = next_job(jp, junit, jji);
+          if (have_next) {
+            prepare(nxt, rnxt, jp, junit, jji);
+            // (only when the ring holds both jobs: otherwise the next job's stages are released by THIS job's last slot)
+            early_take = false;  // (taking the next job's stages here measured slower)
+            if (early_take) take_stages(nxt, nb0, nb1, ns0, ns1);
+            pin(nxt);
           }
         }
       }
+      if (have_next && !early_take) take_stages(nxt, nb0, nb1, ns0, ns1);
+      cur = nxt;
+      rcur = rnxt;
+      wb0 = nb0; wb1 = nb1; cs0 = ns0; cs1 = ns1;
+      have = have_next;
     }
   } else {
     // ===================== epilogue groups =====================
@@ -641,7 +742,8 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
     const float bscale_last = (((4 * lane) % L.PFt) / L.Kp == 2) ? cf.inv1 : cf.inv2;
     float* const sb_warp = &sbias[warp][0][0];
     uint32_t jobctr = 0;                      // bias double-buffer parity
-    uint32_t fullctr0 = 0, fullctr1 = 0;      // accumulator uses per region
+    uint32_t fh0 = 0, fh1 = 0;   // hidden-layer accumulator completions seen so far, per slot (every warp waits for all)
+    uint32_t fo0 = 0, fo1 = 0;   // last-layer chunk completions of the warp's OWN slot, per accumulator region
     int trace_n = 1500 + warp * 300, trace_end = trace_n + 300; (void)trace_n; (void)trace_end;
 
     auto put1 = [&](int r, int k, float v) {
@@ -658,88 +760,91 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
     for (long long p = blockIdx.x; p < n_pairs; p += gridDim.x) {
       const long long tile = 2 * p + t;
       if (tile >= n_tiles) break;  // odd tile count: slot 1 idles in the last pair (the MMA warp skips it too)
+      const bool has_tile = true;
       const long long tile0 = tile * 128;
-      const int rows = (int)min((long long)128, n - tile0);
+      const int rows = has_tile ? (int)min((long long)128, n - tile0) : 0;
       const bool valid = row < rows;
       const long long g = tile0 + row;
       // working copy of x lives in the output buffer (each thread touches only its own row); when sampling,
       // gx holds the noise and the base sample a + b * noise is the starting point
-      MF_TRACE(lane == 0, 8, 0);
-      for (int f0 = 0; f0 < D; f0 += 8) {  // eight loads in flight
-        float xv[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) xv[u] = (valid && f0 + u < D) ? gx[g * D + f0 + u] : 0.f;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int f = f0 + u;
-          if (f < D) {
-            float v0 = xv[u];
-            if (inverse && valid)
-              v0 = (args.base == MF_BASE_DIAG_NORMAL) ? (float)bp.a[f] + (float)bp.b[f] * v0
-                                                     : (float)bp.a[f] + ((float)bp.b[f] - (float)bp.a[f]) * v0;
-            if (!inverse && valid && bp.xmap_kind != MF_XMAP_NONE) v0 = xmap_apply<float>(bp, v0, f);  // logit bridge
-            if (valid) gz[g * D + f] = v0;
-            put1(row, xcol0 + f, v0);  // x columns of the layer-0 operand
-          }
-        }
-      }
       float* gy = static_cast<float*>(args.work);  // sampling: target y of the transform being inverted
       float ladj = 0.f;
-      // ---- stage (ctx | 0) of the layer-0 operand once per tile; every MMA that read the previous tile's
-      //      operand has retired (this group waited on the last accumulator of that tile)
-      {
-        const int kfill = L.in0_ksteps * 16;
-        for (int k = xcol0 + D; k < kfill; ++k) put1(row, k, 0.f);
-        // context: one 16-byte operand chunk (8 columns of one row) per thread and step, four chunks in flight;
-        // consecutive threads take consecutive chunks, so a warp reads a contiguous stretch of global memory
-        const int nchunk = xcol0 >> 3;  // chunks per row (the last one zero-padded when C % 8 != 0)
-        const int total = 128 * nchunk;
-        const float* gct = gc + tile0 * C;
-        for (int q0 = gt; q0 < total; q0 += 4 * GT) {
-          float v[4][8];
-          int rr[4], kc[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int qq = q0 + u * GT;
-            rr[u] = qq / nchunk;
-            kc[u] = qq - rr[u] * nchunk;
-            const bool live = (qq < total) && (rr[u] < rows);
-            const float* src = gct + (long long)rr[u] * C + kc[u] * 8;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[u][e] = (live && kc[u] * 8 + e < C) ? __ldg(src + e) : 0.f;
+      if (has_tile) {
+        MF_TRACE(lane == 0, 8, 0);
+        for (int f0 = 0; f0 < D; f0 += 8) {  // eight loads in flight
+          float xv[8];
+  #pragma unroll
+          for (int u = 0; u < 8; ++u) xv[u] = (valid && f0 + u < D) ? gx[g * D + f0 + u] : 0.f;
+  #pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int f = f0 + u;
+            if (f < D) {
+              float v0 = xv[u];
+              if (inverse && valid)
+                v0 = (args.base == MF_BASE_DIAG_NORMAL) ? (float)bp.a[f] + (float)bp.b[f] * v0
+                                                       : (float)bp.a[f] + ((float)bp.b[f] - (float)bp.a[f]) * v0;
+              if (!inverse && valid && bp.xmap_kind != MF_XMAP_NONE) v0 = xmap_apply<float>(bp, v0, f);  // logit bridge
+              if (valid) gz[g * D + f] = v0;
+              put1(row, xcol0 + f, v0);  // x columns of the layer-0 operand
+            }
           }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (q0 + u * GT < total) {
-              const int r = rr[u], c8 = kc[u];
-              const uint32_t off = (c8 * 8 < kfull_cols)
-                                       ? (uint32_t)(c8 >> 3) * kKBlockBytes + (uint32_t)r * 128u + (uint32_t)(((c8 & 7) ^ (r & 7)) << 4)
-                                       : kFullBytes + (uint32_t)((c8 * 8 - kfull_cols) >> 4) * kTailBytes + (uint32_t)r * 32u +
-                                             (uint32_t)(((c8 & 1) ^ ((r >> 2) & 1)) << 4);
-              uint4 hi, lo;
-              if (NSPLIT == 3) {
-                tc::split_f16(v[u][0], v[u][1], hi.x, lo.x); tc::split_f16(v[u][2], v[u][3], hi.y, lo.y);
-                tc::split_f16(v[u][4], v[u][5], hi.z, lo.z); tc::split_f16(v[u][6], v[u][7], hi.w, lo.w);
-                *reinterpret_cast<uint4*>(a_hi + off) = hi;
-                *reinterpret_cast<uint4*>(a_lo + off) = lo;
-              } else {
-                hi.x = tc::pack_bf16(v[u][0], v[u][1]); hi.y = tc::pack_bf16(v[u][2], v[u][3]);
-                hi.z = tc::pack_bf16(v[u][4], v[u][5]); hi.w = tc::pack_bf16(v[u][6], v[u][7]);
-                *reinterpret_cast<uint4*>(a_hi + off) = hi;
+        }
+        // ---- stage (ctx | 0) of the layer-0 operand once per tile; every MMA that read the previous tile's
+        //      operand has retired (this group waited on the last accumulator of that tile)
+        {
+          const int kfill = L.in0_ksteps * 16;
+          for (int k = xcol0 + D; k < kfill; ++k) put1(row, k, 0.f);
+          // context: one 16-byte operand chunk (8 columns of one row) per thread and step, four chunks in flight;
+          // consecutive threads take consecutive chunks, so a warp reads a contiguous stretch of global memory
+          const int nchunk = xcol0 >> 3;  // chunks per row (the last one zero-padded when C % 8 != 0)
+          const int total = 128 * nchunk;
+          const int G = args.ctx_group;   // x rows per context row (context hoisted per event in the MEM sweep)
+          for (int q0 = gt; q0 < total; q0 += 4 * GT) {
+            float v[4][8];
+            int rr[4], kc[4];
+  #pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int qq = q0 + u * GT;
+              rr[u] = qq / nchunk;
+              kc[u] = qq - rr[u] * nchunk;
+              const bool live = (qq < total) && (rr[u] < rows);
+              const float* src = gc + ((tile0 + rr[u]) / G) * C + kc[u] * 8;
+  #pragma unroll
+              for (int e = 0; e < 8; ++e) v[u][e] = (live && kc[u] * 8 + e < C) ? __ldg(src + e) : 0.f;
+            }
+  #pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (q0 + u * GT < total) {
+                const int r = rr[u], c8 = kc[u];
+                const uint32_t off = (c8 * 8 < kfull_cols)
+                                         ? (uint32_t)(c8 >> 3) * kKBlockBytes + (uint32_t)r * 128u + (uint32_t)(((c8 & 7) ^ (r & 7)) << 4)
+                                         : kFullBytes + (uint32_t)((c8 * 8 - kfull_cols) >> 4) * kTailBytes + (uint32_t)r * 32u +
+                                               (uint32_t)(((c8 & 1) ^ ((r >> 2) & 1)) << 4);
+                uint4 hi, lo;
+                if (NSPLIT == 3) {
+                  tc::split_f16(v[u][0], v[u][1], hi.x, lo.x); tc::split_f16(v[u][2], v[u][3], hi.y, lo.y);
+                  tc::split_f16(v[u][4], v[u][5], hi.z, lo.z); tc::split_f16(v[u][6], v[u][7], hi.w, lo.w);
+                  *reinterpret_cast<uint4*>(a_hi + off) = hi;
+                  *reinterpret_cast<uint4*>(a_lo + off) = lo;
+                } else {
+                  hi.x = tc::pack_bf16(v[u][0], v[u][1]); hi.y = tc::pack_bf16(v[u][2], v[u][3]);
+                  hi.z = tc::pack_bf16(v[u][4], v[u][5]); hi.w = tc::pack_bf16(v[u][6], v[u][7]);
+                  *reinterpret_cast<uint4*>(a_hi + off) = hi;
+                }
               }
             }
           }
         }
-      }
-      {  // pull this slot's next tile (x rows and context rows) into L2 while this one is being processed
-        const long long nt0 = (tile + 2 * (long long)gridDim.x) * 128;
-        if (nt0 < n) {
-          const long long nrows = min((long long)128, n - nt0);
-          const char* px = reinterpret_cast<const char*>(gx + nt0 * D);
-          const char* pc = reinterpret_cast<const char*>(gc + nt0 * C);
-          const long long xb = nrows * D * 4, cb = nrows * C * 4;
-          for (long long o = (long long)gt * 128; o < xb; o += (long long)GT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(px + o));
-          for (long long o = (long long)gt * 128; o < cb; o += (long long)GT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + o));
+        {  // pull this slot's next tile (x rows and context rows) into L2 while this one is being processed
+          const long long nt0 = (tile + 2 * (long long)gridDim.x) * 128;
+          if (nt0 < n) {
+            const long long nrows = min((long long)128, n - nt0);
+            const char* px = reinterpret_cast<const char*>(gx + nt0 * D);
+            const char* pc = reinterpret_cast<const char*>(gc + (nt0 / args.ctx_group) * C);
+            const long long xb = nrows * D * 4, cb = ((nt0 + nrows - 1) / args.ctx_group - nt0 / args.ctx_group + 1) * C * 4;
+            for (long long o = (long long)gt * 128; o < xb; o += (long long)GT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(px + o));
+            for (long long o = (long long)gt * 128; o < cb; o += (long long)GT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + o));
+          }
         }
       }
       float lp_base = 0.f;               // base log-density, accumulated as the last transform's outputs appear
@@ -752,14 +857,14 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
       MF_TRACE(lane == 0, 9, 0);
       for (int unit = 0; unit < n_units; ++unit) {
         const int tr = inverse ? (L.T - 1 - unit / sweeps) : unit;
-        if (inverse && (unit % sweeps) == 0) {  // y <- x, x <- 0  (AutoregressiveTransform._inverse)
+        if (inverse && (unit % sweeps) == 0 && has_tile) {  // y <- x, x <- 0  (AutoregressiveTransform._inverse)
           for (int f = 0; f < D; ++f) {
             if (valid) { gy[g * D + f] = gz[g * D + f]; gz[g * D + f] = 0.f; }
             put1(row, xcol0 + f, 0.f);
           }
         }
         // ---- layer-0 operand: the context part was staged at the tile start, the D columns of x were written
-        //      by this thread when it produced them (tile start / spline output of the previous unit)
+        //      by this thread when it produced them (tile start / spline output of the previous unit).
         fence_proxy_async_smem();
         mbar_arrive_warp(&a_ready[t], lane);
         for (int ji = 0; ji < L.njobs; ++ji) {
@@ -788,60 +893,81 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
             }
           }
           __syncwarp();
-          // inputs of this chunk's splines, fetched before the accumulator wait
-          const float* xsrc = (inverse ? gy : gz) + g * D + j.feat0;
-          float xnext = (j.last && valid) ? xsrc[0] : 0.f;
-          MF_TRACE(lane == 0, 5, ji);
-          mbar_wait(&acc_full[t][j.region], (j.region ? fullctr1 : fullctr0) & 1);
-          if (j.region) ++fullctr1; else ++fullctr0;
-          MF_TRACE(lane == 0, 6, ji);
-          tc::fence_after_thread_sync();
-          const uint32_t taddr = tmem + lane_off + (uint32_t)(t * 256);
           if (!j.last) {
-            // hidden layer: TMEM -> +bias -> ReLU -> operand planes of the next layer (in place)
-            for (int c00 = 0; c00 < j.N; c00 += 32) {
-              float vv[32];
-              tc::tmem_ld16(taddr + c00, vv);
-              if (c00 + 16 < j.N) tc::tmem_ld16(taddr + c00 + 16, vv + 16);
-              float4 bb[8];  // the biases travel from shared memory while the TMEM loads are in flight
+            // Hidden layer: TMEM -> +bias -> ReLU -> fp16 hi/lo operand planes of the next layer (in place).
+            // (Sharing every hidden epilogue between the warps of BOTH slots -- same lane quarter, half the columns each --
+            // shortens one epilogue from ~1900 to ~1300 cycles but was slower overall, 23.5 vs 20.8 ms: with all eight
+            // warps busy the MMA issuer waits even longer for its turn; profiles/trace_flow_tc_r2p.txt.)
+            {
+              const int s_ = t;
+              const bool mine = true;
+              const int half_n = j.N;
+              MF_TRACE(lane == 0, 5, ji);
+              mbar_wait(&acc_hid[s_], (s_ ? fh1 : fh0) & 1);
+              if (s_) ++fh1; else ++fh0;
+              MF_TRACE(lane == 0, 6, ji);
+              tc::fence_after_thread_sync();
+              const uint32_t taddr = tmem + lane_off + (uint32_t)(s_ * 256);
+              const int cb = mine ? 0 : half_n, ce = mine ? half_n : j.N;
+              for (int c00 = cb; c00 < ce; c00 += 32) {
+                float vv[32];
+                tc::tmem_ld16(taddr + c00, vv);
+                if (c00 + 16 < ce) tc::tmem_ld16(taddr + c00 + 16, vv + 16);
+                float4 bb[8];  // the biases travel from shared memory while the TMEM loads are in flight
 #pragma unroll
-              for (int i = 0; i < 8; ++i) bb[i] = *reinterpret_cast<const float4*>(sb + c00 + 4 * i);
-              tc::tmem_ld_wait();
+                for (int i = 0; i < 8; ++i) bb[i] = *reinterpret_cast<const float4*>(sb + c00 + 4 * i);
+                tc::tmem_ld_wait();
 #pragma unroll
-              for (int half = 0; half < 2; ++half) {
-                const int c0 = c00 + half * 16;
-                if (c0 < j.N) {
-                  float* v = vv + half * 16;
-                  float2 w2[8];
+                for (int hf = 0; hf < 2; ++hf) {
+                  const int c0 = c00 + hf * 16;
+                  if (c0 < ce) {
+                    float* v = vv + hf * 16;
+                    float2 w2[8];
 #pragma unroll
-                  for (int i = 0; i < 16; i += 4) {
-                    const float4 b4 = bb[half * 4 + i / 4];
-                    float2 u0 = f2_add(make_float2(v[i], v[i + 1]), make_float2(b4.x, b4.y));
-                    float2 u1 = f2_add(make_float2(v[i + 2], v[i + 3]), make_float2(b4.z, b4.w));
-                    w2[i / 2] = make_float2(fmaxf(u0.x, 0.f), fmaxf(u0.y, 0.f));
-                    w2[i / 2 + 1] = make_float2(fmaxf(u1.x, 0.f), fmaxf(u1.y, 0.f));
-                  }
-                  // 16 values -> 8 packed 16-bit pairs per plane -> operand planes in TMEM
-                  if (NSPLIT == 3) {
-                    uint32_t hi[8], lo[8];
+                    for (int i = 0; i < 16; i += 4) {
+                      const float4 b4 = bb[hf * 4 + i / 4];
+                      float2 u0 = f2_add(make_float2(v[i], v[i + 1]), make_float2(b4.x, b4.y));
+                      float2 u1 = f2_add(make_float2(v[i + 2], v[i + 3]), make_float2(b4.z, b4.w));
+                      w2[i / 2] = make_float2(fmaxf(u0.x, 0.f), fmaxf(u0.y, 0.f));
+                      w2[i / 2 + 1] = make_float2(fmaxf(u1.x, 0.f), fmaxf(u1.y, 0.f));
+                    }
+                    // 16 values -> 8 packed 16-bit pairs per plane -> operand planes in TMEM
+                    if (NSPLIT == 3) {
+                      uint32_t hi[8], lo[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) split_f16_pair(w2[i], hi[i], lo[i]);
-                    tc::tmem_st8(taddr + 128 + c0 / 2, hi);
-                    tc::tmem_st8(taddr + 192 + c0 / 2, lo);
-                  } else {
-                    uint32_t pk[8];
+                      for (int i = 0; i < 8; ++i) split_f16_pair(w2[i], hi[i], lo[i]);
+                      tc::tmem_st8(taddr + 128 + c0 / 2, hi);
+                      tc::tmem_st8(taddr + 192 + c0 / 2, lo);
+                    } else {
+                      uint32_t pk[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) pk[i] = tc::pack_bf16(w2[i].x, w2[i].y);
-                    tc::tmem_st8(taddr + 128 + c0 / 2, pk);
+                      for (int i = 0; i < 8; ++i) pk[i] = tc::pack_bf16(w2[i].x, w2[i].y);
+                      tc::tmem_st8(taddr + 128 + c0 / 2, pk);
+                    }
                   }
                 }
               }
+              MF_TRACE(lane == 0, 4, ji);
+              tc::tmem_st_wait();
+              tc::fence_before_thread_sync();
+              mbar_arrive_warp(&a_ready[s_], lane);
+              MF_TRACE(lane == 0, 7, ji);
+              (void)mine;
             }
-            tc::tmem_st_wait();
-            tc::fence_before_thread_sync();
-            mbar_arrive_warp(&a_ready[t], lane);
-            MF_TRACE(lane == 0, 7, ji);
-          } else {
+            continue;
+          }
+          // last-layer chunk: only the slot's own warps
+          if (!has_tile) continue;
+          // inputs of this chunk's splines, fetched before the accumulator wait
+          const float* xsrc = (inverse ? gy : gz) + g * D + j.feat0;
+          float xnext = valid ? xsrc[0] : 0.f;
+          MF_TRACE(lane == 0, 5, ji);
+          mbar_wait(&acc_full[t][j.region], (j.region ? fo1 : fo0) & 1);
+          if (j.region) ++fo1; else ++fo0;
+          MF_TRACE(lane == 0, 6, ji);
+          tc::fence_after_thread_sync();
+          const uint32_t taddr = tmem + lane_off + (uint32_t)(t * 256);
+          {
             // last-layer chunk: splines of the chunk's features straight out of TMEM
             const unsigned long long fmask = sched ? sched[(size_t)tr * MF_MAX_FEATURES + (unit % sweeps)] : ~0ull;
 #pragma unroll 1
@@ -975,10 +1101,6 @@ int flow_tc_run(const mf_flow_desc& d, const FlowKernelArgs& a, const BaseParams
   FlowKernelArgs a_run = a;
   if (a.mode == 1) a_run.sched = reinterpret_cast<const unsigned long long*>(static_cast<const char*>(a.blob) + tc_sched_offset(L));
   a_run.skip = reinterpret_cast<const unsigned long long*>(static_cast<const char*>(a.blob) + tc_skip_offset(L));
-  if (a.ctx_group > 1) {
-    set_error("context grouping (ctx_group=%d) is not implemented on the tcgen05 path; use MF_GEMM_MMA_3XF16 / MF_GEMM_EXACT", a.ctx_group);
-    return MF_EUNSUPPORTED;
-  }
   if (!(a.slope > 0.0)) {
     set_error("the tcgen05 flow path needs the soft clip of the spline logits (slope > 0); use MF_GEMM_EXACT");
     return MF_EUNSUPPORTED;
@@ -988,7 +1110,8 @@ int flow_tc_run(const mf_flow_desc& d, const FlowKernelArgs& a, const BaseParams
                "tensor-core sampling needs a workspace of mf_flow_workspace_bytes() bytes");
   const int parts = (L.nsplit == 3) ? 2 : 1;
   MF_REQUIRE(L.stages >= 2, "layer-0 operand too large for the weight ring");
-  const size_t smem = (size_t)2 * parts * L.in0_plane_bytes + (size_t)L.stages * parts * kWPartBytes;
+  const size_t smem = (size_t)2 * parts * L.in0_plane_bytes + (size_t)L.stages * parts * kWPartBytes +
+                      (L.pkt_table ? (size_t)L.T * L.njobs * kPktWords * 4 : 0);
   const long long n_pairs = ((a.n + 127) / 128 + 1) / 2;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

@@ -505,8 +505,8 @@ class MAF(nn.Module):
     def effective_gemm(self, dtype, sampling=False, ctx_group=1):
         """Conditioner arithmetic of one call.  fp64 flows run the CUDA-core kernel.  "auto": tcgen05 3xFP16 when the
         shape fits that kernel, else the warp-level MMA kernel up to hidden width 512, else the CUDA-core kernel.
-        What the tcgen05 kernel does not take (context grouping, splines without soft clip) goes to the MMA kernel
-        under "auto" and to the CUDA-core kernel when a tcgen05 mode was asked for explicitly."""
+        What the tcgen05 kernel does not take (splines without soft clip) goes to the MMA kernel under "auto" and to
+        the CUDA-core kernel when a tcgen05 mode was asked for explicitly."""
         if dtype != torch.float32:
             return GEMM_EXACT
         t0 = self.core_transforms()[0]
@@ -517,7 +517,7 @@ class MAF(nn.Module):
             kp = -(-t0.bins // 8) * 8
             tc_ok = max(widths) <= 128 and -(-self.context // 8) * 8 + self.features <= 128 and 3 * kp <= 128
             gemm = GEMM_TC_3XF16 if tc_ok else (GEMM_MMA_3XF16 if mma_ok else GEMM_EXACT)
-        if gemm in (GEMM_TC_3XF16, GEMM_TC_BF16) and (ctx_group > 1 or not t0.slope):
+        if gemm in (GEMM_TC_3XF16, GEMM_TC_BF16) and not t0.slope:
             return GEMM_MMA_3XF16 if (self.gemm == GEMM_AUTO and mma_ok) else GEMM_EXACT
         return gemm
 

@@ -20,6 +20,10 @@ def event_log_prob(phasespace, flow, ps_points, x, context, exist_mask=None):
     B, P, D = x.shape
     mom, weight, x1, x2, logw = phasespace.generator.generateKinematics_batch(ps_points, want_logw=True)
     lp = flow(context).log_prob(x)  # [B, P]
+    if torch.is_grad_enabled() and (lp.requires_grad or logw.requires_grad):
+        # training: the per-event sum stays a differentiable torch expression (three element-wise ops on [B, P])
+        lpm = lp if exist_mask is None else lp * exist_mask.to(lp.dtype)
+        return lpm.sum(1) - logw.to(lp.dtype), mom, weight
     lp = lp.contiguous()
     out = torch.empty(B, dtype=lp.dtype, device=lp.device)
     m = None

@@ -639,6 +639,21 @@ def test_mma_3xf16_sample_parity(cuda, name, mode):
     _check_split_sample(cuda, name, mode, flows.modules.GEMM_MMA_3XF16, max_factor=8.0)
 
 
+def test_tc_context_group_equals_repeated_context(cuda):
+    """ctx_group on the tcgen05 kernel (MEM sweep with the most frequent unfolding-flow shape of the reference)."""
+    flow = build("UF-common", cuda, torch.float32, mode="default")
+    flow.gemm = flows.modules.GEMM_TC_3XF16
+    assert flow.effective_gemm(torch.float32, ctx_group=50) == flows.modules.GEMM_TC_3XF16
+    E, G = 41, 50
+    g = torch.Generator().manual_seed(8)
+    x = (0.3 * torch.randn(E * G, 10, generator=g)).to(cuda)
+    c = torch.randn(E, 32, generator=g).to(cuda)
+    with torch.no_grad():
+        a = flow(c, ctx_group=G).log_prob(x)
+        b = flow(c.repeat_interleave(G, dim=0)).log_prob(x)
+    assert torch.equal(a, b)
+
+
 def test_mma_context_group_equals_repeated_context(cuda):
     flow = build("UF", cuda, torch.float32, mode="default")
     flow.gemm = flows.modules.GEMM_MMA_3XF16
@@ -727,3 +742,55 @@ def test_fused_sigmoid_logit_bridges(cuda, name, gemm, dtype):
     assert torch.equal(torch.isfinite(fused_lp), fin)
     err = ((fused_lp[fin] - ref_lp[fin]).abs() / ref_lp[fin].abs().clamp_min(1.0)).max().item()
     assert err < (5e-5 if dtype == torch.float32 else 1e-10), err   # fp32: logit of the kernel vs torch differ by rounding, amplified by the flow
+
+
+def test_context_group_under_autograd(cuda):
+    """with grad enabled, flow(c, ctx_group=G) must run the kernel with the grouped descriptor and give
+    the gradients of the same flow fed the context repeated G times (context gradient summed over each group)."""
+    flow = build("NCSF", cuda, torch.float64, mode="stress")
+    E, G = 23, 6
+    g = torch.Generator().manual_seed(12)
+    x = (0.5 * torch.randn(E * G, 2, generator=g)).to(cuda, torch.float64)
+    c = torch.randn(E, 8, generator=g).to(cuda, torch.float64)
+    c1 = c.clone().requires_grad_(True)
+    lp1 = flow(c1, ctx_group=G).log_prob(x)
+    (-lp1.mean()).backward()
+    g1 = [c1.grad.clone()] + [p.grad.clone() for p in flow.parameters() if p.grad is not None]
+    for p in flow.parameters():
+        p.grad = None
+    c2 = c.clone().requires_grad_(True)
+    lp2 = flow(c2.repeat_interleave(G, dim=0)).log_prob(x)
+    (-lp2.mean()).backward()
+    g2 = [c2.grad.clone()] + [p.grad.clone() for p in flow.parameters() if p.grad is not None]
+    assert torch.allclose(lp1, lp2, atol=1e-12)
+    assert len(g1) == len(g2) and len(g1) > 3
+    for a, b in zip(g1, g2):
+        assert torch.allclose(a, b, atol=1e-10, rtol=1e-8)
+    # rsample with a trainable context and frozen flow weights keeps the context gradient (ADVICE r1, medium)
+    for p in flow.parameters():
+        p.requires_grad_(False)
+    c3 = c.clone().requires_grad_(True)
+    torch.manual_seed(0)
+    s = flow(c3).rsample()
+    assert s.requires_grad
+    s.square().sum().backward()
+    assert c3.grad is not None and c3.grad.abs().sum() > 0
+
+
+def test_event_log_prob_with_grad_requiring_phase_space_points(cuda):
+    """generateKinematics_batch(..., want_logw=True) on uniforms that require grad returns the 5-tuple."""
+    from memflow_msci_project_b200.likelihood import event_log_prob
+    from memflow_msci_project_b200.phasespace.phasespace import PhaseSpace
+    flow = build("NCSF", cuda, torch.float64, mode="default")
+    for p in flow.parameters():
+        p.requires_grad_(False)
+    ps = PhaseSpace(13000, [21, 21], [25, 6, -6, 21], dev=cuda)
+    B, P = 64, 3
+    g = torch.Generator().manual_seed(2)
+    r = torch.rand(B, 10, generator=g, dtype=torch.float64).clamp_(1e-3, 1 - 1e-3).to(cuda).requires_grad_(True)
+    x = (0.5 * torch.randn(B, P, 2, generator=g)).to(cuda, torch.float64)
+    c = torch.randn(B, P, 8, generator=g).to(cuda, torch.float64)
+    ev, mom, w = event_log_prob(ps, flow, r, x, c)
+    assert ev.shape == (B,) and ev.requires_grad
+    ev.sum().backward()
+    assert r.grad is not None and torch.isfinite(r.grad).all() and r.grad.abs().sum() > 0

@@ -278,8 +278,14 @@ def test_get_ps_from_lab_frame_golden(cuda, golden_dir, dtype):
     cmn = cm.double().cpu().numpy()
     nan_ref = np.isnan(g["lab_cm"]).any(axis=(1, 2))
     assert nan_ref.sum() > 0 and np.array_equal(np.isnan(cmn).any(axis=(1, 2)), nan_ref)
-    E = np.abs(g["lab_cm"][~nan_ref][..., 0:1])
-    assert (np.abs(cmn[~nan_ref] - g["lab_cm"][~nan_ref]) / E).max() < (1e-10 if dtype == torch.float64 else 2e-6)
+    if dtype == torch.float64:
+        E = np.abs(g["lab_cm"][~nan_ref][..., 0:1])
+        assert (np.abs(cmn[~nan_ref] - g["lab_cm"][~nan_ref]) / E).max() < 1e-10
+    else:
+        # fp32 inputs: the lab-frame momenta carry TeV-scale longitudinal components, whose fp32 rounding (6e-5 GeV)
+        # is what survives the boost -- the natural scale is the largest lab component of the event, not the particle
+        scale = np.abs(g["lab"][~nan_ref]).max(axis=(1, 2))[:, None, None]
+        assert (np.abs(cmn[~nan_ref] - g["lab_cm"][~nan_ref]) / scale).max() < 1e-6
     ok = ~g["lab_mask"]
     if dtype == torch.float64:
         assert np.array_equal(mask.cpu().numpy(), g["lab_mask"])
@@ -290,9 +296,10 @@ def test_get_ps_from_lab_frame_golden(cuda, golden_dir, dtype):
         from memflow_msci_project_b200.phasespace import utils as pu
         cm2 = pu.boost_tt(lab, -pu.boostVector_t(bfix).unsqueeze(1))
         ps2, _, mask2 = Compute_ParticlesTensor.get_PS(cm, bfix)
-        assert torch.equal(mask, mask2) and torch.equal(ps_, ps2)
+        assert torch.equal(mask, mask2) and torch.equal(torch.nan_to_num(ps_, nan=-7.0), torch.nan_to_num(ps2, nan=-7.0))
         fin = torch.isfinite(cm2).all(-1).all(-1)
-        assert ((cm[fin] - cm2[fin]).abs() / cm2[fin][..., 0:1].abs()).max().item() < 2e-6
+        ev_scale = lab[fin].abs().amax(dim=(1, 2), keepdim=True)   # fp32 torch boost of TeV-scale components vs fp64 in-kernel
+        assert ((cm[fin] - cm2[fin]).abs() / ev_scale).max().item() < 2e-6
     # the unfused composition of the product helpers gives the same answer as the fused launch (fp64: to rounding)
     if dtype == torch.float64:
         from memflow_msci_project_b200.phasespace import utils as pu

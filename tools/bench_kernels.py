@@ -67,6 +67,9 @@ def main():
                       base=flows.DiagNormal, base_args=[torch.zeros(3), 0.35 * torch.ones(3)], univariate_kwargs={"bound": 1.0}), 4_000_000),
         "UF": (dict(features=10, context=16, transforms=6, bins=40, hidden_features=[512] * 2, passes=2, randperm=True,
                     base=flows.DiagNormal, base_args=[torch.zeros(10), 0.35 * torch.ones(10)], univariate_kwargs={"bound": 1.1}), 500_000),
+        # the most frequent unfolding-flow shape of the reference's configs
+        "UF-common": (dict(features=10, context=32, transforms=10, bins=35, hidden_features=[128] * 4, passes=2, randperm=True,
+                           base=flows.DiagNormal, base_args=[torch.zeros(10), 0.3 * torch.ones(10)], univariate_kwargs={"bound": 1.5}), 1_000_000),
         "TF-1D": (dict(features=1, context=66, transforms=5, bins=16, hidden_features=[256] * 3, passes=1,
                        base=flows.BoxUniform, base_args=[-torch.ones(1), torch.ones(1)], univariate_kwargs={"bound": 1.0}), 2_000_000),
     }
@@ -85,7 +88,7 @@ def main():
                                  ("tc_bf16", flows.modules.GEMM_TC_BF16), ("mma_3xf16", flows.modules.GEMM_MMA_3XF16)):
                 if gmode in (flows.modules.GEMM_TC_3XF16, flows.modules.GEMM_TC_BF16) and max(H) > 128:
                     continue
-                if gmode == flows.modules.GEMM_MMA_3XF16 and name not in ("UF", "TF-1D", "TF-A"):
+                if gmode == flows.modules.GEMM_MMA_3XF16 and name not in ("UF", "TF-1D", "TF-A", "UF-common"):
                     continue
                 flow.gemm = gmode
                 ms = timeit(lambda: flow(c).log_prob(x), reps=5)
@@ -97,9 +100,9 @@ def main():
             nz = torch.randn(n_obj, D, device=dev)
             for gname, gmode in (("exact", flows.modules.GEMM_EXACT), ("tc_3xf16", flows.modules.GEMM_TC_3XF16),
                                  ("mma_3xf16", flows.modules.GEMM_MMA_3XF16)):
-                if gmode == flows.modules.GEMM_TC_3XF16 and (max(H) > 128 or K > 32):
+                if gmode == flows.modules.GEMM_TC_3XF16 and max(H) > 128:
                     continue
-                if gmode == flows.modules.GEMM_MMA_3XF16 and name not in ("UF", "TF-1D", "TF-A"):
+                if gmode == flows.modules.GEMM_MMA_3XF16 and name not in ("UF", "TF-1D", "TF-A", "UF-common"):
                     continue
                 flow.gemm = gmode
                 ms = timeit(lambda: flow(c).sample_from_noise(nz), reps=3)
@@ -107,6 +110,17 @@ def main():
                 res.append(dict(kernel=f"flow sample {name} fp32 {gname} (passes={kw['passes']})", objects=n_obj, ms=ms,
                                 objects_per_s=n_obj / (ms * 1e-3), achieved_tflops=tf, tensor_frac=tf / TF))
             flow.gemm = flows.modules.GEMM_EXACT
+            # fp64 flows (103 of the reference's 106 training configs run in float64): flow_kernel<double> on the fp64 pipe
+            if name in ("TF-A", "UF-common"):
+                n64 = n_obj // 8
+                f64 = flows.NSF(**kw).to(dev).double()
+                x64, c64 = x[:n64].double(), c[:n64].double()
+                ms = timeit(lambda: f64(c64).log_prob(x64), reps=3)
+                tf = fl_obj * n64 / (ms * 1e-3) / 1e12
+                res.append(dict(kernel=f"flow log_prob {name} fp64 exact (flow_kernel<double>)", objects=n64, ms=ms,
+                                objects_per_s=n64 / (ms * 1e-3), flops_per_object=fl_obj, achieved_tflops=tf,
+                                tensor_frac=tf / 40.0, note="fraction of the nominal 40 TFLOP/s fp64 (no measured fp64 peak)"))
+                del f64, x64, c64
         del x, c, flow
     # ---------------- standalone spline on materialised parameters (HBM-bound)
     if args.only in ("all", "rqs", "flow"):

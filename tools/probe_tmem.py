@@ -12,7 +12,7 @@ names = {1: "ld", 2: "st", 4: "split-arith", 8: "+MMAs"}
 for variant in (1, 2, 3, 4, 5, 7, 9, 10, 11, 15):
     out = torch.zeros(64, device=dev)
     for rep in range(2):
-        rc = _cabi.probe_lib().mf_tc_probe_gemm(_cabi._ptr(a), _cabi._ptr(w), _cabi._ptr(out), ctypes.c_int32(200), ctypes.c_int32(16),
+        rc = _cabi.probe_lib().mf_tc_probe_gemm(_cabi._ptr(a), _cabi._ptr(w), _cabi._ptr(out), ctypes.c_int32(208), ctypes.c_int32(16),
                                                 ctypes.c_int32(400 + variant), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
         assert rc == 0, _cabi.probe_lib().mf_last_error()
     torch.cuda.synchronize()

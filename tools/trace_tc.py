@@ -32,7 +32,7 @@ ev = [e for e in ev if abs(e[0] - med) < 10 ** 9]
 t0 = ev[0][0]
 # id = warp * 1000 + code * 20 + job (flow_tc.cu, MF_TRACE).  One column per traced warp: the issuer (warp 1), then the
 # four epilogue warps of tile slot 0 (warps 0-3) and of slot 1 (warps 4-7).
-CODES = {1: "W", 2: "rdy", 3: "iss", 5: "wait", 6: "full", 7: "done", 8: "tile", 9: "staged"}
+CODES = {1: "W", 2: "rdy", 3: "iss", 4: "st", 5: "wait", 6: "full", 7: "done", 8: "tile", 9: "staged"}
 cols = [9, 0, 1, 2, 3, 4, 5, 6, 7]
 print("# clk | issuer (job = 2*ji + slot) | slot 0 warps 0 1 2 3 | slot 1 warps 4 5 6 7   [W weights landed, rdy deps met, iss issued;")
 print("#       wait = waiting for the accumulator, full = accumulator complete, done = epilogue finished and arrived]")
