@@ -99,11 +99,18 @@ class FlatInvertiblePhasespace(VirtualPhaseSpaceGenerator):
 
     def _fold(self):
         if self._pending_flags:
-            # OR of all flag words, bit by bit (max of a masked word = that bit, if any event has it)
-            bits = [torch.stack([(f & b).max() if f.numel() else f.new_zeros(()) for f in self._pending_flags]).max()
-                    for b in (_cabi.MF_FLAG_NAN_INPUT, _cabi.MF_FLAG_NOT_CM, _cabi.MF_FLAG_BELOW_THRESHOLD)]
-            word = bits[0] | bits[1] | bits[2]
-            self._folded_flags = word if self._folded_flags is None else (self._folded_flags | word)
+            # OR of all flag words, bit by bit: amax over events of (word & bit) is that bit if any event carries it
+            dev = self._pending_flags[0].device
+            bits = torch.tensor([_cabi.MF_FLAG_NAN_INPUT, _cabi.MF_FLAG_NOT_CM, _cabi.MF_FLAG_BELOW_THRESHOLD],
+                                dtype=torch.int32, device=dev)
+            word = None
+            for f in self._pending_flags:
+                if f.numel() == 0:
+                    continue
+                m = (f.unsqueeze(1) & bits).amax(0).sum()   # the three bits are disjoint: their sum is their OR
+                word = m if word is None else (word | m)
+            if word is not None:
+                self._folded_flags = word if self._folded_flags is None else (self._folded_flags | word)
             self._pending_flags = []
 
     def raise_if_flagged(self):

@@ -138,14 +138,16 @@ def test_gemm_auto_resolution_table():
     assert tfa.gemm == fm.GEMM_AUTO                                         # the default
     assert tfa.effective_gemm(f32) == fm.GEMM_TC_3XF16
     assert tfa.effective_gemm(f32, sampling=True) == fm.GEMM_TC_3XF16
-    assert tfa.effective_gemm(f32, ctx_group=8) == fm.GEMM_MMA_3XF16        # context grouping: not in the tcgen05 kernel
+    assert tfa.effective_gemm(f32, ctx_group=8) == fm.GEMM_TC_3XF16         # context grouping: in the tcgen05 kernel too (r2)
+    noclip = mk(features=3, context=65, transforms=2, bins=16, hidden_features=[128] * 4, univariate_kwargs={"slope": None})
+    assert noclip.effective_gemm(f32) == fm.GEMM_MMA_3XF16                  # no soft clip: not in the tcgen05 kernel
     assert tfa.effective_gemm(f64) == fm.GEMM_EXACT
     assert uf.effective_gemm(f32) == fm.GEMM_MMA_3XF16 and uf.effective_gemm(f32, sampling=True) == fm.GEMM_MMA_3XF16
     assert tf1d.effective_gemm(f32) == fm.GEMM_MMA_3XF16
     assert huge.effective_gemm(f32) == fm.GEMM_EXACT                        # wider than 512
     assert manybins.effective_gemm(f32) == fm.GEMM_EXACT                    # 3K-1 > 128
-    tfa.gemm = fm.GEMM_TC_3XF16                                             # asked for explicitly: falls to the parity anchor
-    assert tfa.effective_gemm(f32, ctx_group=8) == fm.GEMM_EXACT
+    noclip.gemm = fm.GEMM_TC_3XF16                                          # asked for explicitly: falls to the parity anchor
+    assert noclip.effective_gemm(f32) == fm.GEMM_EXACT
 
 
 def test_gemm_constants_match_header():
