@@ -53,7 +53,7 @@ namespace {
 #define MF_TRACE(cond, code, job) do { } while (0)
 #endif
 
-constexpr int kTcThreads = 10 * 32;              // 8 epilogue warps + loader + MMA issuer
+constexpr int kTcThreads = 11 * 32;              // 8 epilogue warps + loader + one MMA issuer per tile slot
 constexpr int kLoaderWarp = 8, kIssuerWarp = 9;
 constexpr int kMaxStages = 8;                   // weight ring depth: as many as fit next to the layer-0 operands
 constexpr int kMaxJobs = 40;
@@ -97,6 +97,7 @@ struct TcLayout {
   long long t_stride;    // bytes per transform (weights)
   long long bias_off;    // byte offset of the fp32 bias region in the blob
   int bias_stride;       // floats per transform
+  double slope;          // soft-clip slope: the last-layer biases are stored pre-scaled by the soft-clip factors
   TcJob job[kMaxJobs];
 };
 
@@ -106,6 +107,7 @@ int make_tc_layout(const mf_flow_desc& d, int gemm, TcLayout* L) {
   MF_REQUIRE(d.transforms >= 1 && d.transforms <= MF_MAX_TRANSFORMS, "bad transforms");
   MF_REQUIRE(d.n_hidden >= 1 && d.n_hidden <= MF_MAX_HIDDEN_LAYERS, "bad n_hidden");
   L->D = d.features; L->C = d.context; L->K = d.bins; L->T = d.transforms; L->L = d.n_hidden;
+  L->slope = d.slope;
   L->nsplit = (gemm == MF_GEMM_TC_3XF16) ? 3 : 1;
   L->Kp = round_up(d.bins, 8);
   L->PFt = 3 * L->Kp;
@@ -239,6 +241,12 @@ __global__ void flow_tc_pack_kernel(TcLayout L, TcPackArgs<T> a, unsigned char* 
       if (k == 0) {
         float bv = 0.f;
         if (src_row >= 0) bv = (float)a.b[j.layer][src_row];
+        if (j.last) {
+          // the spline works on logits pre-multiplied by 2 / ln(slope) (widths, heights) or 1 / ln(slope) (derivatives,
+          // spline_reg.cuh): accumulator * inv + bias * inv, with the second product done here once
+          const RqsScaled cf = make_rqs_scaled(L.K, 0, 1.0, L.slope);
+          bv *= (((n % L.PFt) / L.Kp) == 2) ? cf.inv1 : cf.inv2;
+        }
         bias_t[j.b_off + n] = bv;
       }
     }
@@ -297,13 +305,22 @@ __device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar, int lane) {
 
 // Spline of one feature with its 3K-1 unconstrained parameters in TMEM (this thread's lane): columns [0,K) widths,
 // [KP,KP+K) heights, [2KP, 2KP+K-1) derivatives (KP = 8 NCH; padded columns hold exact zeros).
-// sb: the parameters' biases in shared memory in the same column layout, PRE-SCALED by the soft-clip factors
-// (widths / heights by inv2, derivatives by inv1), so that accumulator * inv + sb is the scaled logit of spline_reg.cuh.
+// sb: the parameters' biases in shared memory in the same column layout, PRE-SCALED at pack time by the soft-clip
+// factors (widths / heights by inv2, derivatives by inv1), so that accumulator * inv + sb is the scaled logit of
+// spline_reg.cuh.  (Reading them straight from the blob with ld.global.nc was measured slower, r2v: this kernel's
+// shared-memory footprint leaves ~4 KB of L1, so every such load is an L2 round trip.)
 __device__ __forceinline__ void tmem_ld8_raw(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr)
                : "memory");
+}
+
+// one aligned 32-byte sector of read-only global memory (SASS LDG.E.256.CONSTANT)
+__device__ __forceinline__ void ldg256(const float* p, float* v) {
+  asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+      : "l"(p));
 }
 
 // 8 accumulator columns -> scaled logits: acc * inv + sb, two columns per FFMA2
@@ -363,6 +380,79 @@ __device__ __forceinline__ void split_f16_pair(float2 v, uint32_t& hi, uint32_t&
   const __half2 l = __floats2half2_rn(l2.x, l2.y);
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// ReLU + split in two conversions: hi = rz(max(u, 0)), lo = rn(max(u - hi, 0)).  Rounding hi TOWARDS ZERO makes the
+// remainder of a positive u non-negative, so the ReLU of both halves rides on the conversions (`cvt.*.relu`) and the
+// two FMNMX per pair disappear (a negative u gives hi = 0 and a negative remainder, which the second ReLU clears).
+// |u - hi - lo| <= 2^-21 |u| (one bit more than the round-to-nearest split): still fp32-class.
+// The remainder u - hi is one mixed-precision FMA per value (`fma.rn.f32.f16`: fp16 x fp16 + fp32 -> SASS FHFMA with a
+// half selector on the packed hi register), exact in fp32: four instructions per PAIR of values in all.
+__device__ __forceinline__ void split_relu_f16_pair(float2 u, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rz.relu.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(u.y), "f"(u.x));
+  float l0, l1;
+  asm("{\n"
+      ".reg .b16 h0, h1, m1;\n"
+      "mov.b32 {h0, h1}, %2;\n"
+      "mov.b16 m1, 0xBC00;\n"  // -1.0 in fp16
+      "fma.rn.f32.f16 %0, h0, m1, %3;\n"
+      "fma.rn.f32.f16 %1, h1, m1, %4;\n"
+      "}\n"
+      : "=f"(l0), "=f"(l1)
+      : "r"(hi), "f"(u.x), "f"(u.y));
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(l1), "f"(l0));
+}
+__device__ __forceinline__ uint32_t pack_relu_bf16(float2 u) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(u.y), "f"(u.x));
+  return r;
+}
+
+// Hidden-layer epilogue of one warp, full-width layer (N = 128): accumulator columns -> + bias -> ReLU -> operand planes.
+// Straight-line code (no loop control, immediate TMEM offsets) and software-pipelined: the TMEM loads of column block
+// b + 1 are issued BEFORE the arithmetic of block b, so the TMEM round trip hides behind ~130 instructions.  The static
+// schedule of the rolled version was 310 issue cycles + ~165 cycles of exposed TMEM / shared-memory latency per 32
+// columns (190 instructions, 62 of them loop control, address moves and uniform-register transfers).
+template <int NSPLIT>
+__device__ __forceinline__ void hidden_epilogue_128(uint32_t taddr, const float* sb) {
+  float v[2][32];
+  tc::tmem_ld16(taddr, v[0]);
+  tc::tmem_ld16(taddr + 16, v[0] + 16);
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    float4 bb[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) bb[i] = *reinterpret_cast<const float4*>(sb + 32 * b + 4 * i);
+    tc::tmem_ld_wait();  // block b has landed
+    if (b + 1 < 4) {     // next block: in flight during this block's arithmetic
+      tc::tmem_ld16(taddr + 32 * (b + 1), v[(b + 1) & 1]);
+      tc::tmem_ld16(taddr + 32 * (b + 1) + 16, v[(b + 1) & 1] + 16);
+    }
+    const float* vb = v[b & 1];
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      float2 w2[8];
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) {
+        const float4 b4 = bb[hf * 4 + i / 4];
+        w2[i / 2] = f2_add(make_float2(vb[hf * 16 + i], vb[hf * 16 + i + 1]), make_float2(b4.x, b4.y));
+        w2[i / 2 + 1] = f2_add(make_float2(vb[hf * 16 + i + 2], vb[hf * 16 + i + 3]), make_float2(b4.z, b4.w));
+      }
+      const uint32_t c0 = (uint32_t)(32 * b + 16 * hf);
+      if (NSPLIT == 3) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) split_relu_f16_pair(w2[i], hi[i], lo[i]);
+        tc::tmem_st8(taddr + 128 + c0 / 2, hi);
+        tc::tmem_st8(taddr + 192 + c0 / 2, lo);
+      } else {
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pk[i] = pack_relu_bf16(w2[i]);
+        tc::tmem_st8(taddr + 128 + c0 / 2, pk);
+      }
+    }
+  }
 }
 
 // tcgen05.mma under a (uniform) enable predicate: the tail k-steps of a job are switched off without branches.
@@ -490,7 +580,11 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
   const uint32_t kStages = (uint32_t)L.stages;
   __shared__ __align__(8) uint64_t w_full[kMaxStages], w_empty[kMaxStages], a_ready[2], acc_full[2][2], acc_free[2][2], acc_hid[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ uint32_t issue_lock;  // one MMA batch at a time enters the tensor core's queue
   __shared__ __align__(16) float sbias[8][2][128];  // [epilogue warp][job parity][column]: every warp stages its own copy
+  // what an epilogue warp needs to know about job ji, one 16-byte shared-memory load instead of a chain of indexed
+  // parameter-bank loads per job (x = N | last << 8 | region << 9 | nfeat << 16 | feat0 << 24, y = acc_col, z = b_off)
+  __shared__ uint4 epi_s[kMaxJobs];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long n = args.n;
@@ -511,7 +605,8 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
   };
 
   if (tid == 0) {
-    for (int s = 0; s < kMaxStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 2); }  // released by both issuers
+    issue_lock = 0u;
     for (int t = 0; t < 2; ++t) {
       mbar_init(&a_ready[t], 128);
       for (int r = 0; r < 2; ++r) { mbar_init(&acc_full[t][r], 1); mbar_init(&acc_free[t][r], 128); }
@@ -520,6 +615,12 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
       mbar_init(&acc_hid[t], 1);
     }
     fence_mbar_init();
+  }
+  if (tid < L.njobs) {
+    const TcJob& j = L.job[tid];
+    epi_s[tid] = make_uint4((uint32_t)j.N | ((uint32_t)j.last << 8) | ((uint32_t)j.region << 9) | ((uint32_t)j.nfeat << 16) |
+                                ((uint32_t)j.feat0 << 24),
+                            (uint32_t)j.acc_col, (uint32_t)j.b_off, 0u);
   }
   if (warp == kIssuerWarp) tc::tmem_alloc(&tmem_base_s, 512);
   // job packets of every (transform, job), built once per CTA by all threads (the tensor pipe idles for ~1000 cycles per
@@ -580,19 +681,24 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
         }
       }
     }
-  } else if (warp == kIssuerWarp) {
-    // ===================== MMA issuer =====================
-    // One warp walks the (warp-uniform) schedule and waits on the barriers; per K-block one elected lane issues
-    // the MMAs back to back.  The two tile slots take turns job by job (slot 0's job j, slot 1's job j, slot 0's
-    // job j+1, ...): while one slot's MMAs occupy the tensor pipe the other slot's epilogue drains its accumulator.
-    // Dependencies of a job: a hidden layer (and the first last-layer chunk of a unit) waits for its A operand
-    // (a_ready: every thread of the slot has finished the previous epilogue, so the accumulator is drained as well);
-    // a later last-layer chunk waits until the previous chunk in ITS accumulator region has been consumed (acc_free).
+  } else if (warp == kIssuerWarp || warp == kIssuerWarp + 1) {
+    // ===================== MMA issuers: one warp per tile slot =====================
+    // Each issuer walks the (warp-uniform) job schedule for ITS tile slot: wait for the job's weight stages, for the
+    // slot's dependencies (a hidden layer and the first last-layer chunk of a unit wait for the A operand -- a_ready:
+    // every thread of the slot has finished the previous epilogue, so the accumulator is drained as well; a later
+    // last-layer chunk waits until the previous chunk in ITS accumulator region has been consumed -- acc_free), then ONE
+    // elected lane takes the submission lock and issues the MMAs of the whole job back to back.  The lock keeps the
+    // batches of the two slots from interleaving in the tensor core's queue (interleaved, both accumulators complete at
+    // the same time, both epilogues run at once and the pipe idles meanwhile); everything else an issuer does per job --
+    // ~200 dependent scalar instructions, 600-1400 cycles of a single warp (per-warp traces r2m, r2s) -- now overlaps the
+    // OTHER slot's batch instead of sitting between two batches.  A weight stage is released by the commits of both
+    // issuers (w_empty counts 2).
+    const int t = warp - kIssuerWarp;
     uint32_t stage = 0, sphase = 0;  // ring position / phase of the next weight K-block to consume
-    int trace_n = 0, trace_end = 1500; (void)trace_n; (void)trace_end;
-    uint32_t aph0 = 0, aph1 = 0;               // a_ready phases per slot
-    uint32_t nchunk0 = 0, nchunk1 = 0;         // last-layer chunks issued so far per region (both slots walk the same jobs)
-    struct JobRef { long long p; int unit, nact; };
+    int trace_n = t * 750, trace_end = trace_n + 750; (void)trace_n; (void)trace_end;
+    uint32_t aph = 0;                          // a_ready phase of the slot
+    uint32_t nchunk0 = 0, nchunk1 = 0;         // last-layer chunks issued so far per accumulator region
+    struct JobRef { long long p; int unit; };
     // advance (p, unit, ji) to the next job that is executed; false after the last one of this CTA
     auto next_job = [&](long long& p_, int& unit_, int& ji_) -> bool {
       for (;;) {
@@ -606,7 +712,6 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
     };
     auto prepare = [&](JobPkt& q, JobRef& r, long long p_, int unit_, int ji_) {
       r.p = p_; r.unit = unit_;
-      r.nact = (2 * p_ + 1 < n_tiles) ? 2 : 1;  // odd tile count: slot 1 idles in the last pair
       const int tr = inverse ? (L.T - 1 - unit_ / sweeps) : unit_;
       if (L.pkt_table) {
         const uint4* src = reinterpret_cast<const uint4*>(pkt_s + tr * L.njobs + ji_);
@@ -630,30 +735,11 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
     long long jp = blockIdx.x;
     int junit = 0, jji = -1;
     bool have = (jp < n_pairs) && next_job(jp, junit, jji);
-    if (have) prepare(cur, rcur, jp, junit, jji);
+    if (have) { prepare(cur, rcur, jp, junit, jji); pin(cur); }
     bool first_last = true;          // the first EXECUTED last-layer chunk of a unit waits for the last hidden activations
     int in_unit0 = 0, in_unit1 = 0;  // chunks of the current unit issued per region
     long long key_p = -1;
     int key_unit = -1;
-    // ring stages of a job's (at most two) weight K-blocks: wait until they have landed, return their addresses and
-    // advance the ring position
-    uint32_t wb0 = 0, wb1 = 0, cs0 = 0, cs1 = 0;  // current job: stage addresses and stage indices
-    auto take_stages = [&](const JobPkt& q, uint32_t& b0_, uint32_t& b1_, uint32_t& s0_, uint32_t& s1_) {
-      s0_ = stage;
-      const uint32_t ph0 = sphase;
-      if (++stage == kStages) { stage = 0; sphase ^= 1; }
-      s1_ = stage;
-      mbar_wait(&w_full[s0_], ph0);
-      b0_ = smem_u32(w_ring + s0_ * kStageBytes);
-      if (q.nst > 1) {
-        mbar_wait(&w_full[s1_], sphase);
-        if (++stage == kStages) { stage = 0; sphase ^= 1; }
-        b1_ = smem_u32(w_ring + s1_ * kStageBytes);
-      } else {
-        b1_ = b0_ + kParts * (uint32_t)q.N * 128u;  // both K-blocks of a narrow job share the stage
-      }
-    };
-    if (have) take_stages(cur, wb0, wb1, cs0, cs1);
     while (have) {
       if (rcur.p != key_p || rcur.unit != key_unit) {  // a new unit starts
         key_p = rcur.p; key_unit = rcur.unit;
@@ -662,6 +748,7 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
       const int ji = cur.ji;
       const int jreg = cur.reg;
       const bool two = cur.nst > 1;
+      const bool active = (t == 0) || (2 * rcur.p + 1 < n_tiles);  // odd tile count: slot 1 idles in the last pair
       const bool wait_a = cur.last ? first_last : true;
       const bool wait_free = cur.last && (jreg ? in_unit1 : in_unit0) > 0;
       const uint32_t free_par = ((jreg ? nchunk1 : nchunk0) - 1) & 1;  // phase of the previous chunk of this region
@@ -669,50 +756,60 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
         first_last = false;
         if (jreg) { ++in_unit1; ++nchunk1; } else { ++in_unit0; ++nchunk0; }
       }
-      MF_TRACE(lane == 0, 1, 2 * ji);
-      bool have_next = false, early_take = false;
-      uint32_t nb0 = 0, nb1 = 0, ns0 = 0, ns1 = 0;
-      for (int t = 0; t < rcur.nact; ++t) {
+      // ring stages of the job's (at most two) weight K-blocks: wait until they have landed, advance the ring position
+      const uint32_t cs0 = stage, ph0 = sphase;
+      if (++stage == kStages) { stage = 0; sphase ^= 1; }
+      uint32_t cs1 = cs0;
+      mbar_wait(&w_full[cs0], ph0);
+      const uint32_t wb0 = smem_u32(w_ring + cs0 * kStageBytes);
+      uint32_t wb1;
+      if (two) {
+        cs1 = stage;
+        mbar_wait(&w_full[cs1], sphase);
+        if (++stage == kStages) { stage = 0; sphase ^= 1; }
+        wb1 = smem_u32(w_ring + cs1 * kStageBytes);
+      } else {
+        wb1 = wb0 + kParts * (uint32_t)cur.N * 128u;  // both K-blocks of a narrow job share the stage
+      }
+      MF_TRACE(lane == 0, 1, ji);
+      if (active) {
         const uint32_t d_tmem = tmem + (uint32_t)(t * 256) + cur.col;
         const uint32_t a_tmem = tmem + (uint32_t)(t * 256) + 128;  // hi plane; lo plane 64 columns further
         const uint32_t a_base = smem_u32(a_buf + (size_t)t * kParts * kPlane);
         if (wait_a) {
-          mbar_wait(&a_ready[t], t ? aph1 : aph0);
-          if (t) aph1 ^= 1; else aph0 ^= 1;
+          mbar_wait(&a_ready[t], aph);
+          aph ^= 1;
         }
         if (wait_free) mbar_wait(&acc_free[t][jreg], free_par);
-        MF_TRACE(lane == 0, 2, 2 * ji + t);
+        MF_TRACE(lane == 0, 2, ji);
         tc::fence_after_thread_sync();
         if (tc::elect_one()) {
-          // the last slot releases the stages: the first one right after its k-steps when the job spans two stages
-          const bool release = (t == rcur.nact - 1);
-          uint64_t* e0 = (release && two) ? &w_empty[cs0] : nullptr;
-          uint64_t* e1 = release ? (two ? &w_empty[cs1] : &w_empty[cs0]) : nullptr;
+          while (atomicCAS(&issue_lock, 0u, 1u) != 0u) __nanosleep(64);
+          // both issuers commit to the stage barriers: the first stage right after its k-steps when the job spans two
+          uint64_t* e0 = two ? &w_empty[cs0] : nullptr;
+          uint64_t* e1 = &w_empty[cs1];
           if (ji == 0)
             issue_job_ss<NSPLIT>(cur, d_tmem, a_base, a_base + kPlane, wb0, wb1, e0, e1, &acc_hid[t]);
           else
             issue_job_ts<NSPLIT>(cur, d_tmem, a_tmem, wb0, wb1, e0, e1, cur.last ? &acc_full[t][jreg] : &acc_hid[t]);
+          atomicExch(&issue_lock, 0u);
         }
         __syncwarp();
-        MF_TRACE(lane == 0, 3, 2 * ji + t);
-        if (t == 0) {
-          // everything of the NEXT job that does not depend on the epilogues happens here, while the MMAs just issued
-          // execute (a dozen of them sit in the tensor core's queue): its packet, the wait for its weight stages
-          have_next = next_job(jp, junit, jji);
-          if (have_next) {
-            prepare(nxt, rnxt, jp, junit, jji);
-            // (only when the ring holds both jobs: otherwise the next job's stages are released by THIS job's last slot)
-            early_take = false;  // (taking the next job's stages here measured slower)
-            if (early_take) take_stages(nxt, nb0, nb1, ns0, ns1);
-            pin(nxt);
-          }
-        }
+        MF_TRACE(lane == 0, 3, ji);
+      } else if (lane == 0) {
+        // idle slot of the last pair: keep the weight ring moving (the stage was seen full above, so this arrival belongs
+        // to the same use of the stage as the other issuer's commit)
+        if (two) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&w_empty[cs0])) : "memory");
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&w_empty[cs1])) : "memory");
       }
-      if (have_next && !early_take) take_stages(nxt, nb0, nb1, ns0, ns1);
-      cur = nxt;
-      rcur = rnxt;
-      wb0 = nb0; wb1 = nb1; cs0 = ns0; cs1 = ns1;
-      have = have_next;
+      // the next job's packet: prepared while the MMAs just issued (or the other slot's) execute
+      have = next_job(jp, junit, jji);
+      if (have) {
+        prepare(nxt, rnxt, jp, junit, jji);
+        pin(nxt);
+        cur = nxt;
+        rcur = rnxt;
+      }
     }
   } else {
     // ===================== epilogue groups =====================
@@ -739,12 +836,21 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
     // Soft-clip scale of the last-layer columns (same column layout in every chunk): the spline works on logits
     // pre-multiplied by 2 / ln(slope) (widths, heights) or 1 / ln(slope) (derivatives); a 4-aligned group of columns
     // never straddles a segment (segments are multiples of 8 columns wide).
-    const float bscale_last = (((4 * lane) % L.PFt) / L.Kp == 2) ? cf.inv1 : cf.inv2;
     float* const sb_warp = &sbias[warp][0][0];
     uint32_t jobctr = 0;                      // bias double-buffer parity
     uint32_t fh0 = 0, fh1 = 0;   // hidden-layer accumulator completions seen so far, per slot (every warp waits for all)
     uint32_t fo0 = 0, fo1 = 0;   // last-layer chunk completions of the warp's OWN slot, per accumulator region
     int trace_n = 1500 + warp * 300, trace_end = trace_n + 300; (void)trace_n; (void)trace_end;
+
+    struct EpiJob { int N, last, region, nfeat, feat0, acc_col, b_off; };
+    auto epi_job = [&](int ji_) -> EpiJob {
+      const uint4 r = epi_s[ji_];
+      EpiJob e;
+      e.N = (int)(r.x & 0xFFu); e.last = (int)((r.x >> 8) & 1u); e.region = (int)((r.x >> 9) & 1u);
+      e.nfeat = (int)((r.x >> 16) & 0xFFu); e.feat0 = (int)(r.x >> 24); e.acc_col = (int)r.y; e.b_off = (int)r.z;
+      return e;
+    };
+    const int njobs = L.njobs, nhid = L.L, bias_stride = L.bias_stride, PFt = L.PFt;
 
     auto put1 = [&](int r, int k, float v) {
       const uint32_t off = in0_offset(r, k);
@@ -757,6 +863,11 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
       }
     };
 
+    // context staging: chunk index gt of a tile is chunk c_first of row r_first, GT chunks further is (step_r, step_c) on
+    const int nchunk = xcol0 >> 3;  // 16-byte operand chunks per row (the last one zero-padded when C % 8 != 0)
+    const int nchunk_d = nchunk > 0 ? nchunk : 1;  // (no context: the staging loop is empty)
+    const int r_first = gt / nchunk_d, c_first = gt - r_first * nchunk_d;
+    const int step_r = GT / nchunk_d, step_c = GT - step_r * nchunk_d;
     for (long long p = blockIdx.x; p < n_pairs; p += gridDim.x) {
       const long long tile = 2 * p + t;
       if (tile >= n_tiles) break;  // odd tile count: slot 1 idles in the last pair (the MMA warp skips it too)
@@ -789,6 +900,7 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
             }
           }
         }
+        MF_TRACE(lane == 0, 10, 0);
         // ---- stage (ctx | 0) of the layer-0 operand once per tile; every MMA that read the previous tile's
         //      operand has retired (this group waited on the last accumulator of that tile)
         {
@@ -796,45 +908,88 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
           for (int k = xcol0 + D; k < kfill; ++k) put1(row, k, 0.f);
           // context: one 16-byte operand chunk (8 columns of one row) per thread and step, four chunks in flight;
           // consecutive threads take consecutive chunks, so a warp reads a contiguous stretch of global memory
-          const int nchunk = xcol0 >> 3;  // chunks per row (the last one zero-padded when C % 8 != 0)
+          // (chunk index -> (row, chunk of the row) advances incrementally by GT chunks per step: the integer divisions
+          // this replaces -- one of them 64-bit, by the runtime ctx_group -- made the staging of a tile cost 12 k cycles,
+          // per-warp trace r2t)
           const int total = 128 * nchunk;
           const int G = args.ctx_group;   // x rows per context row (context hoisted per event in the MEM sweep)
+          const long long crow0 = tile0 / G;               // context row of the tile's first object ...
+          const int crem0 = (int)(tile0 - crow0 * G);      // ... and that object's position inside its group
+          int r_it = r_first, c_it = c_first;              // (row, chunk) of chunk index gt
+          // The 8 floats of a chunk are only 4-byte aligned in global memory (row stride C floats).  They are fetched as
+          // the one or two 32-byte ALIGNED sectors that hold them (ld.global.nc.v8, SASS LDG.256) and shifted into place
+          // with selects: two sector requests per chunk instead of eight scalar loads that each pull the same sectors
+          // from L2 again (this kernel leaves ~4 KB of L1) -- the L2 -> SM sector rate made the staging of a tile pair
+          // cost ~9 k cycles (per-warp traces r2t, r2u).
+          const float* ctx_end = gc + ((n - 1) / G + 1) * (long long)C;
+          MF_TRACE(lane == 0, 11, 0);
           for (int q0 = gt; q0 < total; q0 += 4 * GT) {
-            float v[4][8];
-            int rr[4], kc[4];
+            float w[4][16];
+            int rr[4], kc[4], sh[4];
   #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const int qq = q0 + u * GT;
-              rr[u] = qq / nchunk;
-              kc[u] = qq - rr[u] * nchunk;
+              rr[u] = r_it;
+              kc[u] = c_it;
+              r_it += step_r; c_it += step_c;
+              if (c_it >= nchunk) { c_it -= nchunk; ++r_it; }
               const bool live = (qq < total) && (rr[u] < rows);
-              const float* src = gc + ((tile0 + rr[u]) / G) * C + kc[u] * 8;
+              int crow = rr[u];
+              if (G != 1) crow = (crem0 + rr[u]) / G;
+              const float* src = gc + (crow0 + crow) * C + kc[u] * 8;
+              const int a = (int)((reinterpret_cast<uintptr_t>(src) >> 2) & 7);  // floats past the sector boundary
+              const float* wp = src - a;
+              sh[u] = 0;
   #pragma unroll
-              for (int e = 0; e < 8; ++e) v[u][e] = (live && kc[u] * 8 + e < C) ? __ldg(src + e) : 0.f;
+              for (int e = 0; e < 16; ++e) w[u][e] = 0.f;
+              if (live && wp + 16 <= ctx_end) {
+                sh[u] = a;
+                ldg256(wp, w[u]);
+                if (a) ldg256(wp + 8, w[u] + 8);
+              } else if (live) {  // the last sectors of the tensor: element by element
+  #pragma unroll
+                for (int e = 0; e < 8; ++e) w[u][e] = (kc[u] * 8 + e < C) ? __ldg(src + e) : 0.f;
+              }
             }
   #pragma unroll
             for (int u = 0; u < 4; ++u) {
               if (q0 + u * GT < total) {
                 const int r = rr[u], c8 = kc[u];
+                float v[1][8];
+                {
+                  // v[e] = w[e + sh], sh = 0..7 per lane: three select stages (shift by 4, 2, 1)
+                  const bool s4 = (sh[u] & 4) != 0, s2 = (sh[u] & 2) != 0, s1 = (sh[u] & 1) != 0;
+                  float t4[12], t2[10];
+  #pragma unroll
+                  for (int e = 0; e < 12; ++e) t4[e] = s4 ? w[u][e + 4] : w[u][e];
+  #pragma unroll
+                  for (int e = 0; e < 10; ++e) t2[e] = s2 ? t4[e + 2] : t4[e];
+  #pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    const float x = s1 ? t2[e + 1] : t2[e];
+                    v[0][e] = (c8 * 8 + e < C) ? x : 0.f;  // columns past C belong to the next row
+                  }
+                }
                 const uint32_t off = (c8 * 8 < kfull_cols)
                                          ? (uint32_t)(c8 >> 3) * kKBlockBytes + (uint32_t)r * 128u + (uint32_t)(((c8 & 7) ^ (r & 7)) << 4)
                                          : kFullBytes + (uint32_t)((c8 * 8 - kfull_cols) >> 4) * kTailBytes + (uint32_t)r * 32u +
                                                (uint32_t)(((c8 & 1) ^ ((r >> 2) & 1)) << 4);
                 uint4 hi, lo;
                 if (NSPLIT == 3) {
-                  tc::split_f16(v[u][0], v[u][1], hi.x, lo.x); tc::split_f16(v[u][2], v[u][3], hi.y, lo.y);
-                  tc::split_f16(v[u][4], v[u][5], hi.z, lo.z); tc::split_f16(v[u][6], v[u][7], hi.w, lo.w);
+                  tc::split_f16(v[0][0], v[0][1], hi.x, lo.x); tc::split_f16(v[0][2], v[0][3], hi.y, lo.y);
+                  tc::split_f16(v[0][4], v[0][5], hi.z, lo.z); tc::split_f16(v[0][6], v[0][7], hi.w, lo.w);
                   *reinterpret_cast<uint4*>(a_hi + off) = hi;
                   *reinterpret_cast<uint4*>(a_lo + off) = lo;
                 } else {
-                  hi.x = tc::pack_bf16(v[u][0], v[u][1]); hi.y = tc::pack_bf16(v[u][2], v[u][3]);
-                  hi.z = tc::pack_bf16(v[u][4], v[u][5]); hi.w = tc::pack_bf16(v[u][6], v[u][7]);
+                  hi.x = tc::pack_bf16(v[0][0], v[0][1]); hi.y = tc::pack_bf16(v[0][2], v[0][3]);
+                  hi.z = tc::pack_bf16(v[0][4], v[0][5]); hi.w = tc::pack_bf16(v[0][6], v[0][7]);
                   *reinterpret_cast<uint4*>(a_hi + off) = hi;
                 }
               }
             }
           }
         }
+        MF_TRACE(lane == 0, 12, 0);
         {  // pull this slot's next tile (x rows and context rows) into L2 while this one is being processed
           const long long nt0 = (tile + 2 * (long long)gridDim.x) * 128;
           if (nt0 < n) {
@@ -854,6 +1009,23 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
         if (4 * lane < L.job[0].N)
           bias_next = __ldg(reinterpret_cast<const float4*>(bias_all + (size_t)tr0 * L.bias_stride + L.job[0].b_off) + lane);
       }
+      // biases of the job after (unit_, ji_) -> bias_next (a register per lane; stored to the warp's slot when that job
+      // starts)
+      auto fetch_next_bias = [&](int unit_, int ji_) {
+        int ju = unit_, jn = ji_ + 1;
+        if (jn == njobs) { jn = 0; ++ju; }
+        if (inverse) {
+          while (ju < n_units && !job_live(ju, jn)) {  // next job that is actually executed
+            if (++jn == njobs) { jn = 0; ++ju; }
+          }
+        }
+        if (ju < n_units) {
+          const int trn = inverse ? (L.T - 1 - ju / sweeps) : ju;
+          const EpiJob nj = epi_job(jn);
+          if (4 * lane < nj.N)
+            bias_next = __ldg(reinterpret_cast<const float4*>(bias_all + (size_t)trn * bias_stride + nj.b_off) + lane);
+        }
+      };
       MF_TRACE(lane == 0, 9, 0);
       for (int unit = 0; unit < n_units; ++unit) {
         const int tr = inverse ? (L.T - 1 - unit / sweeps) : unit;
@@ -867,119 +1039,109 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
         //      by this thread when it produced them (tile start / spline output of the previous unit).
         fence_proxy_async_smem();
         mbar_arrive_warp(&a_ready[t], lane);
-        for (int ji = 0; ji < L.njobs; ++ji) {
-          if (!job_live(unit, ji)) continue;
-          const TcJob& j = L.job[ji];
+        // the first spline input of the unit (every input of a unit is known when the unit starts): in flight during the
+        // hidden layers
+        const float* xs = (inverse ? gy : gz) + g * D;
+        float xfirst = valid ? xs[0] : 0.f;  // (chunks hold consecutive features, the first one feature 0)
+        // ---- hidden layers: jobs [0, nhid)
+        for (int ji = 0; ji < nhid; ++ji) {
+          const EpiJob j = epi_job(ji);
           const uint32_t jpar = jobctr & 1;
           ++jobctr;
           // this job's biases -> the warp's shared-memory slot (double-buffered by job parity), overlapping the MMA
           float* sb = sb_warp + jpar * 128;
-          if (4 * lane < j.N) {
-            float4 bv = bias_next;
-            if (j.last) { bv.x *= bscale_last; bv.y *= bscale_last; bv.z *= bscale_last; bv.w *= bscale_last; }
-            reinterpret_cast<float4*>(sb)[lane] = bv;
-          }
-          {
-            int ju = unit, jn = ji + 1;
-            if (jn == L.njobs) { jn = 0; ++ju; }
-            while (ju < n_units && !job_live(ju, jn)) {  // next job that is actually executed
-              if (++jn == L.njobs) { jn = 0; ++ju; }
-            }
-            if (ju < n_units) {
-              const int trn = inverse ? (L.T - 1 - ju / sweeps) : ju;
-              const TcJob& nj = L.job[jn];
-              if (4 * lane < nj.N)
-                bias_next = __ldg(reinterpret_cast<const float4*>(bias_all + (size_t)trn * L.bias_stride + nj.b_off) + lane);
-            }
-          }
+          if (4 * lane < j.N) reinterpret_cast<float4*>(sb)[lane] = bias_next;
+          fetch_next_bias(unit, ji);  // the next executed job's biases, one job ahead
           __syncwarp();
-          if (!j.last) {
-            // Hidden layer: TMEM -> +bias -> ReLU -> fp16 hi/lo operand planes of the next layer (in place).
-            // (Sharing every hidden epilogue between the warps of BOTH slots -- same lane quarter, half the columns each --
-            // shortens one epilogue from ~1900 to ~1300 cycles but was slower overall, 23.5 vs 20.8 ms: with all eight
-            // warps busy the MMA issuer waits even longer for its turn; profiles/trace_flow_tc_r2p.txt.)
-            {
-              const int s_ = t;
-              const bool mine = true;
-              const int half_n = j.N;
-              MF_TRACE(lane == 0, 5, ji);
-              mbar_wait(&acc_hid[s_], (s_ ? fh1 : fh0) & 1);
-              if (s_) ++fh1; else ++fh0;
-              MF_TRACE(lane == 0, 6, ji);
-              tc::fence_after_thread_sync();
-              const uint32_t taddr = tmem + lane_off + (uint32_t)(s_ * 256);
-              const int cb = mine ? 0 : half_n, ce = mine ? half_n : j.N;
-              for (int c00 = cb; c00 < ce; c00 += 32) {
-                float vv[32];
-                tc::tmem_ld16(taddr + c00, vv);
-                if (c00 + 16 < ce) tc::tmem_ld16(taddr + c00 + 16, vv + 16);
-                float4 bb[8];  // the biases travel from shared memory while the TMEM loads are in flight
-#pragma unroll
-                for (int i = 0; i < 8; ++i) bb[i] = *reinterpret_cast<const float4*>(sb + c00 + 4 * i);
-                tc::tmem_ld_wait();
-#pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {
-                  const int c0 = c00 + hf * 16;
-                  if (c0 < ce) {
-                    float* v = vv + hf * 16;
-                    float2 w2[8];
-#pragma unroll
-                    for (int i = 0; i < 16; i += 4) {
-                      const float4 b4 = bb[hf * 4 + i / 4];
-                      float2 u0 = f2_add(make_float2(v[i], v[i + 1]), make_float2(b4.x, b4.y));
-                      float2 u1 = f2_add(make_float2(v[i + 2], v[i + 3]), make_float2(b4.z, b4.w));
-                      w2[i / 2] = make_float2(fmaxf(u0.x, 0.f), fmaxf(u0.y, 0.f));
-                      w2[i / 2 + 1] = make_float2(fmaxf(u1.x, 0.f), fmaxf(u1.y, 0.f));
-                    }
-                    // 16 values -> 8 packed 16-bit pairs per plane -> operand planes in TMEM
-                    if (NSPLIT == 3) {
-                      uint32_t hi[8], lo[8];
-#pragma unroll
-                      for (int i = 0; i < 8; ++i) split_f16_pair(w2[i], hi[i], lo[i]);
-                      tc::tmem_st8(taddr + 128 + c0 / 2, hi);
-                      tc::tmem_st8(taddr + 192 + c0 / 2, lo);
-                    } else {
-                      uint32_t pk[8];
-#pragma unroll
-                      for (int i = 0; i < 8; ++i) pk[i] = tc::pack_bf16(w2[i].x, w2[i].y);
-                      tc::tmem_st8(taddr + 128 + c0 / 2, pk);
-                    }
-                  }
-                }
-              }
-              MF_TRACE(lane == 0, 4, ji);
-              tc::tmem_st_wait();
-              tc::fence_before_thread_sync();
-              mbar_arrive_warp(&a_ready[s_], lane);
-              MF_TRACE(lane == 0, 7, ji);
-              (void)mine;
-            }
-            continue;
-          }
-          // last-layer chunk: only the slot's own warps
-          if (!has_tile) continue;
-          // inputs of this chunk's splines, fetched before the accumulator wait
-          const float* xsrc = (inverse ? gy : gz) + g * D + j.feat0;
-          float xnext = valid ? xsrc[0] : 0.f;
+          // TMEM -> +bias -> ReLU -> fp16 hi/lo operand planes of the next layer (in place).
+          // (Sharing every hidden epilogue between the warps of BOTH slots -- same lane quarter, half the columns each --
+          // was slower overall, 23.5 vs 20.8 ms, profiles/trace_flow_tc_r2p.txt: the epilogue is bound by the issue rate
+          // of its scheduler's ALU / FMA pipes, not by latency.)
           MF_TRACE(lane == 0, 5, ji);
-          mbar_wait(&acc_full[t][j.region], (j.region ? fo1 : fo0) & 1);
-          if (j.region) ++fo1; else ++fo0;
+          mbar_wait(&acc_hid[t], (t ? fh1 : fh0) & 1);
+          if (t) ++fh1; else ++fh0;
           MF_TRACE(lane == 0, 6, ji);
           tc::fence_after_thread_sync();
           const uint32_t taddr = tmem + lane_off + (uint32_t)(t * 256);
-          {
-            // last-layer chunk: splines of the chunk's features straight out of TMEM
-            const unsigned long long fmask = sched ? sched[(size_t)tr * MF_MAX_FEATURES + (unit % sweeps)] : ~0ull;
+          if (j.N == 128) {
+            hidden_epilogue_128<NSPLIT>(taddr, sb);
+          } else {
+            const int ce = j.N;
+            for (int c00 = 0; c00 < ce; c00 += 32) {
+              float vv[32];
+              tc::tmem_ld16(taddr + c00, vv);
+              if (c00 + 16 < ce) tc::tmem_ld16(taddr + c00 + 16, vv + 16);
+              float4 bb[8];  // the biases travel from shared memory while the TMEM loads are in flight
+#pragma unroll
+              for (int i = 0; i < 8; ++i) bb[i] = *reinterpret_cast<const float4*>(sb + c00 + 4 * i);
+              tc::tmem_ld_wait();
+#pragma unroll
+              for (int hf = 0; hf < 2; ++hf) {
+                const int c0 = c00 + hf * 16;
+                if (c0 < ce) {
+                  float* v = vv + hf * 16;
+                  float2 w2[8];
+#pragma unroll
+                  for (int i = 0; i < 16; i += 4) {
+                    const float4 b4 = bb[hf * 4 + i / 4];
+                    w2[i / 2] = f2_add(make_float2(v[i], v[i + 1]), make_float2(b4.x, b4.y));
+                    w2[i / 2 + 1] = f2_add(make_float2(v[i + 2], v[i + 3]), make_float2(b4.z, b4.w));
+                  }
+                  // 16 values -> 8 packed 16-bit pairs per plane -> operand planes in TMEM
+                  if (NSPLIT == 3) {
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) split_relu_f16_pair(w2[i], hi[i], lo[i]);
+                    tc::tmem_st8(taddr + 128 + c0 / 2, hi);
+                    tc::tmem_st8(taddr + 192 + c0 / 2, lo);
+                  } else {
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) pk[i] = pack_relu_bf16(w2[i]);
+                    tc::tmem_st8(taddr + 128 + c0 / 2, pk);
+                  }
+                }
+              }
+            }
+          }
+          MF_TRACE(lane == 0, 4, ji);
+          tc::tmem_st_wait();
+          tc::fence_before_thread_sync();
+          mbar_arrive_warp(&a_ready[t], lane);
+          MF_TRACE(lane == 0, 7, ji);
+        }
+        // ---- last layer: jobs [nhid, njobs), one chunk of features each.  A tight loop: the chunk's biases come straight
+        //      from the blob (pre-scaled at pack time), its record is one shared-memory load, and the first input of the
+        //      NEXT chunk is fetched before this chunk's splines (all inputs of a unit are known when the unit starts).
+        const unsigned long long fmask = sched ? sched[(size_t)tr * MF_MAX_FEATURES + (unit % sweeps)] : ~0ull;
+        const uint32_t taddr = tmem + lane_off + (uint32_t)(t * 256);
+        for (int ji = nhid; ji < njobs; ++ji) {
+          const EpiJob j = epi_job(ji);
+          const float x0 = xfirst;
+          if (ji + 1 < njobs && valid) xfirst = xs[j.feat0 + j.nfeat];
+          if (!inverse || job_live(unit, ji)) {
+            const uint32_t jpar = jobctr & 1;
+            ++jobctr;
+            float* sb = sb_warp + jpar * 128;
+            if (4 * lane < j.N) reinterpret_cast<float4*>(sb)[lane] = bias_next;
+            fetch_next_bias(unit, ji);
+            __syncwarp();
+            MF_TRACE(lane == 0, 5, ji);
+            mbar_wait(&acc_full[t][j.region], (j.region ? fo1 : fo0) & 1);
+            if (j.region) ++fo1; else ++fo0;
+            MF_TRACE(lane == 0, 6, ji);
+            tc::fence_after_thread_sync();
+            float xnext = x0;
 #pragma unroll 1
             for (int fl = 0; fl < j.nfeat; ++fl) {  // one copy of the spline code (instruction cache)
               const int f = j.feat0 + fl;
               const float xv = xnext;
-              if (fl + 1 < j.nfeat && valid) xnext = xsrc[fl + 1];  // next feature's input, in flight during this spline
+              if (fl + 1 < j.nfeat && valid) xnext = xs[f + 1];  // next feature's input, in flight during this spline
               if (!((fmask >> f) & 1ull)) continue;  // sampling: provisional feature of this sweep, keeps its value
               float out, la;
               int bin;
               bool ins;
-              spline_tmem<NCHK, INV>(taddr + j.acc_col + fl * L.PFt, sb + fl * L.PFt, cf, xv, out, la, bin, ins);
+              spline_tmem<NCHK, INV>(taddr + j.acc_col + fl * PFt, sb + fl * PFt, cf, xv, out, la, bin, ins);
               put1(row, xcol0 + f, valid ? out : 0.f);  // next unit's layer-0 operand (its last reader, job 0, has retired)
               if (valid) {
                 gz[g * D + f] = out;

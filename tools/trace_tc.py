@@ -31,10 +31,10 @@ med = ev[len(ev) // 2][0]
 ev = [e for e in ev if abs(e[0] - med) < 10 ** 9]
 t0 = ev[0][0]
 # id = warp * 1000 + code * 20 + job (flow_tc.cu, MF_TRACE).  One column per traced warp: the issuer (warp 1), then the
-# four epilogue warps of tile slot 0 (warps 0-3) and of slot 1 (warps 4-7).
-CODES = {1: "W", 2: "rdy", 3: "iss", 4: "st", 5: "wait", 6: "full", 7: "done", 8: "tile", 9: "staged"}
-cols = [9, 0, 1, 2, 3, 4, 5, 6, 7]
-print("# clk | issuer (job = 2*ji + slot) | slot 0 warps 0 1 2 3 | slot 1 warps 4 5 6 7   [W weights landed, rdy deps met, iss issued;")
+# (two issuers since r2t: warps 9 and 10), then the four epilogue warps of tile slot 0 (warps 0-3) and of slot 1 (warps 4-7).
+CODES = {1: "W", 2: "rdy", 3: "iss", 4: "st", 5: "wait", 6: "full", 7: "done", 8: "tile", 9: "staged", 10: "xdone", 11: "ctx0", 12: "ctx1"}
+cols = [9, 10, 0, 1, 2, 3, 4, 5, 6, 7]
+print("# clk | issuer of slot 0 | issuer of slot 1 | slot 0 warps 0 1 2 3 | slot 1 warps 4 5 6 7   [W weights landed, rdy deps met, iss issued;")
 print("#       wait = waiting for the accumulator, full = accumulator complete, done = epilogue finished and arrived]")
 for c, i in ev[:int(sys.argv[2]) if len(sys.argv) > 2 else 900]:
     w, code, job = i // 1000, (i % 1000) // 20, i % 20
