@@ -32,6 +32,8 @@ FLAGS = [
 EXTRA_FLAGS = {"rambo.cu": ["--use_fast_math"]}
 if os.environ.get("MF_TC_TRACE") == "1":  # cycle-level trace of the tensor-core flow kernel (tools/trace_tc.py)
     EXTRA_FLAGS["flow_tc.cu"] = ["-DMF_TC_TRACE"]
+if os.environ.get("MF_TC_DEFS"):  # experiment switches of flow_tc.cu (comma-separated macro names), tools/gpu_iter.sh
+    EXTRA_FLAGS["flow_tc.cu"] = EXTRA_FLAGS.get("flow_tc.cu", []) + ["-D" + d for d in os.environ["MF_TC_DEFS"].split(",")]
 
 
 def _stale(target, deps):

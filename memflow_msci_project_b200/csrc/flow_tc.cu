@@ -53,7 +53,8 @@ namespace {
 #define MF_TRACE(cond, code, job) do { } while (0)
 #endif
 
-constexpr int kTcThreads = 11 * 32;              // 8 epilogue warps + loader + one MMA issuer per tile slot
+constexpr int kTcThreads = 12 * 32;              // 8 epilogue warps + loader + one MMA issuer per tile slot + 1 idle
+constexpr int kCtrlRegs = 104, kEpiRegs = 200;   // setmaxnreg: registers move from the control warps to the epilogue warps
 constexpr int kLoaderWarp = 8, kIssuerWarp = 9;
 constexpr int kMaxStages = 8;                   // weight ring depth: as many as fit next to the layer-0 operands
 constexpr int kMaxJobs = 40;
@@ -323,6 +324,18 @@ __device__ __forceinline__ void ldg256(const float* p, float* v) {
       : "l"(p));
 }
 
+// Cold paths of the tile start, kept out of line: the tile prologue runs once per ~150 k cycles, its code is never in
+// the instruction cache when it starts, and all eight epilogue warps wait for the same cache lines (per-warp traces
+// r2x-r3c: the context loop took 5.6 k cycles even with its global loads removed).
+struct F8 { float v[8]; };
+__device__ __noinline__ F8 ldg_sector_guarded(const float* sp, const float* end, bool live) {
+  F8 r;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) r.v[e] = (live && sp + e < end) ? __ldg(sp + e) : 0.f;
+  return r;
+}
+__device__ __noinline__ float xmap_cold(const BaseParams& bp, float v, int f) { return xmap_apply<float>(bp, v, f); }
+
 // 8 accumulator columns -> scaled logits: acc * inv + sb, two columns per FFMA2
 __device__ __forceinline__ void scale8(const uint32_t* r, const float* sb, float inv, float* o) {
   const float4 b0 = *reinterpret_cast<const float4*>(sb), b1 = *reinterpret_cast<const float4*>(sb + 4);
@@ -374,12 +387,20 @@ __device__ __forceinline__ void spline_tmem(uint32_t taddr, const float* sb, con
 
 // ------------------------------------------------------------------------------------------------
 // fp32 pair -> (hi, lo) fp16 pairs with hi + lo = v to ~2^-22 relative; v - float(hi) is exact in fp32
+// (the remainder is one mixed-precision FMA per value, `fma.rn.f32.f16` -> SASS FHFMA: 4 instructions per pair)
 __device__ __forceinline__ void split_f16_pair(float2 v, uint32_t& hi, uint32_t& lo) {
-  const __half2 h = __floats2half2_rn(v.x, v.y);
-  const float2 l2 = f2_fma(__half22float2(h), f2_bcast(-1.f), v);
-  const __half2 l = __floats2half2_rn(l2.x, l2.y);
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(v.y), "f"(v.x));
+  float l0, l1;
+  asm("{\n"
+      ".reg .b16 h0, h1, m1;\n"
+      "mov.b32 {h0, h1}, %2;\n"
+      "mov.b16 m1, 0xBC00;\n"  // -1.0 in fp16
+      "fma.rn.f32.f16 %0, h0, m1, %3;\n"
+      "fma.rn.f32.f16 %1, h1, m1, %4;\n"
+      "}\n"
+      : "=f"(l0), "=f"(l1)
+      : "r"(hi), "f"(v.x), "f"(v.y));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(l1), "f"(l0));
 }
 
 // ReLU + split in two conversions: hi = rz(max(u, 0)), lo = rn(max(u - hi, 0)).  Rounding hi TOWARDS ZERO makes the
@@ -656,6 +677,12 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
   tc::fence_after_thread_sync();
   const uint32_t tmem = tmem_base_s;
 
+  // Register reallocation: the kernel starts with 168 registers per thread (12 warps); the control warpgroup (warps
+  // 8-11: loader, two issuers, one idle warp) gives registers back and the two epilogue warpgroups take them, so the
+  // spline / hidden-layer code is not squeezed into 168 registers (it spilled, and every change of the cold tile-start
+  // code shifted the allocation of the hot loops: r3f was 12 % slower for that reason alone).
+  if (warp >= 8) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kCtrlRegs));
   if (warp == kLoaderWarp) {
     // ===================== weight loader =====================
     if (lane == 0) {
@@ -811,7 +838,9 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
         rcur = rnxt;
       }
     }
+  }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
     // ===================== epilogue groups =====================
     const int t = warp >> 2;                  // tile slot
     const int q = warp & 3;                   // TMEM lane quarter this warp may access (4 consecutive warps cover all)
@@ -863,11 +892,8 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
       }
     };
 
-    // context staging: chunk index gt of a tile is chunk c_first of row r_first, GT chunks further is (step_r, step_c) on
-    const int nchunk = xcol0 >> 3;  // 16-byte operand chunks per row (the last one zero-padded when C % 8 != 0)
-    const int nchunk_d = nchunk > 0 ? nchunk : 1;  // (no context: the staging loop is empty)
-    const int r_first = gt / nchunk_d, c_first = gt - r_first * nchunk_d;
-    const int step_r = GT / nchunk_d, step_c = GT - step_r * nchunk_d;
+    const int nchunk = xcol0 >> 3;  // 16-byte operand chunks per context row (the last one zero-padded when C % 8 != 0)
+    const float* ctx_end = gc + ((n - 1) / args.ctx_group + 1) * (long long)C;  // one past the last context float
     for (long long p = blockIdx.x; p < n_pairs; p += gridDim.x) {
       const long long tile = 2 * p + t;
       if (tile >= n_tiles) break;  // odd tile count: slot 1 idles in the last pair (the MMA warp skips it too)
@@ -882,112 +908,115 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
       float ladj = 0.f;
       if (has_tile) {
         MF_TRACE(lane == 0, 8, 0);
-        for (int f0 = 0; f0 < D; f0 += 8) {  // eight loads in flight
-          float xv[8];
+        // x: the first eight features are requested BEFORE the context staging and consumed after it (their latency
+        // hides behind the context loop); further groups of eight follow the old load-then-use pattern
+        float xv0[8];
   #pragma unroll
-          for (int u = 0; u < 8; ++u) xv[u] = (valid && f0 + u < D) ? gx[g * D + f0 + u] : 0.f;
-  #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int f = f0 + u;
-            if (f < D) {
-              float v0 = xv[u];
-              if (inverse && valid)
-                v0 = (args.base == MF_BASE_DIAG_NORMAL) ? (float)bp.a[f] + (float)bp.b[f] * v0
-                                                       : (float)bp.a[f] + ((float)bp.b[f] - (float)bp.a[f]) * v0;
-              if (!inverse && valid && bp.xmap_kind != MF_XMAP_NONE) v0 = xmap_apply<float>(bp, v0, f);  // logit bridge
-              if (valid) gz[g * D + f] = v0;
-              put1(row, xcol0 + f, v0);  // x columns of the layer-0 operand
-            }
-          }
-        }
+        for (int u = 0; u < 8; ++u) xv0[u] = (valid && u < D) ? gx[g * D + u] : 0.f;
+        auto x_in = [&](float v0, int f) {
+          if (inverse && valid)
+            v0 = (args.base == MF_BASE_DIAG_NORMAL) ? (float)bp.a[f] + (float)bp.b[f] * v0
+                                                   : (float)bp.a[f] + ((float)bp.b[f] - (float)bp.a[f]) * v0;
+          if (!inverse && valid && bp.xmap_kind != MF_XMAP_NONE) v0 = xmap_cold(bp, v0, f);  // logit bridge
+          if (valid) gz[g * D + f] = v0;
+          put1(row, xcol0 + f, v0);  // x columns of the layer-0 operand
+        };
         MF_TRACE(lane == 0, 10, 0);
         // ---- stage (ctx | 0) of the layer-0 operand once per tile; every MMA that read the previous tile's
         //      operand has retired (this group waited on the last accumulator of that tile)
         {
           const int kfill = L.in0_ksteps * 16;
           for (int k = xcol0 + D; k < kfill; ++k) put1(row, k, 0.f);
-          // context: one 16-byte operand chunk (8 columns of one row) per thread and step, four chunks in flight;
-          // consecutive threads take consecutive chunks, so a warp reads a contiguous stretch of global memory
-          // (chunk index -> (row, chunk of the row) advances incrementally by GT chunks per step: the integer divisions
-          // this replaces -- one of them 64-bit, by the runtime ctx_group -- made the staging of a tile cost 12 k cycles,
-          // per-warp trace r2t)
-          const int total = 128 * nchunk;
+          // context: every thread stages ITS OWN row (thread = object = operand row), 16-byte operand chunks of 8 columns.
+          // A context row is only 4-byte aligned in global memory (row stride C floats): it is fetched as the 32-byte
+          // ALIGNED sectors that hold it (ld.global.nc.v8, SASS LDG.256, four sectors in flight, every sector requested
+          // once) and each chunk is shifted into place out of two neighbouring sectors with three select stages whose
+          // predicates are per-thread constants of the tile.  Eight consecutive rows hit the eight swizzle positions of
+          // a 128-byte line, so the 16-byte stores of a warp are conflict-free.
+          // (History, per-warp traces r2t-r3b: one chunk per thread with consecutive threads on consecutive chunks cost
+          // 7-9 k cycles per tile pair -- first 8 scalar loads per chunk, each an L2 round trip because this kernel
+          // leaves ~4 KB of L1, then ~150 instructions of per-chunk bookkeeping; the loop without any load still took
+          // 5.6 k cycles.)
           const int G = args.ctx_group;   // x rows per context row (context hoisted per event in the MEM sweep)
-          const long long crow0 = tile0 / G;               // context row of the tile's first object ...
-          const int crem0 = (int)(tile0 - crow0 * G);      // ... and that object's position inside its group
-          int r_it = r_first, c_it = c_first;              // (row, chunk) of chunk index gt
-          // The 8 floats of a chunk are only 4-byte aligned in global memory (row stride C floats).  They are fetched as
-          // the one or two 32-byte ALIGNED sectors that hold them (ld.global.nc.v8, SASS LDG.256) and shifted into place
-          // with selects: two sector requests per chunk instead of eight scalar loads that each pull the same sectors
-          // from L2 again (this kernel leaves ~4 KB of L1) -- the L2 -> SM sector rate made the staging of a tile pair
-          // cost ~9 k cycles (per-warp traces r2t, r2u).
-          const float* ctx_end = gc + ((n - 1) / G + 1) * (long long)C;
+          long long crow = tile0 + row;
+          if (G != 1) crow = crow / G;
+          const float* rowp = gc + crow * C;
+          const int mis = (int)((reinterpret_cast<uintptr_t>(rowp) >> 2) & 7);  // floats past the sector boundary
+          const float* wp = rowp - mis;
+          const bool s4 = (mis & 4) != 0, s2 = (mis & 2) != 0, s1 = (mis & 1) != 0;
           MF_TRACE(lane == 0, 11, 0);
-          for (int q0 = gt; q0 < total; q0 += 4 * GT) {
-            float w[4][16];
-            int rr[4], kc[4], sh[4];
+          // groups of three chunks = four sectors
+          auto load_group = [&](int c0, float (&sct)[4][8]) {
   #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int qq = q0 + u * GT;
-              rr[u] = r_it;
-              kc[u] = c_it;
-              r_it += step_r; c_it += step_c;
-              if (c_it >= nchunk) { c_it -= nchunk; ++r_it; }
-              const bool live = (qq < total) && (rr[u] < rows);
-              int crow = rr[u];
-              if (G != 1) crow = (crem0 + rr[u]) / G;
-              const float* src = gc + (crow0 + crow) * C + kc[u] * 8;
-              const int a = (int)((reinterpret_cast<uintptr_t>(src) >> 2) & 7);  // floats past the sector boundary
-              const float* wp = src - a;
-              sh[u] = 0;
+            for (int j = 0; j < 4; ++j) {
+              const float* sp = wp + 8 * (c0 + j);
+              if (valid && c0 + j <= nchunk && sp + 8 <= ctx_end) {
+                ldg256(sp, sct[j]);
+              } else {  // rows past the end of the batch (zeros) / the last sector of the tensor (element by element)
+                const F8 g8 = ldg_sector_guarded(sp, ctx_end, valid && c0 + j <= nchunk);
   #pragma unroll
-              for (int e = 0; e < 16; ++e) w[u][e] = 0.f;
-              if (live && wp + 16 <= ctx_end) {
-                sh[u] = a;
-                ldg256(wp, w[u]);
-                if (a) ldg256(wp + 8, w[u] + 8);
-              } else if (live) {  // the last sectors of the tensor: element by element
-  #pragma unroll
-                for (int e = 0; e < 8; ++e) w[u][e] = (kc[u] * 8 + e < C) ? __ldg(src + e) : 0.f;
+                for (int e = 0; e < 8; ++e) sct[j][e] = g8.v[e];
               }
             }
+          };
+          auto convert_group = [&](int c0, const float (&sct)[4][8]) {
   #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              if (q0 + u * GT < total) {
-                const int r = rr[u], c8 = kc[u];
-                float v[1][8];
+            for (int u = 0; u < 3; ++u) {
+              const int c8 = c0 + u;
+              if (c8 < nchunk) {
+                float v[8];
                 {
-                  // v[e] = w[e + sh], sh = 0..7 per lane: three select stages (shift by 4, 2, 1)
-                  const bool s4 = (sh[u] & 4) != 0, s2 = (sh[u] & 2) != 0, s1 = (sh[u] & 1) != 0;
+                  // v[e] = window[e + mis], window = sectors u, u + 1
                   float t4[12], t2[10];
   #pragma unroll
-                  for (int e = 0; e < 12; ++e) t4[e] = s4 ? w[u][e + 4] : w[u][e];
+                  for (int e = 0; e < 12; ++e) t4[e] = s4 ? (e + 4 < 8 ? sct[u][e + 4] : sct[u + 1][e - 4]) : (e < 8 ? sct[u][e] : sct[u + 1][e - 8]);
   #pragma unroll
                   for (int e = 0; e < 10; ++e) t2[e] = s2 ? t4[e + 2] : t4[e];
   #pragma unroll
-                  for (int e = 0; e < 8; ++e) {
-                    const float x = s1 ? t2[e + 1] : t2[e];
-                    v[0][e] = (c8 * 8 + e < C) ? x : 0.f;  // columns past C belong to the next row
+                  for (int e = 0; e < 8; ++e) v[e] = s1 ? t2[e + 1] : t2[e];
+                  if (c8 == nchunk - 1) {  // columns past C belong to the next row
+  #pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] = (c8 * 8 + e < C) ? v[e] : 0.f;
                   }
                 }
+                const int r = row;
                 const uint32_t off = (c8 * 8 < kfull_cols)
                                          ? (uint32_t)(c8 >> 3) * kKBlockBytes + (uint32_t)r * 128u + (uint32_t)(((c8 & 7) ^ (r & 7)) << 4)
                                          : kFullBytes + (uint32_t)((c8 * 8 - kfull_cols) >> 4) * kTailBytes + (uint32_t)r * 32u +
                                                (uint32_t)(((c8 & 1) ^ ((r >> 2) & 1)) << 4);
                 uint4 hi, lo;
                 if (NSPLIT == 3) {
-                  tc::split_f16(v[0][0], v[0][1], hi.x, lo.x); tc::split_f16(v[0][2], v[0][3], hi.y, lo.y);
-                  tc::split_f16(v[0][4], v[0][5], hi.z, lo.z); tc::split_f16(v[0][6], v[0][7], hi.w, lo.w);
+                  split_f16_pair(make_float2(v[0], v[1]), hi.x, lo.x); split_f16_pair(make_float2(v[2], v[3]), hi.y, lo.y);
+                  split_f16_pair(make_float2(v[4], v[5]), hi.z, lo.z); split_f16_pair(make_float2(v[6], v[7]), hi.w, lo.w);
                   *reinterpret_cast<uint4*>(a_hi + off) = hi;
                   *reinterpret_cast<uint4*>(a_lo + off) = lo;
                 } else {
-                  hi.x = tc::pack_bf16(v[0][0], v[0][1]); hi.y = tc::pack_bf16(v[0][2], v[0][3]);
-                  hi.z = tc::pack_bf16(v[0][4], v[0][5]); hi.w = tc::pack_bf16(v[0][6], v[0][7]);
+                  hi.x = tc::pack_bf16(v[0], v[1]); hi.y = tc::pack_bf16(v[2], v[3]);
+                  hi.z = tc::pack_bf16(v[4], v[5]); hi.w = tc::pack_bf16(v[6], v[7]);
                   *reinterpret_cast<uint4*>(a_hi + off) = hi;
                 }
               }
             }
+          };
+          // (requesting group k + 1 before converting group k hides ~2.5 k cycles of load latency per tile but made the
+          // whole kernel 12 % slower, r3f: 64 more live registers at this point change the allocation of the hot loops)
+          for (int c0 = 0; c0 < nchunk; c0 += 3) {
+            float sct[4][8];
+            load_group(c0, sct);
+            convert_group(c0, sct);
           }
+        }
+        // x columns (requested before the context loop)
+  #pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (u < D) x_in(xv0[u], u);
+        for (int f0 = 8; f0 < D; f0 += 8) {  // eight loads in flight
+          float xv[8];
+  #pragma unroll
+          for (int u = 0; u < 8; ++u) xv[u] = (valid && f0 + u < D) ? gx[g * D + f0 + u] : 0.f;
+  #pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (f0 + u < D) x_in(xv[u], f0 + u);
         }
         MF_TRACE(lane == 0, 12, 0);
         {  // pull this slot's next tile (x rows and context rows) into L2 while this one is being processed
@@ -997,8 +1026,10 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
             const char* px = reinterpret_cast<const char*>(gx + nt0 * D);
             const char* pc = reinterpret_cast<const char*>(gc + (nt0 / args.ctx_group) * C);
             const long long xb = nrows * D * 4, cb = ((nt0 + nrows - 1) / args.ctx_group - nt0 / args.ctx_group + 1) * C * 4;
-            for (long long o = (long long)gt * 128; o < xb; o += (long long)GT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(px + o));
-            for (long long o = (long long)gt * 128; o < cb; o += (long long)GT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + o));
+            // one prefetch per 32-byte SECTOR (a prefetch of one address per 128-byte line left the tile start waiting
+            // for DRAM: 7 k cycles for the three context rounds, per-warp traces r2x-r2z)
+            for (long long o = (long long)gt * 32; o < xb; o += (long long)GT * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(px + o));
+            for (long long o = (long long)gt * 32; o < cb; o += (long long)GT * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + o));
           }
         }
       }
@@ -1163,7 +1194,7 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
         if (args.logprob) static_cast<float*>(args.logprob)[g] = lp_base + ladj;
       }
       if (valid && inverse && bp.xmap_kind != MF_XMAP_NONE)  // output map of sample (sigmoid bridge) on the thread's own row
-        for (int f = 0; f < D; ++f) gz[g * D + f] = xmap_apply<float>(bp, gz[g * D + f], f);
+        for (int f = 0; f < D; ++f) gz[g * D + f] = xmap_cold(bp, gz[g * D + f], f);
     }
   }
   tc::fence_before_thread_sync();

@@ -15,3 +15,7 @@ fi
 MF_TC_TRACE=1 timeout 300 python -c "from memflow_msci_project_b200 import build; build.build(force=True)" > gpurun_out/build_trace.log 2>&1
 timeout 60 python tools/trace_tc.py tc_3xf16 2600 > gpurun_out/trace_$TAG.txt 2>&1
 tail -2 gpurun_out/trace_$TAG.txt
+for EXP in $3; do   # extra traced builds with experiment macros
+  MF_TC_TRACE=1 MF_TC_DEFS=$EXP timeout 300 python -c "from memflow_msci_project_b200 import build; build.build(force=True)" > gpurun_out/build_trace_$EXP.log 2>&1
+  timeout 60 python tools/trace_tc.py tc_3xf16 2600 > gpurun_out/trace_${TAG}_$EXP.txt 2>&1
+done
