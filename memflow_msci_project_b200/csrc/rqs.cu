@@ -12,6 +12,7 @@
 // needs ~17 warp-instructions per element (K = 16); a warp-per-element schedule built on shuffles (log-step
 // max / sum / scan, ballot bin search) needs ~150, which would make this streaming kernel issue-bound at
 // ~25 % of the HBM roofline, so shuffles are not used here.
+#include <algorithm>
 #include "flow_common.cuh"
 #include "spline_reg.cuh"
 
@@ -64,13 +65,16 @@ __device__ __forceinline__ void rqs_row<float>(float* p, const SplineCfg<float>&
 #undef MF_RQS_CASE
 }
 
+// Persistent: a CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  With `nbuf` = 2 the parameter tile of the NEXT
+// tile travels (one bulk async copy completing on an mbarrier) while the splines of the current tile are evaluated; with
+// one tile per CTA and load -> wait -> compute in sequence the kernel was latency-bound (67.8 % of the HBM roofline at
+// K = 16 with four CTAs per SM: the copy engine idles while a CTA computes).
 template <typename T>
 __global__ void __launch_bounds__(kRqsRows, 2) rqs_kernel(const T* __restrict__ g_par, const T* __restrict__ g_x, long long n, int K, int univariate,
                            double bound, double slope, int inverse, T* __restrict__ g_y, T* __restrict__ g_ladj,
-                           int8_t* __restrict__ g_bins, uint8_t* __restrict__ g_inside, int use_tma) {
+                           int8_t* __restrict__ g_bins, uint8_t* __restrict__ g_inside, int use_tma, int nbuf) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  T* s_par = reinterpret_cast<T*>(smem_raw);
-  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t bar[2];
   const int R = blockDim.x;
   const int P = 3 * K - 1;
   const int tid = threadIdx.x;
@@ -78,31 +82,56 @@ __global__ void __launch_bounds__(kRqsRows, 2) rqs_kernel(const T* __restrict__ 
   cfg.K = K; cfg.univariate = univariate; cfg.bound = (T)bound;
   cfg.inv_ls2 = slope > 0.0 ? (T)(2.0 / log(slope)) : T(0);
   cfg.inv_ls1 = slope > 0.0 ? (T)(1.0 / log(slope)) : T(0);
-  const long long first = (long long)blockIdx.x * R;
-  const int rows = (int)min((long long)R, n - first);
   const uint32_t tile_bytes = (uint32_t)((size_t)R * P * sizeof(T));
-  const bool tma = use_tma && rows == R && (tile_bytes % 16 == 0);
-  if (tma) {
-    if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
-    __syncthreads();
-    if (tid == 0) {
-      mbar_expect_tx(&bar, tile_bytes);
-      bulk_g2s(s_par, g_par + first * P, tile_bytes, &bar);
-    }
-    mbar_wait(&bar, 0);
-  } else {
-    for (int i = tid; i < rows * P; i += R) s_par[i] = g_par[first * P + i];
-    __syncthreads();
+  const long long n_tiles = (n + R - 1) / R;
+  const bool tma_ok = use_tma && (tile_bytes % 16 == 0);
+  auto buf_of = [&](int b) { return reinterpret_cast<T*>(smem_raw + (size_t)b * tile_bytes); };
+  auto is_tma_tile = [&](long long tile) { return tma_ok && tile < n_tiles && (tile + 1) * R <= n; };
+  if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_mbar_init(); }
+  __syncthreads();
+  uint32_t ph0 = 0, ph1 = 0;  // phases of the two barriers
+  long long tile = blockIdx.x;
+  if (tid == 0 && is_tma_tile(tile)) {
+    mbar_expect_tx(&bar[0], tile_bytes);
+    bulk_g2s(buf_of(0), g_par + tile * R * P, tile_bytes, &bar[0]);
   }
-  if (tid < rows) {
-    T out, la;
-    int bin;
-    bool ins;
-    rqs_row<T>(s_par + (size_t)tid * P, cfg, slope, inverse != 0, g_x[first + tid], out, la, bin, ins);
-    g_y[first + tid] = out;
-    if (g_ladj) g_ladj[first + tid] = la;
-    if (g_bins) g_bins[first + tid] = (int8_t)bin;
-    if (g_inside) g_inside[first + tid] = ins ? 1 : 0;
+  int b = 0;
+  for (; tile < n_tiles; tile += gridDim.x) {
+    const long long first = tile * R;
+    const int rows = (int)min((long long)R, n - first);
+    const long long next = tile + gridDim.x;
+    const int nb = (nbuf == 2) ? (b ^ 1) : 0;
+    // the next tile's parameters: requested now when there is a second buffer (its last readers passed the barrier at
+    // the end of the previous iteration), otherwise after this tile's splines
+    if (nbuf == 2 && tid == 0 && is_tma_tile(next)) {
+      mbar_expect_tx(&bar[nb], tile_bytes);
+      bulk_g2s(buf_of(nb), g_par + next * R * P, tile_bytes, &bar[nb]);
+    }
+    const T xv = (tid < rows) ? g_x[first + tid] : T(0);
+    T* s_par = buf_of(b);
+    if (is_tma_tile(tile)) {
+      mbar_wait(&bar[b], b ? ph1 : ph0);
+      if (b) ph1 ^= 1; else ph0 ^= 1;
+    } else {
+      for (int i = tid; i < rows * P; i += R) s_par[i] = g_par[first * P + i];
+      __syncthreads();
+    }
+    if (tid < rows) {
+      T out, la;
+      int bin;
+      bool ins;
+      rqs_row<T>(s_par + (size_t)tid * P, cfg, slope, inverse != 0, xv, out, la, bin, ins);
+      g_y[first + tid] = out;
+      if (g_ladj) g_ladj[first + tid] = la;
+      if (g_bins) g_bins[first + tid] = (int8_t)bin;
+      if (g_inside) g_inside[first + tid] = ins ? 1 : 0;
+    }
+    __syncthreads();  // every thread is done with this buffer
+    if (nbuf != 2 && tid == 0 && is_tma_tile(next)) {
+      mbar_expect_tx(&bar[0], tile_bytes);
+      bulk_g2s(buf_of(0), g_par + next * R * P, tile_bytes, &bar[0]);
+    }
+    b = nb;
   }
 }
 
@@ -240,18 +269,28 @@ extern "C" int mf_rqs_transform(const void* d_params, const void* d_x, int64_t n
   const size_t esz = dtype == MF_F32 ? 4 : 8;
   int rows = dtype == MF_F32 ? 128 : kRqsRows;  // fp32: 128 rows x 128 registers -> four CTAs per SM (measured best)
   while (rows > 32 && (size_t)rows * P * esz > 56 * 1024) rows >>= 1;  // <= 56 KB per CTA: four CTAs per SM
-  const size_t smem = (size_t)rows * P * esz;
-  MF_REQUIRE(smem <= 220 * 1024, "mf_rqs_transform: bins too large for shared memory");
-  const unsigned grid = (unsigned)((n + rows - 1) / rows);
+  const size_t tile = (size_t)rows * P * esz;
+  MF_REQUIRE(tile <= 220 * 1024, "mf_rqs_transform: bins too large for shared memory");
+  // persistent CTAs, four per SM; two parameter buffers per CTA when four CTAs x two tiles fit the SM's shared memory
+  const int nbuf = (tile * 2 * 4 <= 216 * 1024) ? 2 : 1;
+  const size_t smem = tile * nbuf;
+  int sms = 148;
+  {
+    int dev = 0;
+    MF_CUDA_CHECK(cudaGetDevice(&dev));
+    MF_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const long long n_tiles = (n + rows - 1) / rows;
+  const unsigned grid = (unsigned)std::min<long long>(n_tiles, (long long)sms * 4);
   const int use_tma = tma_enabled() && (reinterpret_cast<uintptr_t>(d_params) & 15u) == 0;
   if (dtype == MF_F32) {
     MF_CUDA_CHECK(cudaFuncSetAttribute(rqs_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     rqs_kernel<float><<<grid, rows, smem, st>>>((const float*)d_params, (const float*)d_x, n, bins, univariate, bound,
-                                               slope, inverse, (float*)d_y, (float*)d_ladj, d_bins, d_inside, use_tma);
+                                               slope, inverse, (float*)d_y, (float*)d_ladj, d_bins, d_inside, use_tma, nbuf);
   } else {
     MF_CUDA_CHECK(cudaFuncSetAttribute(rqs_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     rqs_kernel<double><<<grid, rows, smem, st>>>((const double*)d_params, (const double*)d_x, n, bins, univariate, bound,
-                                                slope, inverse, (double*)d_y, (double*)d_ladj, d_bins, d_inside, use_tma);
+                                                slope, inverse, (double*)d_y, (double*)d_ladj, d_bins, d_inside, use_tma, nbuf);
   }
   return post_launch("rqs_kernel");
 }
