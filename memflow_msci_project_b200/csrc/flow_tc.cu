@@ -998,6 +998,10 @@ flow_tc_kernel(const __grid_constant__ TcLayout L, const __grid_constant__ FlowK
               }
             }
           };
+          // (Measured and not kept: staging the NEXT tile's context three chunks at a time in front of the last unit's
+          // hidden-layer waits -- the tile start shrank from ~10 k to 3.8 k cycles but the last unit grew by as much,
+          // profiles/trace_flow_tc_r3j_prestaged_context.txt; evaluating the two splines of a chunk pair side by side for
+          // instruction-level parallelism -- 7.19 instead of 6.47 ms on TF-A, profiles/trace_flow_tc_r3h_paired_splines.txt.)
           // (requesting group k + 1 before converting group k hides ~2.5 k cycles of load latency per tile but made the
           // whole kernel 12 % slower, r3f: 64 more live registers at this point change the allocation of the hot loops)
           for (int c0 = 0; c0 < nchunk; c0 += 3) {
