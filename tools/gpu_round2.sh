@@ -4,6 +4,7 @@
 # Every step is bounded by its own timeout; outputs land in gpurun_out/ (scratch) and are summarised into profiles/.
 set -x
 mkdir -p gpurun_out
+timeout 90 python tools/gate_tc.py > gpurun_out/gate_final.log 2>&1 || { echo "GATE FAILED"; tail -5 gpurun_out/gate_final.log; exit 7; }
 timeout 700 python -m pytest tests -q -m gpu > gpurun_out/gpu_tests.log 2>&1; echo "exit: $?" >> gpurun_out/gpu_tests.log
 tail -3 gpurun_out/gpu_tests.log
 timeout 120 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; echo "exit: $?" >> gpurun_out/smoke.log; tail -2 gpurun_out/smoke.log
