@@ -145,6 +145,24 @@ int mf_rambo_inverse_f64(const mf_rambo_desc* desc, const double* d_momenta, con
                          double* d_detjacinv, int32_t* d_flags, void* stream);
 
 /*
+ * Gradient of the forward map w.r.t. its uniforms: what torch autograd does for
+ * generateKinematics_batch(..., requires_grad=True) (rambo_generator.py:168-398; call sites
+ * scripts/run_model_labframe_sampling.py:432,709).  fp64 (the reference runs this path in fp64).
+ *   d_r             [N, 3n-2]   the uniforms of the forward call
+ *   d_grad_momenta  [N, n+2, 4] cotangent of the momenta                       (may be NULL)
+ *   d_grad_weight   [N]         cotangent of the weight                        (may be NULL)
+ *   d_grad_x1/x2    [N]         cotangents of x1, x2                           (may be NULL)
+ *   d_weight_fwd    [N]         the forward call's weight: where it is 0 (cut) the weight cotangent is dropped (may be NULL)
+ *   d_grad_r        [N, 3n-2]   out
+ * full_derivative = 0 reproduces the REFERENCE's autograd graph (no gradient through the bisection root, the
+ * intermediate masses do not see x1/x2 -- rambo_generator.py:264-284, 400-446); 1 = the full derivative of the map.
+ */
+int mf_rambo_forward_backward(const mf_rambo_desc* desc, const double* d_r, int64_t n_events,
+                              const double* d_grad_momenta, const double* d_grad_weight,
+                              const double* d_grad_x1, const double* d_grad_x2, const double* d_weight_fwd,
+                              int32_t full_derivative, double* d_grad_r, void* stream);
+
+/*
  * Compute_ParticlesTensor.get_PS (unfolding_flow/utils.py:1056-1152): n=4 inverse
  * without Jacobian; x1,x2 from the boost four-vector; bool problem mask.
  *   d_momenta [N,4,4], d_boost [N,4] (E,px,py,pz of the total system in the lab)

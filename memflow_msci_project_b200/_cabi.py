@@ -113,6 +113,15 @@ def rambo_get_ps_lab(desc: RamboDesc, momenta_lab, boost, perm, m_min_tot, momen
     check(rc, "mf_rambo_get_ps_lab")
 
 
+def rambo_forward_backward(desc: RamboDesc, r, g_mom, g_w, g_x1, g_x2, w_fwd, full_derivative, grad_r):
+    """Cotangent of the uniforms of the RAMBO forward map (mf_rambo_forward_backward); fp64 tensors, None = absent."""
+    with torch.cuda.device(r.device):
+        rc = lib().mf_rambo_forward_backward(ctypes.byref(desc), _ptr(r), ctypes.c_int64(r.shape[0]), _ptr(g_mom), _ptr(g_w),
+                                             _ptr(g_x1), _ptr(g_x2), _ptr(w_fwd), ctypes.c_int32(1 if full_derivative else 0),
+                                             _ptr(grad_r), _stream(r.device))
+    check(rc, "mf_rambo_forward_backward")
+
+
 # ---- conditional spline flows ---------------------------------------------------------------------
 def _dtype_code(dtype):
     return {torch.float32: MF_F32, torch.float64: MF_F64}[dtype]

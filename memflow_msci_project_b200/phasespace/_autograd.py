@@ -1,10 +1,10 @@
 """Autograd bridge of the RAMBO forward map (`generateKinematics_batch(..., requires_grad=True)`,
 reference call sites `scripts/run_model_labframe_sampling.py:432,709`).
 
-The FORWARD is the fused sm_100a kernel (fp64 compute).  The BACKWARD re-evaluates the map with differentiable
-fp64 torch ops on the GPU (the algorithm of `memflow/phasespace/rambo_generator.py:168-398` restated below) and
-lets torch autograd produce d(momenta, weight, x1, x2)/d(uniforms); it never runs on the CPU and never touches
-oracle/.  Interim like the flow backward: correct gradients at eager-torch speed.
+The FORWARD is the fused sm_100a kernel (fp64 compute).  The BACKWARD is ONE launch of `mf_rambo_forward_backward`
+(csrc/rambo_bwd.cu: forward-mode dual numbers, fp64).  The differentiable fp64 torch restatement of the algorithm of
+`memflow/phasespace/rambo_generator.py:168-398` below is what that kernel is tested against (and the round-1
+backward, `NATIVE_BACKWARD = False`); neither path runs on the CPU or touches oracle/.
 
 Gradient semantics follow the reference's autograd graph (checked against gradients produced by the reference
 itself, tests/golden/rambo_grad_*.npz), which is NOT the full derivative of the map:
@@ -21,6 +21,12 @@ import math
 import torch
 
 from .. import _cabi
+
+
+# True: the backward is the native kernel (csrc/rambo_bwd.cu).  False: the differentiable torch restatement below --
+# kept as the checker the kernel is tested against (tests/test_rambo_gpu.py) and as documentation of the reference's
+# autograd graph.
+NATIVE_BACKWARD = True
 
 
 def _massless_map(u, e):
@@ -151,6 +157,14 @@ class RamboForwardFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_mom, g_w, g_x1, g_x2):
         rd, w_fwd = ctx.saved_tensors
+        if NATIVE_BACKWARD:
+            # one launch of mf_rambo_forward_backward (forward-mode duals, fp64): no tape, no eager kernels
+            def c64(g):
+                return None if g is None else g.detach().double().contiguous()
+            gr = torch.empty_like(rd)
+            _cabi.rambo_forward_backward(ctx.desc, rd, c64(g_mom), c64(g_w), c64(g_x1), c64(g_x2), w_fwd,
+                                         not ctx.gen.reference_quirks, gr)
+            return None, gr.to(ctx.in_dtype), None, None, None
         with torch.enable_grad():
             rr = rd.detach().requires_grad_(True)
             mom, weight, x1, x2 = eager_forward(ctx.gen, ctx.desc, rr, full_derivative=not ctx.gen.reference_quirks)

@@ -654,6 +654,27 @@ def test_tc_context_group_equals_repeated_context(cuda):
     assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("name", ["TF-A", "UF-common"])
+def test_tc_context_rows_at_any_alignment(cuda, name):
+    """The tcgen05 kernel fetches context rows as 32-byte aligned sectors and shifts them into place: the result must not
+    depend on where the tensor starts (views at every 4-byte offset of a larger buffer, ragged last tile, the last row
+    ending exactly at the end of the buffer) -- bit-equal to the same values in a freshly allocated tensor."""
+    flow = build(name, cuda, torch.float32, mode="default")
+    flow.gemm = flows.modules.GEMM_TC_3XF16
+    n = 3 * 128 + 77
+    x, c = inputs(flow, n, 11, cuda, torch.float32)
+    C = c.shape[1]
+    with torch.no_grad():
+        ref = flow(c.clone()).log_prob(x)
+    for off in range(1, 8):
+        buf = torch.empty(off + n * C, device=cuda, dtype=torch.float32)
+        view = buf[off:].view(n, C)
+        view.copy_(c)
+        assert (view.data_ptr() - buf.data_ptr()) == 4 * off
+        with torch.no_grad():
+            assert torch.equal(flow(view).log_prob(x), ref), off
+
+
 def test_mma_context_group_equals_repeated_context(cuda):
     flow = build("UF", cuda, torch.float32, mode="default")
     flow.gemm = flows.modules.GEMM_MMA_3XF16

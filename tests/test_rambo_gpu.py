@@ -227,6 +227,57 @@ def test_requires_grad_matches_reference_graph(cuda, golden_dir, case, dtype):
     assert ((r.grad.double() - ref).abs() / scale).max().item() < tol
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["n4_HttG", "n8_ttH_decay", "n3_Htt"])
+@pytest.mark.parametrize("quirks", [True, False])
+def test_native_backward_matches_torch_restatement(cuda, golden_dir, name, quirks):
+    """mf_rambo_forward_backward (forward-mode duals in one launch) against torch autograd through the differentiable fp64
+    restatement of the same map (phasespace/_autograd.py, itself pinned to the reference's own gradients by the test
+    above): both gradient semantics, cut events (weight cotangent dropped), missing cotangents."""
+    from memflow_msci_project_b200.phasespace import _autograd as ag
+    g = load(golden_dir, name)
+    masses = g["masses"].tolist()
+    n = len(masses)
+    ps = make_ps(masses, cuda)
+    ps.generator.reference_quirks = quirks
+    gen = torch.Generator().manual_seed(17)
+    N = 2053
+    r0 = (torch.rand(N, 3 * n - 2, generator=gen, dtype=torch.float64) * 0.98 + 0.01).to(cuda)
+    cots = [torch.randn(N, n + 2, 4, generator=gen, dtype=torch.float64).to(cuda), torch.randn(N, generator=gen, dtype=torch.float64).to(cuda),
+            torch.randn(N, generator=gen, dtype=torch.float64).to(cuda), torch.randn(N, generator=gen, dtype=torch.float64).to(cuda)]
+    cuts = dict(pT_mincut=30.0, delR_mincut=0.4, rap_maxcut=2.5) if n == 4 else {}
+
+    def grad(native, use):
+        ag.NATIVE_BACKWARD = native
+        try:
+            r = r0.clone().requires_grad_(True)
+            outs = ps.get_momenta_from_ps(r, requires_grad=True, **cuts)
+            w = outs[1]
+            finite = torch.isfinite(w.detach())           # n = 8: the reference's fp32 volume overflows for some events
+            loss = 0.0
+            for o, c, u in zip(outs, cots, use):
+                if u:
+                    oc = o.double() * c
+                    if o is w:
+                        oc = torch.where(finite, oc, torch.zeros_like(oc))
+                    loss = loss + oc.sum()
+            loss.backward()
+            return r.grad, finite, (w.detach() == 0)
+        finally:
+            ag.NATIVE_BACKWARD = True
+
+    for use in ((1, 1, 1, 1), (1, 0, 0, 0), (0, 1, 0, 1)):
+        a, finite, cut = grad(True, use)
+        b, _, _ = grad(False, use)
+        if n == 4:
+            assert cut.any() and not cut.all()
+        ok = finite & torch.isfinite(b).all(1)
+        scale = b[ok].abs().max(0).values.clamp_min(1e-300)
+        assert ((a[ok] - b[ok]).abs() / scale).max().item() < 1e-9, use
+        if quirks:
+            assert torch.all(a[:, : n - 2] == 0)
+
+
 # ------------------------------------------------------------------------------------------------
 # a2: PhaseSpace.generate_random_phase_space_points (phasespace.py:64-80)
 @pytest.mark.parametrize("name", ["n4_HttG", "n8_ttH_decay"])
