@@ -341,6 +341,29 @@ int mf_flow_set_sample_schedule(const mf_flow_desc* desc, const int32_t* h_order
  * words on the device and copy them in place instead of calling mf_flow_set_sample_schedule (which synchronises). */
 int64_t mf_flow_sched_offset(const mf_flow_desc* desc, int dtype, int gemm);
 
+/*
+ * C[m, n] = A[m, k] * B[n, k]^T (+ bias[n]) (ReLU) in fp32-class arithmetic on the tensor cores (fp16 hi/lo split
+ * operands, three MMAs per product, fp32 accumulate): the GEMMs of the hyper-network backward of the training step,
+ * which torch autograd runs as cuBLAS fp32 SIMT kernels in the reference (scripts/run_model_labframe_sampling.py:499-501,
+ * scripts/run_transferFlow_paperVersion_AllPartons_btag.py:385).  Row-major fp32 operands with leading dimensions;
+ * n <= 256.  k_split > 1: the K range is cut into that many pieces whose partial sums are ADDED into C (the caller
+ * zeroes C; no ReLU).  d_mask (optional, shaped like A, leading dimension ldm): A is multiplied by (mask > 0), the
+ * derivative of the ReLU whose output is `mask`.  d_scale_a / d_scale_b: optional device scalars (powers of two) the
+ * operands are multiplied by before the fp16 split -- gradients are far below the fp16 range --; the result is
+ * divided by their product.
+ */
+int mf_gemm_nt_3xf16(const float* d_a, int64_t lda, const float* d_b, int64_t ldb, float* d_c, int64_t ldc,
+                     int64_t m, int32_t n, int64_t k, const float* d_bias, int32_t relu, int32_t k_split,
+                     const float* d_mask, int64_t ldm, const float* d_scale_a, const float* d_scale_b, void* stream);
+/*
+ * C[m, n] (+)= A[k, m]^T * B[k, n]: the weight gradient dW = dZ^T H of a linear layer straight from the row-major
+ * activations (k = rows; A = dY [rows, out] with the optional ReLU mask, B = H [rows, in]); same arithmetic and
+ * k_split / scale conventions.  d_colsum (optional, [m]): += sum_k A[k, m], the bias gradient (zeroed by the caller).
+ */
+int mf_gemm_tn_3xf16(const float* d_a, int64_t lda, const float* d_b, int64_t ldb, float* d_c, int64_t ldc,
+                     int64_t m, int32_t n, int64_t k, int32_t k_split, const float* d_mask, int64_t ldm,
+                     float* d_colsum, const float* d_scale_a, const float* d_scale_b, void* stream);
+
 /* Backward of the forward spline of mf_rqs_transform (plain MF_UNIV_RQS): gradients of a scalar loss w.r.t. the packed
  * parameters [n, 3K-1] and w.r.t. x [n], given dL/dy [n] and dL/dladj [n] (d_grad_ladj may be NULL = 0).
  * Replaces what torch autograd derives from zuko MonotonicRQSTransform.call_and_ladj in the reference's training steps

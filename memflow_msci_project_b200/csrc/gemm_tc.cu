@@ -1,0 +1,314 @@
+// gemm_tc.cu -- C[M,N] = A[M,K] * B[N,K]^T (+ bias, ReLU) in fp32-class arithmetic on tcgen05 (mf_gemm_nt_3xf16).
+//
+// The GEMMs of the hyper-network BACKWARD of the training step (BASELINE config 4; reference:
+// scripts/run_model_labframe_sampling.py:499-501, scripts/run_transferFlow_paperVersion_AllPartons_btag.py:385, where
+// torch autograd runs them as cuBLAS fp32 SIMT kernels -- 42 of the 68 ms of a likelihood step):
+//   forward recompute   H_l  = relu(H_{l-1} W_l^T + b_l)        A = H_{l-1} [rows, in],   B = W_l   [out, in]
+//   input gradient      dH   = dZ W_l                           A = dZ      [rows, out],  B = W_l^T [in, out]
+//   weight gradient     dW_l = dZ^T H_{l-1}                     A = dZ^T    [out, rows],  B = H^T   [in, rows]   (split-K)
+// Arithmetic as in flow_tc.cu: every fp32 operand value is split into fp16 hi = rn(v), lo = rn(v - hi) and each product
+// is formed as hi*hi + hi*lo + lo*hi with fp32 accumulation in TMEM.  Gradients are far below the fp16 range, so each
+// operand can be multiplied by a power of two read from device memory before the split (d_scale_a / d_scale_b; the
+// result is divided by their product) -- the caller derives it from the operand's largest magnitude without a host sync.
+//
+// One CTA = one 128-row tile of A and one K-range; 256 threads: all eight warps convert the operand K-blocks (64
+// columns) from global memory into the swizzled fp16 hi/lo layout of tc_common.cuh; one thread issues the 12 MMAs of a
+// K-block and commits them to the buffer's mbarrier; warps 0-3 (thread = row = TMEM lane) run the epilogue, transposing
+// through shared memory so that C is written in full row pieces.  Long K-ranges (the weight gradient) use two operand
+// buffers -- K-block i + 1 is staged while the tensor core works on K-block i --, short ones a single buffer so that
+// two or three CTAs share an SM and hide each other's load / MMA / store latencies.  With k_split > 1 the partial
+// sums of the K-ranges are added into C with red.global.add.f32 (C must be zeroed by the caller).
+#include <algorithm>
+
+#include "common.cuh"
+#include "spline_reg.cuh"
+#include "tc_common.cuh"
+
+namespace mf {
+namespace {
+
+constexpr int kGemmThreads = 256;
+
+struct GemmArgs {
+  const float* A; long long lda;
+  const float* B; long long ldb;
+  float* C; long long ldc;
+  long long M, K;
+  int N, Np;            // Np = N rounded up to 16 (MMA N)
+  const float* bias;
+  int relu, k_split;
+  long long kb_per_split;  // K-blocks of 64 per K-range
+  const float* scale_a; const float* scale_b;
+  int vec_a, vec_b;     // rows are 16-byte aligned: float4 loads
+  int trans;            // 0: C = A B^T with A [M,K], B [N,K] (K contiguous); 1: C = A^T B with A [K,M], B [K,N] (K = rows)
+  const float* mask; long long ldm;  // optional, same shape as A: A is multiplied by (mask > 0) (ReLU derivative)
+  float* colsum;        // trans = 1: optional [M] output, += sum_k A[k, m] (the bias gradient), as column N of the product
+  int nbuf;             // operand buffers: 2 when a CTA walks many K-blocks (staging overlaps the MMAs), else 1 (more CTAs per SM)
+  int tmem_cols;        // power of two >= Np
+};
+
+// 32 consecutive columns [k0, k0 + 32) of one operand row -> hi / lo planes of the K-block (half = 0 / 1: which half of
+// the 64 columns); src == nullptr: a row past the end of the matrix (zeros)
+__device__ __forceinline__ void stage_half_row(const float* src, const float* msk, long long k_left, bool vec, float scale,
+                                               unsigned char* hi, unsigned char* lo, int r, int half) {
+  float v[32];
+  if (src == nullptr || k_left <= 0) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) v[e] = 0.f;
+  } else if (vec && k_left >= 32) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(src) + q);
+      v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) v[e] = (e < k_left) ? __ldg(src + e) : 0.f;
+  }
+  if (msk != nullptr && src != nullptr) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) v[e] = (e < k_left && __ldg(msk + e) > 0.f) ? v[e] : 0.f;
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {  // four 16-byte chunks of 8 columns
+    uint4 h, l;
+    tc::split_f16(v[8 * c] * scale, v[8 * c + 1] * scale, h.x, l.x);
+    tc::split_f16(v[8 * c + 2] * scale, v[8 * c + 3] * scale, h.y, l.y);
+    tc::split_f16(v[8 * c + 4] * scale, v[8 * c + 5] * scale, h.z, l.z);
+    tc::split_f16(v[8 * c + 6] * scale, v[8 * c + 7] * scale, h.w, l.w);
+    const int chunk = half * 4 + c;
+    const uint32_t off = (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
+    *reinterpret_cast<uint4*>(hi + off) = h;
+    *reinterpret_cast<uint4*>(lo + off) = l;
+  }
+}
+
+// trans = 1: one K-block (64 rows k of a [K, C] row-major matrix) -> the K-major operand tile [R rows c][64 k].  A thread
+// takes one k and 32 consecutive columns (128 contiguous bytes of global memory); consecutive lanes hold consecutive k, so
+// the 2-byte shared-memory stores of a warp fall into one 128-byte row (no bank conflicts).
+__device__ __forceinline__ void stage_tn(const float* base, long long ld, const float* msk, long long ldm, long long k0,
+                                         long long K, long long c0, long long C, int R, int ones_col, float scale, bool vec,
+                                         unsigned char* hi, unsigned char* lo, int tid) {
+  const int quarters = (R + 31) / 32;
+  for (int idx = tid; idx < 64 * quarters; idx += kGemmThreads) {
+    const int k = idx & 63, q = idx >> 6;
+    const long long kk = k0 + k, cc = c0 + 32 * q;
+    float v[32];
+    const bool live = kk < K;
+    if (live && vec && cc + 32 <= C) {
+      const float4* src = reinterpret_cast<const float4*>(base + kk * ld + cc);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 t = __ldg(src + j);
+        v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = (live && cc + j < C) ? __ldg(base + kk * ld + cc + j) : 0.f;
+    }
+    if (msk != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = (live && cc + j < C && __ldg(msk + kk * ldm + cc + j) > 0.f) ? v[j] : 0.f;
+    }
+    if (ones_col >= 0 && ones_col >= 32 * q && ones_col < 32 * q + 32) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (32 * q + j == ones_col) v[j] = live ? 1.f / scale : 0.f;  // (the operand scale is applied below)
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int r = 32 * q + j;
+      if (r < R) {
+        const float x = v[j] * scale;
+        const __half h = __float2half_rn(x);
+        const __half l = __float2half_rn(x - __half2float(h));
+        const uint32_t off = (uint32_t)r * 128u + (uint32_t)((((k >> 3) ^ (r & 7)) << 4) + (k & 7) * 2);
+        *reinterpret_cast<__half*>(hi + off) = h;
+        *reinterpret_cast<__half*>(lo + off) = l;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 2) gemm_nt_kernel(const __grid_constant__ GemmArgs g) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t a_plane = 128u * 128u;                 // [128 rows x 64] 16-bit
+  const uint32_t b_plane = (uint32_t)g.Np * 128u;       // [Np rows x 64] 16-bit
+  const uint32_t buf_bytes = 2u * a_plane + 2u * b_plane;
+  const long long m0 = (long long)blockIdx.x * 128;
+  const long long n_kb = (g.K + 63) / 64;
+  const long long kb0 = (long long)blockIdx.y * g.kb_per_split;
+  const long long kb1 = min(n_kb, kb0 + g.kb_per_split);
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, (uint32_t)g.tmem_cols);
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fence_mbar_init();
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  const uint32_t tmem = tmem_base_s;
+  const float sa = g.scale_a ? __ldg(g.scale_a) : 1.f, sb = g.scale_b ? __ldg(g.scale_b) : 1.f;
+  const uint32_t idesc = tc::make_idesc_f16(0, 128, g.Np);
+
+  long long it = 0;
+  for (long long kb = kb0; kb < kb1; ++kb, ++it) {
+    const int b = (g.nbuf == 2) ? (int)(it & 1) : 0;
+    unsigned char* a_hi = smem + (size_t)b * buf_bytes;
+    unsigned char* a_lo = a_hi + a_plane;
+    unsigned char* b_hi = a_lo + a_plane;
+    unsigned char* b_lo = b_hi + b_plane;
+    if (it >= g.nbuf) mbar_wait(&bar[b], (uint32_t)(((it / g.nbuf) - 1) & 1));  // the MMAs that read this buffer have retired
+    const long long k0 = kb * 64;
+    if (g.trans) {
+      stage_tn(g.A, g.lda, g.mask, g.ldm, k0, g.K, m0, g.M, 128, -1, sa, g.vec_a != 0, a_hi, a_lo, tid);
+      stage_tn(g.B, g.ldb, nullptr, 0, k0, g.K, 0, g.N, g.Np, g.colsum ? g.N : -1, sb, g.vec_b != 0, b_hi, b_lo, tid);
+    } else {
+      // A: 128 rows x 2 halves = 256 half rows, one per thread
+      {
+        const int r = tid >> 1, half = tid & 1;
+        const long long row = m0 + r, kk = k0 + half * 32;
+        stage_half_row(row < g.M ? g.A + row * g.lda + kk : nullptr, (row < g.M && g.mask) ? g.mask + row * g.ldm + kk : nullptr,
+                       g.K - kk, g.vec_a != 0, sa, a_hi, a_lo, r, half);
+      }
+      // B: Np rows x 2 halves
+      for (int i = tid; i < 2 * g.Np; i += kGemmThreads) {
+        const int r = i >> 1, half = i & 1;
+        const long long kk = k0 + half * 32;
+        stage_half_row(r < g.N ? g.B + (long long)r * g.ldb + kk : nullptr, nullptr, g.K - kk, g.vec_b != 0, sb, b_hi, b_lo, r, half);
+      }
+    }
+    fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core
+    __syncthreads();
+    if (tid == 0) {
+      tc::fence_after_thread_sync();
+      const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t dah = tc::make_smem_desc(ah + ks * 32u), dal = tc::make_smem_desc(al + ks * 32u);
+        const uint64_t dbh = tc::make_smem_desc(bh + ks * 32u), dbl = tc::make_smem_desc(bl + ks * 32u);
+        tc::mma_f16_ss(tmem, dah, dbh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+        tc::mma_f16_ss(tmem, dah, dbl, idesc, 1u);
+        tc::mma_f16_ss(tmem, dal, dbh, idesc, 1u);
+      }
+      tc::mma_commit(&bar[b]);
+    }
+  }
+  if (it > 0) {
+    // the last commit completes when ALL MMAs of the issuing thread have retired
+    const long long last = it - 1;
+    mbar_wait(&bar[(g.nbuf == 2) ? (last & 1) : 0], (uint32_t)((last / g.nbuf) & 1));
+    tc::fence_after_thread_sync();
+    if (warp < 4) {
+      // Epilogue through shared memory (the operand buffers are free now): a thread owns a ROW of the accumulator, the
+      // rows of C are contiguous in global memory -- each warp transposes 32 rows x 64 columns through a scratch tile
+      // (row stride 65 floats: conflict-free both ways) and writes full 256-byte row pieces.
+      float* scratch = reinterpret_cast<float*>(smem) + (size_t)warp * 32 * 65;
+      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+      const float inv = 1.f / (sa * sb);
+      const bool add_bias = g.bias != nullptr && blockIdx.y == 0;
+      const long long row0 = m0 + warp * 32;
+      for (int cb = 0; cb < g.Np; cb += 64) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int c0 = cb + 16 * q;
+          if (c0 < g.Np) {
+            float v[16];
+            tc::tmem_ld16(taddr + c0, v);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              float x = v[e] * inv;
+              if (add_bias && c0 + e < g.N) x += __ldg(g.bias + c0 + e);
+              if (g.relu) x = fmaxf(x, 0.f);
+              scratch[lane * 65 + 16 * q + e] = x;
+            }
+          }
+        }
+        __syncwarp();
+        for (int r = 0; r < 32; ++r) {
+          const long long row = row0 + r;
+          if (row >= g.M) break;
+          float* dst = g.C + row * g.ldc + cb;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int c = lane + 32 * h;
+            if (cb + c < g.N) {
+              const float x = scratch[r * 65 + c];
+              if (g.k_split > 1) atomicAdd(dst + c, x);
+              else dst[c] = x;
+            } else if (g.colsum != nullptr && cb + c == g.N) {
+              atomicAdd(g.colsum + row, scratch[r * 65 + c]);
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, (uint32_t)g.tmem_cols);
+}
+
+}  // namespace
+}  // namespace mf
+
+using namespace mf;
+
+static int gemm_launch(int trans, const float* d_a, int64_t lda, const float* d_b, int64_t ldb, float* d_c, int64_t ldc,
+                       int64_t m, int32_t n, int64_t k, const float* d_bias, int32_t relu, int32_t k_split,
+                       const float* d_mask, int64_t ldm, float* d_colsum, const float* d_scale_a, const float* d_scale_b,
+                       void* stream, const char* who) {
+  MF_REQUIRE(m >= 0 && n >= 0 && k >= 0, "%s: negative dimension", who);
+  if (m == 0 || n == 0) return MF_OK;
+  MF_REQUIRE(d_a && d_b && d_c, "%s: null argument", who);
+  MF_REQUIRE(n + (d_colsum ? 1 : 0) <= 256, "%s: n=%d > 256 (one accumulator tile)", who, n);
+  MF_REQUIRE(k >= 1, "%s: k must be positive", who);
+  if (trans) MF_REQUIRE(lda >= m && ldb >= n && ldc >= n, "%s: leading dimension smaller than the row length", who);
+  else MF_REQUIRE(lda >= k && ldb >= k && ldc >= n, "%s: leading dimension smaller than the row length", who);
+  MF_REQUIRE(k_split >= 1, "%s: k_split must be >= 1", who);
+  MF_REQUIRE(!(relu && k_split > 1), "%s: ReLU cannot be applied to partial sums (k_split > 1)", who);
+  GemmArgs g;
+  g.A = d_a; g.lda = lda; g.B = d_b; g.ldb = ldb; g.C = d_c; g.ldc = ldc;
+  g.M = m; g.K = k; g.N = n; g.Np = (n + (d_colsum ? 1 : 0) + 15) / 16 * 16;
+  g.bias = d_bias; g.relu = relu;
+  g.trans = trans; g.mask = d_mask; g.ldm = ldm; g.colsum = d_colsum;
+  const long long n_kb = (k + 63) / 64;
+  const long long ks = std::min<long long>(k_split, n_kb);
+  g.kb_per_split = (n_kb + ks - 1) / ks;
+  const long long splits = (n_kb + g.kb_per_split - 1) / g.kb_per_split;
+  g.k_split = (int)splits;
+  g.scale_a = d_scale_a; g.scale_b = d_scale_b;
+  g.vec_a = ((reinterpret_cast<uintptr_t>(d_a) & 15u) == 0 && lda % 4 == 0) ? 1 : 0;
+  g.vec_b = ((reinterpret_cast<uintptr_t>(d_b) & 15u) == 0 && ldb % 4 == 0) ? 1 : 0;
+  g.nbuf = (g.kb_per_split > 3) ? 2 : 1;
+  g.tmem_cols = 32;
+  while (g.tmem_cols < g.Np) g.tmem_cols *= 2;
+  const size_t smem = std::max<size_t>((size_t)g.nbuf * (2 * 128 * 128 + 2 * (size_t)g.Np * 128), 4 * 32 * 65 * 4);
+  MF_CUDA_CHECK(cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long m_tiles = (m + 127) / 128;
+  MF_REQUIRE(m_tiles <= 0x7fffffffLL && splits <= 65535, "%s: grid too large", who);
+  dim3 grid((unsigned)m_tiles, (unsigned)splits);
+  gemm_nt_kernel<<<grid, kGemmThreads, smem, static_cast<cudaStream_t>(stream)>>>(g);
+  return post_launch("gemm_nt_kernel");
+}
+
+extern "C" int mf_gemm_nt_3xf16(const float* d_a, int64_t lda, const float* d_b, int64_t ldb, float* d_c, int64_t ldc,
+                                int64_t m, int32_t n, int64_t k, const float* d_bias, int32_t relu, int32_t k_split,
+                                const float* d_mask, int64_t ldm, const float* d_scale_a, const float* d_scale_b,
+                                void* stream) {
+  return gemm_launch(0, d_a, lda, d_b, ldb, d_c, ldc, m, n, k, d_bias, relu, k_split, d_mask, ldm, nullptr, d_scale_a,
+                     d_scale_b, stream, "mf_gemm_nt_3xf16");
+}
+
+extern "C" int mf_gemm_tn_3xf16(const float* d_a, int64_t lda, const float* d_b, int64_t ldb, float* d_c, int64_t ldc,
+                                int64_t m, int32_t n, int64_t k, int32_t k_split, const float* d_mask, int64_t ldm,
+                                float* d_colsum, const float* d_scale_a, const float* d_scale_b, void* stream) {
+  return gemm_launch(1, d_a, lda, d_b, ldb, d_c, ldc, m, n, k, nullptr, 0, k_split, d_mask, ldm, d_colsum, d_scale_a,
+                     d_scale_b, stream, "mf_gemm_tn_3xf16");
+}

@@ -1,10 +1,11 @@
 """Autograd bridges of the fused flow kernels (training path, BASELINE config 4).
 
-STATUS (round 1): the FORWARD of a differentiable ``log_prob`` / ``rsample`` is the fused sm_100a kernel;
+STATUS (round 2): the FORWARD of a differentiable ``log_prob`` / ``rsample`` is the fused sm_100a kernel;
 the BACKWARD re-evaluates the flow transform by transform on the GPU: the hyper-network (masked linears + ReLU)
-with torch ops (cuBLAS GEMMs, torch autograd), the spline with native kernels -- forward `mf_rqs_transform`,
-backward `mf_rqs_backward` (closed-form gradient w.r.t. the 3K-1 logits and x; the inverse direction by the
-implicit function theorem) -- instead of ~300 eager elementwise kernels per transform.  This keeps the reference's
+through `_MaskedLinearFn`, whose three GEMMs per layer (recompute, dX, dW) run on tcgen05 in fp32-class 3xFP16
+arithmetic (`mf_gemm_nt_3xf16`; fp32 only -- fp64 training keeps torch's GEMMs), the spline with native kernels --
+forward `mf_rqs_transform`, backward `mf_rqs_backward` (closed-form gradient w.r.t. the 3K-1 logits and x; the
+inverse direction by the implicit function theorem) -- instead of ~300 eager elementwise kernels per transform.  This keeps the reference's
 training loops working unchanged (`loss = -flow(c).log_prob(x).mean(); loss.backward()`); it never runs on the CPU
 and never touches oracle/.  `MEMFLOW_B200_EAGER_SPLINE=1` selects the pure-torch spline restated below (the
 formulation the native backward is tested against).
@@ -69,13 +70,77 @@ def _wrap(x, bound):
     return torch.remainder(x + bound, 2 * bound) - bound
 
 
+def _native_gemm():
+    """fp32 hyper-network GEMMs of the recompute / backward on tcgen05 (mf_gemm_nt_3xf16) instead of cuBLAS;
+    MEMFLOW_B200_TORCH_GEMM=1 keeps torch's (the formulation the native path is tested against)."""
+    return os.environ.get("MEMFLOW_B200_TORCH_GEMM") != "1"
+
+
+def _pow2_scale(t):
+    """device scalar 2^s that lifts the largest magnitude of t to ~2^14 (fp16 tops out at 2^16; the lo part of a value stays a normal fp16 number down to 2^-17 of the largest one) (no host sync): gradients are far below the
+    fp16 range of the split operands of mf_gemm_nt_3xf16"""
+    amax = torch.linalg.vector_norm(t, ord=float("inf")).clamp_min(1e-30)
+    return torch.exp2(torch.floor(14.0 - torch.log2(amax))).reshape(1).to(torch.float32)
+
+
+class _MaskedLinearFn(torch.autograd.Function):
+    """y = [relu](x @ (mask * weight).T + bias) with all three GEMMs (forward, dX, dW) on tcgen05 in fp32-class 3xFP16
+    arithmetic: the native hyper-network backward."""
+
+    @staticmethod
+    def forward(ctx, x, weight, mask, bias, relu):
+        wm = (mask * weight).contiguous()
+        x = x.contiguous()
+        y = torch.empty((x.shape[0], wm.shape[0]), dtype=x.dtype, device=x.device)
+        _cabi.gemm_nt(x, wm, y, bias=bias.contiguous(), relu=relu)
+        ctx.relu = relu
+        ctx.save_for_backward(x, wm, mask, y if relu else x.new_empty(0))
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, wm, mask, y = ctx.saved_tensors
+        gy = gy.contiguous()
+        relu_of = y if ctx.relu else None     # the ReLU derivative (y > 0) is applied inside the GEMMs' operand staging
+        scale = _pow2_scale(gy)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_like(x)
+            _cabi.gemm_nt(gy, wm.t().contiguous(), gx, mask=relu_of, scale_a=scale)
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[3]:
+            # dW = dZ^T X and db = column sums of dZ in ONE launch straight from the row-major activations; K = rows,
+            # cut into pieces whose partial sums are added into gw / gb
+            out, inn = wm.shape
+            gw = torch.zeros_like(wm)
+            gb = torch.zeros(out, dtype=wm.dtype, device=wm.device)
+            k_split = max(1, min(592, x.shape[0] // 512))
+            if out > 128 and inn <= 128 and relu_of is None:
+                # a few rows over one 128-row tile (the last layer, 141 outputs): the transposed product X^T dY has ONE
+                # row tile instead of a second, nearly empty one that would stage the whole of X again
+                gwt = torch.zeros((inn, out), dtype=wm.dtype, device=wm.device)
+                _cabi.gemm_tn(x, gy, gwt, k_split=k_split, scale_b=scale)
+                gw, gb = gwt.t(), gy.sum(0)
+            elif inn + 1 <= 256:
+                _cabi.gemm_tn(gy, x, gw, k_split=k_split, mask=relu_of, colsum=gb, scale_a=scale)
+            else:  # wider than one accumulator tile: torch
+                gz = gy * (y > 0) if ctx.relu else gy
+                gw, gb = gz.t() @ x, gz.sum(0)
+            gw = gw * mask
+        return gx, gw, None, gb, None
+
+
+def _linear(h, lin, relu):
+    if _native_gemm() and h.is_cuda and h.dtype == torch.float32 and h.dim() == 2:
+        return _MaskedLinearFn.apply(h, lin.weight, lin.mask, lin.bias, relu)
+    h = F.linear(h, lin.mask * lin.weight, lin.bias)
+    return torch.relu(h) if relu else h
+
+
 def _hyper_phi(t, x, c):
     h = x if c is None else torch.cat((x, c), dim=-1)
     lins = t.hyper.linears()
     for i, lin in enumerate(lins):
-        h = F.linear(h, lin.mask * lin.weight, lin.bias)
-        if i < len(lins) - 1:
-            h = torch.relu(h)
+        h = _linear(h, lin, i < len(lins) - 1)
     return h.unflatten(-1, (t.features, t.total))
 
 

@@ -765,6 +765,75 @@ def test_fused_sigmoid_logit_bridges(cuda, name, gemm, dtype):
     assert err < (5e-5 if dtype == torch.float32 else 1e-10), err   # fp32: logit of the kernel vs torch differ by rounding, amplified by the flow
 
 
+def test_masked_linear_fn_gradients(cuda):
+    """`_MaskedLinearFn` (forward, dX, dW on tcgen05 via mf_gemm_nt_3xf16) against fp64 arithmetic with the SAME ReLU
+    mask (the mask of a pre-activation within rounding of zero is a matter of arithmetic, not of correctness)."""
+    from memflow_msci_project_b200.flows import _autograd as ag
+    g = torch.Generator().manual_seed(4)
+    rows, inn, out = 5000, 68, 128
+    x = torch.randn(rows, inn, generator=g).to(cuda).requires_grad_(True)
+    w = (torch.randn(out, inn, generator=g) / inn ** 0.5).to(cuda).requires_grad_(True)
+    mask = (torch.rand(out, inn, generator=g) > 0.4).to(cuda)
+    b = torch.randn(out, generator=g).to(cuda).requires_grad_(True)
+    gy = (torch.randn(rows, out, generator=g) * 1e-6 * torch.exp(2 * torch.randn(rows, 1, generator=g))).to(cuda)
+    for relu in (True, False):
+        for t in (x, w, b):
+            t.grad = None
+        y = ag._MaskedLinearFn.apply(x, w, mask, b, relu)
+        y.backward(gy)
+        wm64 = (mask * w).double().detach()
+        pre = x.double().detach() @ wm64.t() + b.double().detach()
+        ref_y = pre.clamp_min(0) if relu else pre
+        gz = gy.double() * (y.detach() > 0) if relu else gy.double()
+        ref = (gz @ wm64, (gz.t() @ x.double().detach()) * mask, gz.sum(0))
+
+        def rel(a, r):
+            return ((a.double() - r).norm() / r.norm()).item()
+
+        assert rel(y.detach(), ref_y) < 2e-6
+        errs = [rel(x.grad, ref[0]), rel(w.grad, ref[1]), rel(b.grad, ref[2])]
+        assert max(errs) < 1e-5, errs
+        assert (w.grad[~mask] == 0).all()
+
+
+@pytest.mark.parametrize("name", ["TF-A", "UF-common"])
+def test_native_hypernet_backward_matches_torch_gemms(cuda, monkeypatch, name):
+    """fp32 training step: the hyper-network recompute / dX / dW GEMMs on tcgen05 (mf_gemm_nt_3xf16, `_MaskedLinearFn`)
+    against the same backward with torch's fp32 GEMMs (MEMFLOW_B200_TORCH_GEMM=1) and against the fp64 gradients.  Whole
+    flows are compared loosely: a hidden pre-activation within rounding of zero gets a different ReLU mask in different
+    arithmetic, and one such flip in 4e5 activations moves a gradient by ~1e-3 of its norm (both fp32 backwards show it
+    against fp64); the GEMMs themselves are pinned by the test above."""
+    flow = build(name, cuda, torch.float32, mode="default")
+    x, c = inputs(flow, 3000, 21, cuda, torch.float32, outside_frac=0.0)
+
+    def grads(f, xx, cc):
+        for p in f.parameters():
+            p.grad = None
+        xx = xx.detach().clone().requires_grad_(True)
+        cc = cc.detach().clone().requires_grad_(True)
+        (-f(cc).log_prob(xx).mean()).backward()
+        return [xx.grad.double(), cc.grad.double()] + [p.grad.double().clone() for p in f.parameters() if p.grad is not None]
+
+    g_native = grads(flow, x, c)
+    monkeypatch.setenv("MEMFLOW_B200_TORCH_GEMM", "1")
+    g_torch = grads(flow, x, c)
+    monkeypatch.delenv("MEMFLOW_B200_TORCH_GEMM")
+    flow64 = build(name, cuda, torch.float64, mode="default")
+    flow64.load_state_dict(flow.state_dict())
+    g64 = grads(flow64, x.double(), c.double())
+    assert len(g_native) == len(g_torch) == len(g64) and len(g_native) > 4
+
+    def rel(a, b):
+        return ((a - b).norm() / b.norm().clamp_min(1e-300)).item()
+
+    errs = [(rel(a, r), rel(b, r)) for a, b, r in zip(g_native, g_torch, g64)]
+    print("    gradient error vs fp64 (native, torch fp32): " + ", ".join(f"({ea:.1e}, {eb:.1e})" for ea, eb in errs))
+    for ea, eb in errs:
+        assert ea < 5e-3, (ea, eb)
+    med_native, med_torch = (sorted(e[i] for e in errs)[len(errs) // 2] for i in (0, 1))
+    assert med_native < max(3 * med_torch, 2e-5)   # the typical tensor is as close to fp64 as with torch's fp32 GEMMs
+
+
 def test_context_group_under_autograd(cuda):
     """with grad enabled, flow(c, ctx_group=G) must run the kernel with the grouped descriptor and give
     the gradients of the same flow fed the context repeated G times (context gradient summed over each group)."""

@@ -3,7 +3,8 @@
 per GPU (x10 objects), Adam, and ONE flat NCCL gradient all-reduce per step under torchrun.
 
 The forward of log_prob and rsample runs in the fused sm_100a kernels; the backward recomputes the flow transform by
-transform (flows/_autograd.py): hyper-network in torch (cuBLAS), spline forward / backward in the
+transform (flows/_autograd.py): hyper-network GEMMs (recompute, dX, dW) on tcgen05 through
+mf_gemm_nt_3xf16 (MEMFLOW_B200_TORCH_GEMM=1: torch / cuBLAS, the round-1 backward), spline forward / backward in the
 native kernels mf_rqs_transform / mf_rqs_backward.
 
     python tools/bench_train.py [--events 65536] [--steps 3] [--warmup 2] [--no-sampling-loss]
@@ -78,7 +79,7 @@ def main():
                           "events_per_gpu": args.events, "objects_per_event": args.objects, "n_gpus": world, "ms_per_step": ms,
                           "events_per_s": args.events * world / ms * 1e3, "parameters": nparam, "loss": float(loss.item()),
                           "fused_kernel_launches_per_step": (_cabi.launch_count() - l0) / args.steps,
-                          "backward": "recompute per transform: torch hyper-network (cuBLAS) + native spline forward/backward kernels", "peak_mem_GB": torch.cuda.max_memory_allocated() / 2**30}), flush=True)
+                          "backward": ("recompute per transform: torch hyper-network (cuBLAS)" if os.environ.get("MEMFLOW_B200_TORCH_GEMM") == "1" else "recompute per transform: hyper-network GEMMs on tcgen05 (mf_gemm_nt_3xf16)") + " + native spline forward/backward kernels", "peak_mem_GB": torch.cuda.max_memory_allocated() / 2**30}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
