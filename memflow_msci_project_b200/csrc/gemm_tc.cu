@@ -39,7 +39,7 @@ struct GemmArgs {
   int relu, k_split;
   long long kb_per_split;  // K-blocks of 64 per K-range
   const float* scale_a; const float* scale_b;
-  int vec_a, vec_b;     // rows are 16-byte aligned: float4 loads
+  int vec_a, vec_b, vec_m;  // rows are 16-byte aligned: float4 loads
   int trans;            // 0: C = A B^T with A [M,K], B [N,K] (K contiguous); 1: C = A^T B with A [K,M], B [K,N] (K = rows)
   const float* mask; long long ldm;  // optional, same shape as A: A is multiplied by (mask > 0) (ReLU derivative)
   float* colsum;        // trans = 1: optional [M] output, += sum_k A[k, m] (the bias gradient), as column N of the product
@@ -49,8 +49,8 @@ struct GemmArgs {
 
 // 32 consecutive columns [k0, k0 + 32) of one operand row -> hi / lo planes of the K-block (half = 0 / 1: which half of
 // the 64 columns); src == nullptr: a row past the end of the matrix (zeros)
-__device__ __forceinline__ void stage_half_row(const float* src, const float* msk, long long k_left, bool vec, float scale,
-                                               unsigned char* hi, unsigned char* lo, int r, int half) {
+__device__ __forceinline__ void stage_half_row(const float* src, const float* msk, long long k_left, bool vec, bool vec_m,
+                                               float scale, unsigned char* hi, unsigned char* lo, int r, int half) {
   float v[32];
   if (src == nullptr || k_left <= 0) {
 #pragma unroll
@@ -66,8 +66,17 @@ __device__ __forceinline__ void stage_half_row(const float* src, const float* ms
     for (int e = 0; e < 32; ++e) v[e] = (e < k_left) ? __ldg(src + e) : 0.f;
   }
   if (msk != nullptr && src != nullptr) {
+    if (vec_m && k_left >= 32) {
 #pragma unroll
-    for (int e = 0; e < 32; ++e) v[e] = (e < k_left && __ldg(msk + e) > 0.f) ? v[e] : 0.f;
+      for (int q = 0; q < 8; ++q) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(msk) + q);
+        v[4 * q] = t.x > 0.f ? v[4 * q] : 0.f; v[4 * q + 1] = t.y > 0.f ? v[4 * q + 1] : 0.f;
+        v[4 * q + 2] = t.z > 0.f ? v[4 * q + 2] : 0.f; v[4 * q + 3] = t.w > 0.f ? v[4 * q + 3] : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) v[e] = (e < k_left && __ldg(msk + e) > 0.f) ? v[e] : 0.f;
+    }
   }
 #pragma unroll
   for (int c = 0; c < 4; ++c) {  // four 16-byte chunks of 8 columns
@@ -88,7 +97,7 @@ __device__ __forceinline__ void stage_half_row(const float* src, const float* ms
 // the 2-byte shared-memory stores of a warp fall into one 128-byte row (no bank conflicts).
 __device__ __forceinline__ void stage_tn(const float* base, long long ld, const float* msk, long long ldm, long long k0,
                                          long long K, long long c0, long long C, int R, int ones_col, float scale, bool vec,
-                                         unsigned char* hi, unsigned char* lo, int tid) {
+                                         bool vec_m, unsigned char* hi, unsigned char* lo, int tid) {
   const int quarters = (R + 31) / 32;
   for (int idx = tid; idx < 64 * quarters; idx += kGemmThreads) {
     const int k = idx & 63, q = idx >> 6;
@@ -107,8 +116,18 @@ __device__ __forceinline__ void stage_tn(const float* base, long long ld, const 
       for (int j = 0; j < 32; ++j) v[j] = (live && cc + j < C) ? __ldg(base + kk * ld + cc + j) : 0.f;
     }
     if (msk != nullptr) {
+      if (live && vec_m && cc + 32 <= C) {
+        const float4* mp = reinterpret_cast<const float4*>(msk + kk * ldm + cc);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = (live && cc + j < C && __ldg(msk + kk * ldm + cc + j) > 0.f) ? v[j] : 0.f;
+        for (int j = 0; j < 8; ++j) {
+          const float4 t = __ldg(mp + j);
+          v[4 * j] = t.x > 0.f ? v[4 * j] : 0.f; v[4 * j + 1] = t.y > 0.f ? v[4 * j + 1] : 0.f;
+          v[4 * j + 2] = t.z > 0.f ? v[4 * j + 2] : 0.f; v[4 * j + 3] = t.w > 0.f ? v[4 * j + 3] : 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = (live && cc + j < C && __ldg(msk + kk * ldm + cc + j) > 0.f) ? v[j] : 0.f;
+      }
     }
     if (ones_col >= 0 && ones_col >= 32 * q && ones_col < 32 * q + 32) {
 #pragma unroll
@@ -130,7 +149,7 @@ __device__ __forceinline__ void stage_tn(const float* base, long long ld, const 
   }
 }
 
-__global__ void __launch_bounds__(kGemmThreads, 2) gemm_nt_kernel(const __grid_constant__ GemmArgs g) {
+__global__ void __launch_bounds__(kGemmThreads, 3) gemm_nt_kernel(const __grid_constant__ GemmArgs g) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar[2];
   __shared__ uint32_t tmem_base_s;
@@ -165,21 +184,21 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_nt_kernel(const __grid_c
     if (it >= g.nbuf) mbar_wait(&bar[b], (uint32_t)(((it / g.nbuf) - 1) & 1));  // the MMAs that read this buffer have retired
     const long long k0 = kb * 64;
     if (g.trans) {
-      stage_tn(g.A, g.lda, g.mask, g.ldm, k0, g.K, m0, g.M, 128, -1, sa, g.vec_a != 0, a_hi, a_lo, tid);
-      stage_tn(g.B, g.ldb, nullptr, 0, k0, g.K, 0, g.N, g.Np, g.colsum ? g.N : -1, sb, g.vec_b != 0, b_hi, b_lo, tid);
+      stage_tn(g.A, g.lda, g.mask, g.ldm, k0, g.K, m0, g.M, 128, -1, sa, g.vec_a != 0, g.vec_m != 0, a_hi, a_lo, tid);
+      stage_tn(g.B, g.ldb, nullptr, 0, k0, g.K, 0, g.N, g.Np, g.colsum ? g.N : -1, sb, g.vec_b != 0, false, b_hi, b_lo, tid);
     } else {
       // A: 128 rows x 2 halves = 256 half rows, one per thread
       {
         const int r = tid >> 1, half = tid & 1;
         const long long row = m0 + r, kk = k0 + half * 32;
         stage_half_row(row < g.M ? g.A + row * g.lda + kk : nullptr, (row < g.M && g.mask) ? g.mask + row * g.ldm + kk : nullptr,
-                       g.K - kk, g.vec_a != 0, sa, a_hi, a_lo, r, half);
+                       g.K - kk, g.vec_a != 0, g.vec_m != 0, sa, a_hi, a_lo, r, half);
       }
       // B: Np rows x 2 halves
       for (int i = tid; i < 2 * g.Np; i += kGemmThreads) {
         const int r = i >> 1, half = i & 1;
         const long long kk = k0 + half * 32;
-        stage_half_row(r < g.N ? g.B + (long long)r * g.ldb + kk : nullptr, nullptr, g.K - kk, g.vec_b != 0, sb, b_hi, b_lo, r, half);
+        stage_half_row(r < g.N ? g.B + (long long)r * g.ldb + kk : nullptr, nullptr, g.K - kk, g.vec_b != 0, false, sb, b_hi, b_lo, r, half);
       }
     }
     fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core
@@ -286,6 +305,7 @@ static int gemm_launch(int trans, const float* d_a, int64_t lda, const float* d_
   g.scale_a = d_scale_a; g.scale_b = d_scale_b;
   g.vec_a = ((reinterpret_cast<uintptr_t>(d_a) & 15u) == 0 && lda % 4 == 0) ? 1 : 0;
   g.vec_b = ((reinterpret_cast<uintptr_t>(d_b) & 15u) == 0 && ldb % 4 == 0) ? 1 : 0;
+  g.vec_m = (d_mask && (reinterpret_cast<uintptr_t>(d_mask) & 15u) == 0 && ldm % 4 == 0) ? 1 : 0;
   g.nbuf = (g.kb_per_split > 3) ? 2 : 1;
   g.tmem_cols = 32;
   while (g.tmem_cols < g.Np) g.tmem_cols *= 2;

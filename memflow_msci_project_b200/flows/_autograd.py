@@ -114,7 +114,7 @@ class _MaskedLinearFn(torch.autograd.Function):
             gw = torch.zeros_like(wm)
             gb = torch.zeros(out, dtype=wm.dtype, device=wm.device)
             k_split = max(1, min(592, x.shape[0] // 512))
-            if out > 128 and inn <= 128 and relu_of is None:
+            if 128 < out <= 256 and inn <= 128 and relu_of is None:
                 # a few rows over one 128-row tile (the last layer, 141 outputs): the transposed product X^T dY has ONE
                 # row tile instead of a second, nearly empty one that would stage the whole of X again
                 gwt = torch.zeros((inn, out), dtype=wm.dtype, device=wm.device)
