@@ -22,7 +22,11 @@ def _err(c, ref, a, b):
 
 
 @pytest.mark.parametrize("m,n,k,bias,relu", [(1000, 128, 68, True, True), (4099, 141, 128, True, False), (300, 128, 141, False, False),
-                                              (128, 16, 64, False, False), (77, 256, 200, True, True), (513, 300, 96, True, False)])
+                                              (128, 16, 64, False, False), (77, 256, 200, True, True), (513, 300, 96, True, False),
+                                              # K = 64 / 128 with several row tiles: the persistent kernel (resident weights,
+                                              # bulk-copied A K-blocks), incl. a ragged last tile and more tiles than SMs
+                                              (5000, 128, 128, True, True), (2001, 68, 128, False, False), (1000, 128, 64, True, False),
+                                              (148 * 128 * 2 + 300, 141, 128, True, True)])
 def test_gemm_nt_matches_fp64(cuda, m, n, k, bias, relu):
     g = torch.Generator().manual_seed(m + n + k)
     a = torch.randn(m, k, generator=g).to(cuda)
@@ -92,9 +96,9 @@ def test_gemm_tn_weight_gradient_with_relu_mask_and_bias_gradient(cuda, rows, ou
         assert ((gb.double() - ref_b).norm() / ref_b.norm()).item() < 3e-5
 
 
-def test_gemm_nt_with_relu_mask(cuda):
+@pytest.mark.parametrize("rows,out,inn", [(3001, 141, 128), (3001, 128, 128), (40000, 128, 68)])
+def test_gemm_nt_with_relu_mask(cuda, rows, out, inn):
     g = torch.Generator().manual_seed(3)
-    rows, out, inn = 3001, 141, 128
     dy = torch.randn(rows, out, generator=g).to(cuda)
     y = torch.randn(rows, out, generator=g).clamp_min(0).to(cuda)
     wt = (torch.randn(inn, out, generator=g) / out ** 0.5).to(cuda)      # W^T [in, out]
