@@ -53,9 +53,15 @@ def main():
             loss = loss + torch.nn.functional.huber_loss(xs, x)
         loss.backward()
         if world > 1:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
             all_reduce_gradients(flow.parameters())
+            e1.record()
+            ar_events.append((e0, e1))
         opt.step()
         return loss
+
+    ar_events = []
 
     for _ in range(args.warmup):
         step()
@@ -63,6 +69,7 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     l0 = _cabi.launch_count()
+    ar_events.clear()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(args.steps):
@@ -73,11 +80,12 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
+    ar_ms = sum(e0.elapsed_time(e1) for e0, e1 in ar_events) / max(1, args.steps)   # flat-buffer gradient all-reduce per step
     if rank == 0:
         print(json.dumps({"config": "transfer-flow training step: likelihood" + ("" if args.no_sampling_loss else " + sampling (Huber) loss") +
                           ", TF-A (D=3,C=65,T=5,K=16,[128]x4), Adam, flat NCCL gradient all-reduce",
                           "events_per_gpu": args.events, "objects_per_event": args.objects, "n_gpus": world, "ms_per_step": ms,
-                          "events_per_s": args.events * world / ms * 1e3, "parameters": nparam, "loss": float(loss.item()),
+                          "events_per_s": args.events * world / ms * 1e3, "all_reduce_ms_per_step": ar_ms, "parameters": nparam, "loss": float(loss.item()),
                           "fused_kernel_launches_per_step": (_cabi.launch_count() - l0) / args.steps,
                           "backward": ("recompute per transform: torch hyper-network (cuBLAS)" if os.environ.get("MEMFLOW_B200_TORCH_GEMM") == "1" else "recompute per transform: hyper-network GEMMs on tcgen05 (mf_gemm_nt_3xf16)") + " + native spline forward/backward kernels", "peak_mem_GB": torch.cuda.max_memory_allocated() / 2**30}), flush=True)
     if world > 1:
