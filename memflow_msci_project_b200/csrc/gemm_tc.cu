@@ -19,6 +19,7 @@
 // two or three CTAs share an SM and hide each other's load / MMA / store latencies.  With k_split > 1 the partial
 // sums of the K-ranges are added into C with red.global.add.f32 (C must be zeroed by the caller).
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "spline_reg.cuh"
@@ -46,6 +47,9 @@ struct GemmArgs {
   int nbuf;             // operand buffers: 2 when a CTA walks many K-blocks (staging overlaps the MMAs), else 1 (more CTAs per SM)
   int tmem_cols;        // power of two >= Np
 };
+
+__device__ __forceinline__ void store_half_row(const float* v, float scale, unsigned char* hi, unsigned char* lo, int r,
+                                               int half);
 
 // 32 consecutive columns [k0, k0 + 32) of one operand row -> hi / lo planes of the K-block (half = 0 / 1: which half of
 // the 64 columns); src == nullptr: a row past the end of the matrix (zeros)
@@ -78,6 +82,12 @@ __device__ __forceinline__ void stage_half_row(const float* src, const float* ms
       for (int e = 0; e < 32; ++e) v[e] = (e < k_left && __ldg(msk + e) > 0.f) ? v[e] : 0.f;
     }
   }
+  store_half_row(v, scale, hi, lo, r, half);
+}
+
+// 32 consecutive K values of operand row r (half = which half of the 64-wide K-block) -> fp16 hi / lo planes
+__device__ __forceinline__ void store_half_row(const float* v, float scale, unsigned char* hi, unsigned char* lo, int r,
+                                               int half) {
 #pragma unroll
   for (int c = 0; c < 4; ++c) {  // four 16-byte chunks of 8 columns
     uint4 h, l;
@@ -235,43 +245,204 @@ __global__ void __launch_bounds__(kGemmThreads, 3) gemm_nt_kernel(const __grid_c
       const float inv = 1.f / (sa * sb);
       const bool add_bias = g.bias != nullptr && blockIdx.y == 0;
       const long long row0 = m0 + warp * 32;
+      const int rows_w = (int)max(0LL, min(32LL, g.M - row0));  // rows of this warp inside the matrix
       for (int cb = 0; cb < g.Np; cb += 64) {
+        // this block's biases: lane l holds columns cb + l and cb + 32 + l (one coalesced load instead of an L2 round
+        // trip per element: with this kernel's shared-memory footprint little L1 is left), spread by shuffles
+        const float bias_lo = (add_bias && cb + lane < g.N) ? __ldg(g.bias + cb + lane) : 0.f;
+        const float bias_hi = (add_bias && cb + 32 + lane < g.N) ? __ldg(g.bias + cb + 32 + lane) : 0.f;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int c0 = cb + 16 * q;
-          if (c0 < g.Np) {
+          if (c0 < g.Np) {   // warp-uniform
             float v[16];
             tc::tmem_ld16(taddr + c0, v);
             tc::tmem_ld_wait();
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
-              float x = v[e] * inv;
-              if (add_bias && c0 + e < g.N) x += __ldg(g.bias + c0 + e);
+              const float bv = __shfl_sync(0xffffffffu, (q < 2) ? bias_lo : bias_hi, (16 * q + e) & 31);
+              float x = v[e] * inv + bv;
               if (g.relu) x = fmaxf(x, 0.f);
               scratch[lane * 65 + 16 * q + e] = x;
             }
           }
         }
         __syncwarp();
-        for (int r = 0; r < 32; ++r) {
-          const long long row = row0 + r;
-          if (row >= g.M) break;
-          float* dst = g.C + row * g.ldc + cb;
+        // rows of C: eight rows per step, loads first, then stores (a rolled load -> store loop is a chain of
+        // shared-memory latencies: 4.5 k cycles per warp and tile, ncu)
+        for (int r0 = 0; r0 < rows_w; r0 += 8) {
+          float x0[8], x1[8];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int c = lane + 32 * h;
-            if (cb + c < g.N) {
-              const float x = scratch[r * 65 + c];
-              if (g.k_split > 1) atomicAdd(dst + c, x);
-              else dst[c] = x;
-            } else if (g.colsum != nullptr && cb + c == g.N) {
-              atomicAdd(g.colsum + row, scratch[r * 65 + c]);
+          for (int u = 0; u < 8; ++u) {
+            x0[u] = scratch[(r0 + u) * 65 + lane];
+            x1[u] = scratch[(r0 + u) * 65 + lane + 32];
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            if (r0 + u < rows_w) {
+              const long long row = row0 + r0 + u;
+              float* dst = g.C + row * g.ldc + cb;
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int c = lane + 32 * h;
+                const float x = h ? x1[u] : x0[u];
+                if (cb + c < g.N) {
+                  if (g.k_split > 1) atomicAdd(dst + c, x);
+                  else dst[c] = x;
+                } else if (g.colsum != nullptr && cb + c == g.N) {
+                  atomicAdd(g.colsum + row, x);
+                }
+              }
             }
           }
         }
         __syncwarp();
       }
     }
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, (uint32_t)g.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Persistent variant of the non-transposed product for K = 64 or 128 and a CONTIGUOUS A (lda = K: every hidden-layer
+// GEMM of the training step): one CTA per SM walks 128-row tiles of A.  B (the weights) is converted ONCE per CTA and
+// stays in shared memory; a whole raw fp32 tile of A (128 rows x K, one contiguous block of global memory) arrives by ONE
+// bulk async copy completing on an mbarrier, requested as soon as the previous tile has been converted, so the
+// global-memory latency -- what bounds the one-tile-per-CTA kernel above (25 % issue-active, ncu) -- hides behind the
+// previous tile's MMAs and epilogue.  All eight warps convert the landed tile: consecutive threads take consecutive
+// 16-byte pieces (conflict-free reads), each piece = four k-values of one row = one 8-byte store per operand plane.
+// (A first persistent version fetched the tile as 128 row pieces of 256 bytes, one bulk copy per thread: 0.54 ms per
+// GEMM instead of 0.40 -- small bulk copies cost ~100 cycles each in the copy engine.)
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_nt_persistent_kernel(const __grid_constant__ GemmArgs g) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t raw_full, mma_done;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_kb = (int)(g.K / 64);
+  const int q4 = (int)(g.K / 4), q4_shift = (g.K == 128) ? 5 : 4;  // float4 pieces per row
+  const uint32_t b_plane = (uint32_t)g.Np * 128u, a_plane = 128u * 128u;
+  unsigned char* b_conv = smem;                                   // [n_kb][hi | lo]
+  unsigned char* conv = b_conv + (size_t)n_kb * 2 * b_plane;      // [n_kb][hi | lo], 1024-byte aligned (b_plane % 2048 == 0)
+  unsigned char* raw = conv + (size_t)n_kb * 2 * a_plane;         // [128 rows x K] fp32
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, (uint32_t)g.tmem_cols);
+  if (tid == 0) {
+    mbar_init(&raw_full, 1);
+    mbar_init(&mma_done, 1);
+    fence_mbar_init();
+  }
+  const float sa = g.scale_a ? __ldg(g.scale_a) : 1.f, sb = g.scale_b ? __ldg(g.scale_b) : 1.f;
+  // B: all K-blocks, converted once
+  for (int kb = 0; kb < n_kb; ++kb)
+    for (int i = tid; i < 2 * g.Np; i += kGemmThreads) {
+      const int r = i >> 1, half = i & 1;
+      const long long kk = (long long)kb * 64 + half * 32;
+      stage_half_row(r < g.N ? g.B + (long long)r * g.ldb + kk : nullptr, nullptr, g.K - kk, g.vec_b != 0, false, sb,
+                     b_conv + (size_t)kb * 2 * b_plane, b_conv + (size_t)kb * 2 * b_plane + b_plane, r, half);
+    }
+  fence_proxy_async_smem();
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t idesc = tc::make_idesc_f16(0, 128, g.Np);
+  const long long m_tiles = (g.M + 127) / 128;
+  auto request = [&](long long tile) {  // the raw tile: one contiguous block
+    if (tid == 0 && tile < m_tiles) {
+      const long long rows = min((long long)128, g.M - tile * 128);
+      const uint32_t bytes = (uint32_t)(rows * g.K * 4);
+      mbar_expect_tx(&raw_full, bytes);
+      bulk_g2s(raw, g.A + tile * 128 * g.K, bytes, &raw_full);
+    }
+  };
+  request(blockIdx.x);
+  long long it = 0;
+  for (long long tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
+    const long long m0 = tile * 128;
+    const int rows = (int)min((long long)128, g.M - m0);
+    mbar_wait(&raw_full, (uint32_t)(it & 1));  // the raw tile has landed
+    // (the operand buffers are free: this tile's predecessor waited for its MMAs before its epilogue)
+    for (int f = tid; f < 128 * q4; f += kGemmThreads) {
+      const int r = f >> q4_shift, c4 = f & (q4 - 1);
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < rows) {
+        t = reinterpret_cast<const float4*>(raw)[f];
+        if (g.mask != nullptr) {
+          const float4 mk = __ldg(reinterpret_cast<const float4*>(g.mask + (m0 + r) * g.ldm) + c4);
+          t.x = mk.x > 0.f ? t.x : 0.f; t.y = mk.y > 0.f ? t.y : 0.f; t.z = mk.z > 0.f ? t.z : 0.f; t.w = mk.w > 0.f ? t.w : 0.f;
+        }
+      }
+      uint2 h, l;
+      tc::split_f16(t.x * sa, t.y * sa, h.x, l.x);
+      tc::split_f16(t.z * sa, t.w * sa, h.y, l.y);
+      const int kb = c4 >> 4, k = (c4 & 15) * 4;
+      unsigned char* hi = conv + (size_t)kb * 2 * a_plane;
+      const uint32_t off = (uint32_t)r * 128u + (uint32_t)((((k >> 3) ^ (r & 7)) << 4) + (k & 7) * 2);
+      *reinterpret_cast<uint2*>(hi + off) = h;
+      *reinterpret_cast<uint2*>(hi + a_plane + off) = l;
+    }
+    fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core
+    __syncthreads();           // (also: every thread is done with the raw tile)
+    if (tid == 0) {
+      tc::fence_after_thread_sync();
+      for (int kb = 0; kb < n_kb; ++kb) {
+        const uint32_t ah = smem_u32(conv + (size_t)kb * 2 * a_plane), al = ah + a_plane;
+        const uint32_t bh = smem_u32(b_conv + (size_t)kb * 2 * b_plane), bl = bh + b_plane;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t dah = tc::make_smem_desc(ah + ks * 32u), dal = tc::make_smem_desc(al + ks * 32u);
+          const uint64_t dbh = tc::make_smem_desc(bh + ks * 32u), dbl = tc::make_smem_desc(bl + ks * 32u);
+          tc::mma_f16_ss(tmem, dah, dbh, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+          tc::mma_f16_ss(tmem, dah, dbl, idesc, 1u);
+          tc::mma_f16_ss(tmem, dal, dbh, idesc, 1u);
+        }
+      }
+      tc::mma_commit(&mma_done);
+    }
+    request(tile + gridDim.x);  // the raw buffer is free again: the next tile travels during the MMAs and the epilogue
+    mbar_wait(&mma_done, (uint32_t)(it & 1));
+    tc::fence_after_thread_sync();
+    {
+      // Epilogue by ALL eight warps: warp w reads TMEM lanes 32 (w % 4) .. + 31 (its rows); warps 0-3 take the 16-column
+      // blocks with an even index, warps 4-7 the odd ones (with four warps the epilogue was ~70 % of a tile, ncu: the
+      // other four waited at the next barrier).  Each block goes through the warp's scratch tile (row stride 17 floats)
+      // so that C is written in 64-byte row pieces, two rows per store.
+      const int wq = warp & 3, wh = warp >> 2;
+      const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16);
+      const float inv = 1.f / (sa * sb);
+      const long long row0 = m0 + wq * 32;
+      const int rows_w = (int)max(0LL, min(32LL, g.M - row0));
+      float* sc = reinterpret_cast<float*>(raw + (size_t)128 * g.K * 4) + (size_t)warp * 32 * 17;
+      for (int c0 = 16 * wh; c0 < g.Np; c0 += 32) {
+        const float bias_l = (g.bias != nullptr && lane < 16 && c0 + lane < g.N) ? __ldg(g.bias + c0 + lane) : 0.f;
+        float v[16];
+        tc::tmem_ld16(taddr + c0, v);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          float x = v[e] * inv + __shfl_sync(0xffffffffu, bias_l, e);
+          if (g.relu) x = fmaxf(x, 0.f);
+          sc[lane * 17 + e] = x;
+        }
+        __syncwarp();
+        const int c = lane & 15, rsub = lane >> 4;
+        if (c0 + c < g.N) {
+          for (int r0 = 0; r0 < rows_w; r0 += 16) {
+            float x0[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) x0[u] = sc[(r0 + 2 * u + rsub) * 17 + c];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              if (r0 + 2 * u + rsub < rows_w) g.C[(row0 + r0 + 2 * u + rsub) * g.ldc + c0 + c] = x0[u];
+          }
+        }
+        __syncwarp();
+      }
+      tc::fence_before_thread_sync();
+    }
+    // (the next tile's conversion only touches shared memory; its MMAs are issued behind the __syncthreads above, i.e.
+    // after every warp has left this epilogue)
   }
   tc::fence_before_thread_sync();
   __syncthreads();
@@ -314,8 +485,26 @@ static int gemm_launch(int trans, const float* d_a, int64_t lda, const float* d_
   g.tmem_cols = 32;
   while (g.tmem_cols < g.Np) g.tmem_cols *= 2;
   const size_t smem = std::max<size_t>((size_t)g.nbuf * (2 * 128 * 128 + 2 * (size_t)g.Np * 128), 4 * 32 * 65 * 4);
-  MF_CUDA_CHECK(cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long m_tiles = (m + 127) / 128;
+  // persistent variant: resident weights, bulk-copied A K-blocks (see gemm_nt_persistent_kernel)
+  const bool mask_ok = d_mask == nullptr || (ldm == k && (reinterpret_cast<uintptr_t>(d_mask) & 15u) == 0);
+  // (MF_GEMM_PERSISTENT=0 selects the one-tile-per-CTA kernel for every shape: the comparison of tools/bench_gemm.py)
+  static const bool use_persistent = !(getenv("MF_GEMM_PERSISTENT") != nullptr && getenv("MF_GEMM_PERSISTENT")[0] == '0');
+  if (use_persistent && !trans && g.k_split == 1 && (k == 64 || k == 128) && lda == k && (reinterpret_cast<uintptr_t>(d_a) & 15u) == 0 &&
+      mask_ok && m_tiles >= 2) {
+    const size_t n_kb = (size_t)(k / 64);
+    const size_t psmem = n_kb * 2 * (size_t)g.Np * 128 + n_kb * 2 * 128 * 128 + (size_t)128 * k * 4 + 8 * 32 * 17 * 4;
+    if (psmem <= 225 * 1024) {
+      int dev = 0, sms = 148;
+      MF_CUDA_CHECK(cudaGetDevice(&dev));
+      MF_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      MF_CUDA_CHECK(cudaFuncSetAttribute(gemm_nt_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+      const unsigned pgrid = (unsigned)std::min<long long>(m_tiles, sms);
+      gemm_nt_persistent_kernel<<<pgrid, kGemmThreads, psmem, static_cast<cudaStream_t>(stream)>>>(g);
+      return post_launch("gemm_nt_persistent_kernel");
+    }
+  }
+  MF_CUDA_CHECK(cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   MF_REQUIRE(m_tiles <= 0x7fffffffLL && splits <= 65535, "%s: grid too large", who);
   dim3 grid((unsigned)m_tiles, (unsigned)splits);
   gemm_nt_kernel<<<grid, kGemmThreads, smem, static_cast<cudaStream_t>(stream)>>>(g);
