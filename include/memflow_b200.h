@@ -348,13 +348,16 @@ int64_t mf_flow_sched_offset(const mf_flow_desc* desc, int dtype, int gemm);
  * scripts/run_transferFlow_paperVersion_AllPartons_btag.py:385).  Row-major fp32 operands with leading dimensions;
  * n <= 256.  k_split > 1: the K range is cut into that many pieces whose partial sums are ADDED into C (the caller
  * zeroes C; no ReLU).  d_mask (optional, shaped like A, leading dimension ldm): A is multiplied by (mask > 0), the
- * derivative of the ReLU whose output is `mask`.  d_scale_a / d_scale_b: optional device scalars (powers of two) the
+ * derivative of the ReLU whose output is `mask`.  d_out_mask (optional, shaped like C, leading dimension ldo; k_split = 1):
+ * C is multiplied by (out_mask > 0) -- the input gradient of a layer fed by a ReLU leaves already masked for the
+ * layer below.  d_scale_a / d_scale_b: optional device scalars (powers of two) the
  * operands are multiplied by before the fp16 split -- gradients are far below the fp16 range --; the result is
  * divided by their product.
  */
 int mf_gemm_nt_3xf16(const float* d_a, int64_t lda, const float* d_b, int64_t ldb, float* d_c, int64_t ldc,
                      int64_t m, int32_t n, int64_t k, const float* d_bias, int32_t relu, int32_t k_split,
-                     const float* d_mask, int64_t ldm, const float* d_scale_a, const float* d_scale_b, void* stream);
+                     const float* d_mask, int64_t ldm, const float* d_out_mask, int64_t ldo,
+                     const float* d_scale_a, const float* d_scale_b, void* stream);
 /*
  * C[m, n] (+)= A[k, m]^T * B[k, n]: the weight gradient dW = dZ^T H of a linear layer straight from the row-major
  * activations (k = rows; A = dY [rows, out] with the optional ReLU mask, B = H [rows, in]); same arithmetic and

@@ -122,23 +122,26 @@ def rambo_forward_backward(desc: RamboDesc, r, g_mom, g_w, g_x1, g_x2, w_fwd, fu
     check(rc, "mf_rambo_forward_backward")
 
 
-def gemm_nt(a, b, c, bias=None, relu=False, k_split=1, mask=None, scale_a=None, scale_b=None):
+def gemm_nt(a, b, c, bias=None, relu=False, k_split=1, mask=None, out_mask=None, scale_a=None, scale_b=None):
     """c[m, n] (+)= (a * (mask > 0))[m, k] @ b[n, k].T (+ bias) (ReLU) on tcgen05, fp32-class (mf_gemm_nt_3xf16).  2-D fp32
     CUDA tensors with unit inner stride; any n (columns are processed 256 at a time)."""
     m, k = a.shape
     n = b.shape[0]
     assert b.shape[1] == k and c.shape == (m, n) and a.stride(1) == 1 and b.stride(1) == 1 and c.stride(1) == 1
     assert mask is None or (mask.shape == a.shape and mask.stride(1) == 1)
+    assert out_mask is None or (out_mask.shape == c.shape and out_mask.stride(1) == 1)
     with torch.cuda.device(a.device):
         for n0 in range(0, n, 256):
             n1 = min(n, n0 + 256)
             bb, cc = b[n0:n1], c[:, n0:n1]
+            om = out_mask[:, n0:n1] if out_mask is not None else None
             rc = lib().mf_gemm_nt_3xf16(_ptr(a), ctypes.c_int64(a.stride(0)), _ptr(bb), ctypes.c_int64(b.stride(0)), _ptr(cc),
                                         ctypes.c_int64(c.stride(0)), ctypes.c_int64(m), ctypes.c_int32(n1 - n0),
                                         ctypes.c_int64(k), _ptr(bias[n0:n1]) if bias is not None else ctypes.c_void_p(0),
                                         ctypes.c_int32(1 if relu else 0), ctypes.c_int32(k_split), _ptr(mask),
-                                        ctypes.c_int64(mask.stride(0) if mask is not None else 0), _ptr(scale_a), _ptr(scale_b),
-                                        _stream(a.device))
+                                        ctypes.c_int64(mask.stride(0) if mask is not None else 0), _ptr(om),
+                                        ctypes.c_int64(out_mask.stride(0) if out_mask is not None else 0), _ptr(scale_a),
+                                        _ptr(scale_b), _stream(a.device))
             check(rc, "mf_gemm_nt_3xf16")
 
 

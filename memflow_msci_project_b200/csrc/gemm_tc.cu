@@ -43,6 +43,7 @@ struct GemmArgs {
   int vec_a, vec_b, vec_m;  // rows are 16-byte aligned: float4 loads
   int trans;            // 0: C = A B^T with A [M,K], B [N,K] (K contiguous); 1: C = A^T B with A [K,M], B [K,N] (K = rows)
   const float* mask; long long ldm;  // optional, same shape as A: A is multiplied by (mask > 0) (ReLU derivative)
+  const float* out_mask; long long ldo;  // optional, shaped like C: C is multiplied by (out_mask > 0) (trans = 0, no split)
   float* colsum;        // trans = 1: optional [M] output, += sum_k A[k, m] (the bias gradient), as column N of the product
   int nbuf;             // operand buffers: 2 when a CTA walks many K-blocks (staging overlaps the MMAs), else 1 (more CTAs per SM)
   int tmem_cols;        // power of two >= Np
@@ -163,6 +164,77 @@ __device__ __forceinline__ void stage_tn(const float* base, long long ld, const 
   }
 }
 
+// Epilogue of warps 0-3 through shared memory (the operand buffers are free by then): a thread owns a ROW of the
+// accumulator, the rows of C are contiguous in global memory -- each warp transposes 32 rows x 64 columns through a
+// scratch tile (row stride 65 floats: conflict-free both ways) and writes / adds full 256-byte row pieces.
+__device__ __forceinline__ void gemm_epilogue(const GemmArgs& g, float* scratch_base, uint32_t tmem, long long m0, float sa,
+                                              float sb, int warp, int lane) {
+  {
+      // Epilogue through shared memory (the operand buffers are free now): a thread owns a ROW of the accumulator, the
+      // rows of C are contiguous in global memory -- each warp transposes 32 rows x 64 columns through a scratch tile
+      // (row stride 65 floats: conflict-free both ways) and writes full 256-byte row pieces.
+      float* scratch = scratch_base + (size_t)warp * 32 * 65;
+      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+      const float inv = 1.f / (sa * sb);
+      const bool add_bias = g.bias != nullptr && blockIdx.y == 0;
+      const long long row0 = m0 + warp * 32;
+      const int rows_w = (int)max(0LL, min(32LL, g.M - row0));  // rows of this warp inside the matrix
+      for (int cb = 0; cb < g.Np; cb += 64) {
+        // this block's biases: lane l holds columns cb + l and cb + 32 + l (one coalesced load instead of an L2 round
+        // trip per element: with this kernel's shared-memory footprint little L1 is left), spread by shuffles
+        const float bias_lo = (add_bias && cb + lane < g.N) ? __ldg(g.bias + cb + lane) : 0.f;
+        const float bias_hi = (add_bias && cb + 32 + lane < g.N) ? __ldg(g.bias + cb + 32 + lane) : 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int c0 = cb + 16 * q;
+          if (c0 < g.Np) {   // warp-uniform
+            float v[16];
+            tc::tmem_ld16(taddr + c0, v);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const float bv = __shfl_sync(0xffffffffu, (q < 2) ? bias_lo : bias_hi, (16 * q + e) & 31);
+              float x = v[e] * inv + bv;
+              if (g.relu) x = fmaxf(x, 0.f);
+              scratch[lane * 65 + 16 * q + e] = x;
+            }
+          }
+        }
+        __syncwarp();
+        // rows of C: eight rows per step, loads first, then stores (a rolled load -> store loop is a chain of
+        // shared-memory latencies: 4.5 k cycles per warp and tile, ncu)
+        for (int r0 = 0; r0 < rows_w; r0 += 8) {
+          float x0[8], x1[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            x0[u] = scratch[(r0 + u) * 65 + lane];
+            x1[u] = scratch[(r0 + u) * 65 + lane + 32];
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            if (r0 + u < rows_w) {
+              const long long row = row0 + r0 + u;
+              float* dst = g.C + row * g.ldc + cb;
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int c = lane + 32 * h;
+                const float x = h ? x1[u] : x0[u];
+                if (cb + c < g.N) {
+                  if (g.k_split > 1) atomicAdd(dst + c, x);
+                  else if (g.out_mask != nullptr) dst[c] = (__ldg(g.out_mask + row * g.ldo + cb + c) > 0.f) ? x : 0.f;
+                  else dst[c] = x;
+                } else if (g.colsum != nullptr && cb + c == g.N) {
+                  atomicAdd(g.colsum + row, x);
+                }
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
+      }
+}
+
 __global__ void __launch_bounds__(kGemmThreads, 3) gemm_nt_kernel(const __grid_constant__ GemmArgs g) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar[2];
@@ -236,69 +308,7 @@ __global__ void __launch_bounds__(kGemmThreads, 3) gemm_nt_kernel(const __grid_c
     const long long last = it - 1;
     mbar_wait(&bar[(g.nbuf == 2) ? (last & 1) : 0], (uint32_t)((last / g.nbuf) & 1));
     tc::fence_after_thread_sync();
-    if (warp < 4) {
-      // Epilogue through shared memory (the operand buffers are free now): a thread owns a ROW of the accumulator, the
-      // rows of C are contiguous in global memory -- each warp transposes 32 rows x 64 columns through a scratch tile
-      // (row stride 65 floats: conflict-free both ways) and writes full 256-byte row pieces.
-      float* scratch = reinterpret_cast<float*>(smem) + (size_t)warp * 32 * 65;
-      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
-      const float inv = 1.f / (sa * sb);
-      const bool add_bias = g.bias != nullptr && blockIdx.y == 0;
-      const long long row0 = m0 + warp * 32;
-      const int rows_w = (int)max(0LL, min(32LL, g.M - row0));  // rows of this warp inside the matrix
-      for (int cb = 0; cb < g.Np; cb += 64) {
-        // this block's biases: lane l holds columns cb + l and cb + 32 + l (one coalesced load instead of an L2 round
-        // trip per element: with this kernel's shared-memory footprint little L1 is left), spread by shuffles
-        const float bias_lo = (add_bias && cb + lane < g.N) ? __ldg(g.bias + cb + lane) : 0.f;
-        const float bias_hi = (add_bias && cb + 32 + lane < g.N) ? __ldg(g.bias + cb + 32 + lane) : 0.f;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int c0 = cb + 16 * q;
-          if (c0 < g.Np) {   // warp-uniform
-            float v[16];
-            tc::tmem_ld16(taddr + c0, v);
-            tc::tmem_ld_wait();
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const float bv = __shfl_sync(0xffffffffu, (q < 2) ? bias_lo : bias_hi, (16 * q + e) & 31);
-              float x = v[e] * inv + bv;
-              if (g.relu) x = fmaxf(x, 0.f);
-              scratch[lane * 65 + 16 * q + e] = x;
-            }
-          }
-        }
-        __syncwarp();
-        // rows of C: eight rows per step, loads first, then stores (a rolled load -> store loop is a chain of
-        // shared-memory latencies: 4.5 k cycles per warp and tile, ncu)
-        for (int r0 = 0; r0 < rows_w; r0 += 8) {
-          float x0[8], x1[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            x0[u] = scratch[(r0 + u) * 65 + lane];
-            x1[u] = scratch[(r0 + u) * 65 + lane + 32];
-          }
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            if (r0 + u < rows_w) {
-              const long long row = row0 + r0 + u;
-              float* dst = g.C + row * g.ldc + cb;
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const int c = lane + 32 * h;
-                const float x = h ? x1[u] : x0[u];
-                if (cb + c < g.N) {
-                  if (g.k_split > 1) atomicAdd(dst + c, x);
-                  else dst[c] = x;
-                } else if (g.colsum != nullptr && cb + c == g.N) {
-                  atomicAdd(g.colsum + row, x);
-                }
-              }
-            }
-          }
-        }
-        __syncwarp();
-      }
-    }
+    if (warp < 4) gemm_epilogue(g, reinterpret_cast<float*>(smem), tmem, m0, sa, sb, warp, lane);
   }
   tc::fence_before_thread_sync();
   __syncthreads();
@@ -401,6 +411,23 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_nt_persistent_kernel(con
       tc::mma_commit(&mma_done);
     }
     request(tile + gridDim.x);  // the raw buffer is free again: the next tile travels during the MMAs and the epilogue
+    // output mask (input gradient of a layer fed by a ReLU): this thread's mask values of the whole tile are requested
+    // NOW, into registers, so that their L2 latency passes under the MMAs (fetched inside the epilogue they doubled it)
+    float mk[5][2][8];
+    if (g.out_mask != nullptr) {
+      const int wq_ = warp & 3, wh_ = warp >> 2, c_ = lane & 15, rsub_ = lane >> 4;
+      const long long row0_ = m0 + wq_ * 32;
+#pragma unroll
+      for (int j = 0; j < 5; ++j)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int col = 16 * wh_ + 32 * j + c_;
+            const long long row = row0_ + 16 * h + 2 * u + rsub_;
+            mk[j][h][u] = (col < g.N && row < g.M) ? __ldg(g.out_mask + row * g.ldo + col) : 0.f;
+          }
+    }
     mbar_wait(&mma_done, (uint32_t)(it & 1));
     tc::fence_after_thread_sync();
     {
@@ -414,7 +441,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_nt_persistent_kernel(con
       const long long row0 = m0 + wq * 32;
       const int rows_w = (int)max(0LL, min(32LL, g.M - row0));
       float* sc = reinterpret_cast<float*>(raw + (size_t)128 * g.K * 4) + (size_t)warp * 32 * 17;
-      for (int c0 = 16 * wh; c0 < g.Np; c0 += 32) {
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const int c0 = 16 * wh + 32 * j;
+        if (c0 >= g.Np) break;
         const float bias_l = (g.bias != nullptr && lane < 16 && c0 + lane < g.N) ? __ldg(g.bias + c0 + lane) : 0.f;
         float v[16];
         tc::tmem_ld16(taddr + c0, v);
@@ -428,10 +458,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_nt_persistent_kernel(con
         __syncwarp();
         const int c = lane & 15, rsub = lane >> 4;
         if (c0 + c < g.N) {
-          for (int r0 = 0; r0 < rows_w; r0 += 16) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int r0 = 16 * h;
+            if (r0 >= rows_w) break;
             float x0[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) x0[u] = sc[(r0 + 2 * u + rsub) * 17 + c];
+            if (g.out_mask != nullptr) {
+#pragma unroll
+              for (int u = 0; u < 8; ++u) x0[u] = mk[j][h][u] > 0.f ? x0[u] : 0.f;
+            }
 #pragma unroll
             for (int u = 0; u < 8; ++u)
               if (r0 + 2 * u + rsub < rows_w) g.C[(row0 + r0 + 2 * u + rsub) * g.ldc + c0 + c] = x0[u];
@@ -449,6 +486,118 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_nt_persistent_kernel(con
   if (warp == 0) tc::tmem_dealloc(tmem, (uint32_t)g.tmem_cols);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Transposed product (weight gradient) with bulk-copied operands: for contiguous A [K, M <= 128] and B [K, N] a K-block
+// of 64 rows is ONE contiguous block of each matrix.  Thread 0 requests the raw fp32 blocks two K-blocks ahead (two
+// stages, completing on mbarriers); all warps transpose a landed block out of shared memory: a warp takes 32 consecutive
+// columns and a group of eight k -- eight conflict-free row reads, then every lane owns the eight k-values of its
+// column = one 16-byte chunk of the K-major operand row.  (The same mapping fed by global loads was the slowest of the
+// three tried above; out of shared memory it is ~300 instead of ~1 350 instructions per thread and K-block and no load
+// sits on the critical path.)  No ReLU mask here: the caller passes the masked gradient.
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_tn_tma_kernel(const __grid_constant__ GemmArgs g) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t raw_full[2], mma_done;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int M = (int)g.M, N = g.N;
+  const uint32_t a_plane = 128u * 128u, b_plane = (uint32_t)g.Np * 128u;
+  const uint32_t raw_a = 64u * (uint32_t)M * 4u, raw_b = 64u * (uint32_t)N * 4u;
+  const uint32_t raw_stage = (raw_a + raw_b + 127u) / 128u * 128u;
+  unsigned char* a_hi = smem;
+  unsigned char* a_lo = a_hi + a_plane;
+  unsigned char* b_hi = a_lo + a_plane;
+  unsigned char* b_lo = b_hi + b_plane;
+  unsigned char* raw = b_lo + b_plane;
+  const long long n_kb = (g.K + 63) / 64;
+  const long long kb0 = (long long)blockIdx.y * g.kb_per_split;
+  const long long kb1 = min(n_kb, kb0 + g.kb_per_split);
+  const long long n_it = kb1 - kb0;
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, (uint32_t)g.tmem_cols);
+  if (tid == 0) {
+    mbar_init(&raw_full[0], 1); mbar_init(&raw_full[1], 1); mbar_init(&mma_done, 1);
+    fence_mbar_init();
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  const uint32_t tmem = tmem_base_s;
+  const float sa = g.scale_a ? __ldg(g.scale_a) : 1.f, sb = g.scale_b ? __ldg(g.scale_b) : 1.f;
+  const uint32_t idesc = tc::make_idesc_f16(0, 128, g.Np);
+  auto request = [&](long long it) {
+    if (tid == 0 && it < n_it) {
+      const long long k0 = (kb0 + it) * 64;
+      const long long rows = min((long long)64, g.K - k0);
+      unsigned char* dst = raw + (size_t)(it & 1) * raw_stage;
+      uint64_t* bar = &raw_full[it & 1];
+      mbar_expect_tx(bar, (uint32_t)(rows * (M + N) * 4));
+      bulk_g2s(dst, g.A + k0 * M, (uint32_t)(rows * M * 4), bar);
+      bulk_g2s(dst + raw_a, g.B + k0 * N, (uint32_t)(rows * N * 4), bar);
+    }
+  };
+  // one operand: raw [64 k][C] fp32 -> K-major [R rows c][64 k] hi / lo planes
+  auto transpose = [&](const float* src, int C, int R, int rows, int ones_col, float scale, unsigned char* hi, unsigned char* lo) {
+    const int blocks = (R + 31) / 32;
+    for (int item = warp; item < 8 * blocks; item += kGemmThreads / 32) {
+      const int kg = item & 7, cb = item >> 3;
+      const int r = 32 * cb + lane;
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int k = 8 * kg + e;
+        float x = (k < rows && r < C) ? src[k * C + r] : 0.f;
+        if (r == ones_col) x = (k < rows) ? 1.f / scale : 0.f;  // (the operand scale is applied below)
+        v[e] = x * scale;
+      }
+      if (r < R) {
+        uint4 h, l;
+        tc::split_f16(v[0], v[1], h.x, l.x); tc::split_f16(v[2], v[3], h.y, l.y);
+        tc::split_f16(v[4], v[5], h.z, l.z); tc::split_f16(v[6], v[7], h.w, l.w);
+        const uint32_t off = (uint32_t)r * 128u + (uint32_t)((kg ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(hi + off) = h;
+        *reinterpret_cast<uint4*>(lo + off) = l;
+      }
+    }
+  };
+  request(0);
+  request(1);
+  for (long long it = 0; it < n_it; ++it) {
+    const int s = (int)(it & 1);
+    const long long k0 = (kb0 + it) * 64;
+    const int rows = (int)min((long long)64, g.K - k0);
+    mbar_wait(&raw_full[s], (uint32_t)((it >> 1) & 1));          // the raw blocks have landed
+    if (it >= 1) mbar_wait(&mma_done, (uint32_t)((it - 1) & 1));  // the previous K-block's MMAs have read the operands
+    const float* ra = reinterpret_cast<const float*>(raw + (size_t)s * raw_stage);
+    transpose(ra, M, 128, rows, -1, sa, a_hi, a_lo);
+    transpose(reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(ra) + raw_a), N, g.Np, rows,
+              g.colsum ? N : -1, sb, b_hi, b_lo);
+    fence_proxy_async_smem();
+    __syncthreads();  // (also: every thread is done with raw stage s)
+    if (tid == 0) {
+      tc::fence_after_thread_sync();
+      const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t dah = tc::make_smem_desc(ah + ks * 32u), dal = tc::make_smem_desc(al + ks * 32u);
+        const uint64_t dbh = tc::make_smem_desc(bh + ks * 32u), dbl = tc::make_smem_desc(bl + ks * 32u);
+        tc::mma_f16_ss(tmem, dah, dbh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+        tc::mma_f16_ss(tmem, dah, dbl, idesc, 1u);
+        tc::mma_f16_ss(tmem, dal, dbh, idesc, 1u);
+      }
+      tc::mma_commit(&mma_done);
+    }
+    request(it + 2);
+  }
+  if (n_it > 0) {
+    mbar_wait(&mma_done, (uint32_t)((n_it - 1) & 1));
+    tc::fence_after_thread_sync();
+    __syncthreads();  // every warp is past its last operand access: the epilogue scratch overlays the operand planes
+    if (warp < 4) gemm_epilogue(g, reinterpret_cast<float*>(smem), tmem, 0, sa, sb, warp, lane);
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, (uint32_t)g.tmem_cols);
+}
+
 }  // namespace
 }  // namespace mf
 
@@ -456,8 +605,8 @@ using namespace mf;
 
 static int gemm_launch(int trans, const float* d_a, int64_t lda, const float* d_b, int64_t ldb, float* d_c, int64_t ldc,
                        int64_t m, int32_t n, int64_t k, const float* d_bias, int32_t relu, int32_t k_split,
-                       const float* d_mask, int64_t ldm, float* d_colsum, const float* d_scale_a, const float* d_scale_b,
-                       void* stream, const char* who) {
+                       const float* d_mask, int64_t ldm, const float* d_out_mask, int64_t ldo, float* d_colsum,
+                       const float* d_scale_a, const float* d_scale_b, void* stream, const char* who) {
   MF_REQUIRE(m >= 0 && n >= 0 && k >= 0, "%s: negative dimension", who);
   if (m == 0 || n == 0) return MF_OK;
   MF_REQUIRE(d_a && d_b && d_c, "%s: null argument", who);
@@ -471,7 +620,8 @@ static int gemm_launch(int trans, const float* d_a, int64_t lda, const float* d_
   g.A = d_a; g.lda = lda; g.B = d_b; g.ldb = ldb; g.C = d_c; g.ldc = ldc;
   g.M = m; g.K = k; g.N = n; g.Np = (n + (d_colsum ? 1 : 0) + 15) / 16 * 16;
   g.bias = d_bias; g.relu = relu;
-  g.trans = trans; g.mask = d_mask; g.ldm = ldm; g.colsum = d_colsum;
+  g.trans = trans; g.mask = d_mask; g.ldm = ldm; g.colsum = d_colsum; g.out_mask = d_out_mask; g.ldo = ldo;
+  MF_REQUIRE(!(d_out_mask && (trans || k_split > 1)), "%s: an output mask needs the plain (unsplit, non-transposed) product", who);
   const long long n_kb = (k + 63) / 64;
   const long long ks = std::min<long long>(k_split, n_kb);
   g.kb_per_split = (n_kb + ks - 1) / ks;
@@ -487,9 +637,21 @@ static int gemm_launch(int trans, const float* d_a, int64_t lda, const float* d_
   const size_t smem = std::max<size_t>((size_t)g.nbuf * (2 * 128 * 128 + 2 * (size_t)g.Np * 128), 4 * 32 * 65 * 4);
   const long long m_tiles = (m + 127) / 128;
   // persistent variant: resident weights, bulk-copied A K-blocks (see gemm_nt_persistent_kernel)
-  const bool mask_ok = d_mask == nullptr || (ldm == k && (reinterpret_cast<uintptr_t>(d_mask) & 15u) == 0);
   // (MF_GEMM_PERSISTENT=0 selects the one-tile-per-CTA kernel for every shape: the comparison of tools/bench_gemm.py)
   static const bool use_persistent = !(getenv("MF_GEMM_PERSISTENT") != nullptr && getenv("MF_GEMM_PERSISTENT")[0] == '0');
+  // transposed product with bulk-copied operands (see gemm_tn_tma_kernel): contiguous A [k, m <= 128] and B [k, n], no mask
+  if (use_persistent && trans && d_mask == nullptr && lda == m && ldb == n && m <= 128 && m % 4 == 0 && n % 4 == 0 &&
+      (reinterpret_cast<uintptr_t>(d_a) & 15u) == 0 && (reinterpret_cast<uintptr_t>(d_b) & 15u) == 0) {
+    const size_t raw_stage = ((size_t)64 * (m + n) * 4 + 127) / 128 * 128;
+    const size_t tsmem = 2 * 128 * 128 + 2 * (size_t)g.Np * 128 + 2 * raw_stage;
+    if (tsmem <= 225 * 1024 && tsmem >= 4 * 32 * 65 * 4) {
+      MF_CUDA_CHECK(cudaFuncSetAttribute(gemm_tn_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+      dim3 tgrid(1, (unsigned)splits);
+      gemm_tn_tma_kernel<<<tgrid, kGemmThreads, tsmem, static_cast<cudaStream_t>(stream)>>>(g);
+      return post_launch("gemm_tn_tma_kernel");
+    }
+  }
+  const bool mask_ok = d_mask == nullptr || (ldm == k && (reinterpret_cast<uintptr_t>(d_mask) & 15u) == 0);
   if (use_persistent && !trans && g.k_split == 1 && (k == 64 || k == 128) && lda == k && (reinterpret_cast<uintptr_t>(d_a) & 15u) == 0 &&
       mask_ok && m_tiles >= 2) {
     const size_t n_kb = (size_t)(k / 64);
@@ -513,15 +675,15 @@ static int gemm_launch(int trans, const float* d_a, int64_t lda, const float* d_
 
 extern "C" int mf_gemm_nt_3xf16(const float* d_a, int64_t lda, const float* d_b, int64_t ldb, float* d_c, int64_t ldc,
                                 int64_t m, int32_t n, int64_t k, const float* d_bias, int32_t relu, int32_t k_split,
-                                const float* d_mask, int64_t ldm, const float* d_scale_a, const float* d_scale_b,
-                                void* stream) {
-  return gemm_launch(0, d_a, lda, d_b, ldb, d_c, ldc, m, n, k, d_bias, relu, k_split, d_mask, ldm, nullptr, d_scale_a,
-                     d_scale_b, stream, "mf_gemm_nt_3xf16");
+                                const float* d_mask, int64_t ldm, const float* d_out_mask, int64_t ldo,
+                                const float* d_scale_a, const float* d_scale_b, void* stream) {
+  return gemm_launch(0, d_a, lda, d_b, ldb, d_c, ldc, m, n, k, d_bias, relu, k_split, d_mask, ldm, d_out_mask, ldo, nullptr,
+                     d_scale_a, d_scale_b, stream, "mf_gemm_nt_3xf16");
 }
 
 extern "C" int mf_gemm_tn_3xf16(const float* d_a, int64_t lda, const float* d_b, int64_t ldb, float* d_c, int64_t ldc,
                                 int64_t m, int32_t n, int64_t k, int32_t k_split, const float* d_mask, int64_t ldm,
                                 float* d_colsum, const float* d_scale_a, const float* d_scale_b, void* stream) {
-  return gemm_launch(1, d_a, lda, d_b, ldb, d_c, ldc, m, n, k, nullptr, 0, k_split, d_mask, ldm, d_colsum, d_scale_a,
-                     d_scale_b, stream, "mf_gemm_tn_3xf16");
+  return gemm_launch(1, d_a, lda, d_b, ldb, d_c, ldc, m, n, k, nullptr, 0, k_split, d_mask, ldm, nullptr, 0, d_colsum,
+                     d_scale_a, d_scale_b, stream, "mf_gemm_tn_3xf16");
 }

@@ -88,7 +88,14 @@ class _MaskedLinearFn(torch.autograd.Function):
     arithmetic: the native hyper-network backward."""
 
     @staticmethod
-    def forward(ctx, x, weight, mask, bias, relu):
+    def forward(ctx, x, weight, mask, bias, relu, chained=False, input_is_relu=False):
+        """chained: this layer sits inside the masked MLP, i.e. its input is the ReLU output of the layer below (unless
+        it is the first layer) and its output feeds the next `_MaskedLinearFn`.  Then the input gradient leaves this
+        layer already multiplied by the ReLU derivative of the layer below (x > 0, applied in the GEMM epilogue), and
+        the gradient this layer receives arrives masked the same way by the layer above -- no mask operand in the
+        staging of either GEMM, and the weight gradient can take its operands by bulk copy."""
+        ctx.chained = chained
+        ctx.input_is_relu = input_is_relu
         wm = (mask * weight).contiguous()
         x = x.contiguous()
         y = torch.empty((x.shape[0], wm.shape[0]), dtype=x.dtype, device=x.device)
@@ -101,12 +108,15 @@ class _MaskedLinearFn(torch.autograd.Function):
     def backward(ctx, gy):
         x, wm, mask, y = ctx.saved_tensors
         gy = gy.contiguous()
-        relu_of = y if ctx.relu else None     # the ReLU derivative (y > 0) is applied inside the GEMMs' operand staging
+        # the ReLU derivative (y > 0): inside the GEMMs' operand staging, unless the layer above already applied it
+        relu_of = y if (ctx.relu and not ctx.chained) else None
         scale = _pow2_scale(gy)
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             gx = torch.empty_like(x)
-            _cabi.gemm_nt(gy, wm.t().contiguous(), gx, mask=relu_of, scale_a=scale)
+            # chained and fed by a ReLU (every layer but the first): gx leaves masked with (x > 0) for the layer below
+            fed_by_relu = ctx.chained and ctx.input_is_relu
+            _cabi.gemm_nt(gy, wm.t().contiguous(), gx, mask=relu_of, out_mask=x if fed_by_relu else None, scale_a=scale)
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[3]:
             # dW = dZ^T X and db = column sums of dZ in ONE launch straight from the row-major activations; K = rows,
             # cut into pieces whose partial sums are added into gw / gb
@@ -126,12 +136,12 @@ class _MaskedLinearFn(torch.autograd.Function):
                 gz = gy * (y > 0) if ctx.relu else gy
                 gw, gb = gz.t() @ x, gz.sum(0)
             gw = gw * mask
-        return gx, gw, None, gb, None
+        return gx, gw, None, gb, None, None, None
 
 
-def _linear(h, lin, relu):
+def _linear(h, lin, relu, first=True, chained=False):
     if _native_gemm() and h.is_cuda and h.dtype == torch.float32 and h.dim() == 2:
-        return _MaskedLinearFn.apply(h, lin.weight, lin.mask, lin.bias, relu)
+        return _MaskedLinearFn.apply(h, lin.weight, lin.mask, lin.bias, relu, chained, not first)
     h = F.linear(h, lin.mask * lin.weight, lin.bias)
     return torch.relu(h) if relu else h
 
@@ -140,7 +150,7 @@ def _hyper_phi(t, x, c):
     h = x if c is None else torch.cat((x, c), dim=-1)
     lins = t.hyper.linears()
     for i, lin in enumerate(lins):
-        h = _linear(h, lin, i < len(lins) - 1)
+        h = _linear(h, lin, i < len(lins) - 1, first=(i == 0), chained=True)
     return h.unflatten(-1, (t.features, t.total))
 
 

@@ -106,3 +106,33 @@ def test_gemm_nt_with_relu_mask(cuda, rows, out, inn):
     _cabi.gemm_nt(dy, wt, gx, mask=y)
     ref = (dy.double() * (y > 0)) @ wt.double().t()
     assert ((gx.double() - ref).norm() / ref.norm()).item() < 2e-6
+
+
+@pytest.mark.parametrize("rows,out,inn", [(70001, 128, 128), (40000, 128, 68), (5000, 64, 128), (333, 128, 16)])
+def test_gemm_tn_bulk_copied_operands(cuda, rows, out, inn):
+    """contiguous operands without a mask: the kernel that takes its K-blocks by bulk copy (tail K-block, several splits)"""
+    g = torch.Generator().manual_seed(rows + out)
+    dz = (torch.randn(rows, out, generator=g) * 1e-7 * torch.exp(2 * torch.randn(rows, 1, generator=g))).to(cuda)
+    x = torch.randn(rows, inn, generator=g).to(cuda)
+    ref_w, ref_b = dz.double().t() @ x.double(), dz.double().sum(0)
+    scale = torch.exp2(torch.floor(14.0 - torch.log2(dz.abs().amax()))).reshape(1)
+    for k_split in (7, 296):
+        gw = torch.zeros(out, inn, device=cuda)
+        gb = torch.zeros(out, device=cuda)
+        _cabi.gemm_tn(dz, x, gw, k_split=k_split, colsum=gb, scale_a=scale)
+        assert ((gw.double() - ref_w).norm() / ref_w.norm()).item() < 3e-5
+        assert ((gb.double() - ref_b).norm() / ref_b.norm()).item() < 3e-5
+
+
+@pytest.mark.parametrize("rows,out,inn", [(3001, 128, 128), (3001, 141, 128), (700, 128, 68)])
+def test_gemm_nt_output_mask(cuda, rows, out, inn):
+    """input gradient leaving already multiplied by the ReLU derivative of the layer below (its input x > 0)"""
+    g = torch.Generator().manual_seed(11)
+    dy = torch.randn(rows, out, generator=g).to(cuda)
+    wt = (torch.randn(inn, out, generator=g) / out ** 0.5).to(cuda)
+    x = torch.randn(rows, inn, generator=g).clamp_min(0).to(cuda)
+    gx = torch.empty(rows, inn, device=cuda)
+    _cabi.gemm_nt(dy, wt, gx, out_mask=x)
+    ref = (dy.double() @ wt.double().t()) * (x > 0)
+    assert ((gx.double() - ref).norm() / ref.norm()).item() < 2e-6
+    assert (gx[x <= 0] == 0).all()

@@ -39,3 +39,6 @@ for name, k, n in (("layer 128->128", 128, 128), ("layer 68->128", 68, 128), ("l
     t_nat = timed(lambda: _cabi.gemm_tn(gz, x, gw, k_split=592, mask=y, colsum=gb, scale_a=s))
     t_ref = timed(lambda: ((gz * (y > 0)).t() @ x, (gz * (y > 0)).sum(0)))
     print(f"dW + db {name}: native {t_nat:.3f} ms, torch {t_ref:.3f} ms", flush=True)
+    if k % 4 == 0 and n <= 128:
+        t_nat = timed(lambda: _cabi.gemm_tn(gz, x, gw, k_split=592, colsum=gb, scale_a=s))
+        print(f"dW + db {name}, gradient already masked (bulk-copied operands): native {t_nat:.3f} ms", flush=True)
