@@ -640,7 +640,8 @@ static int gemm_launch(int trans, const float* d_a, int64_t lda, const float* d_
   // (MF_GEMM_PERSISTENT=0 selects the one-tile-per-CTA kernel for every shape: the comparison of tools/bench_gemm.py)
   static const bool use_persistent = !(getenv("MF_GEMM_PERSISTENT") != nullptr && getenv("MF_GEMM_PERSISTENT")[0] == '0');
   // transposed product with bulk-copied operands (see gemm_tn_tma_kernel): contiguous A [k, m <= 128] and B [k, n], no mask
-  if (use_persistent && trans && d_mask == nullptr && lda == m && ldb == n && m <= 128 && m % 4 == 0 && n % 4 == 0 &&
+  if (use_persistent && trans && d_mask == nullptr && lda == m && ldb == n && m <= 128 && m % 4 == 0 && (n % 4 == 0 || k % 64 == 0) &&  // (bulk copies move multiples of 16 bytes)
+     
       (reinterpret_cast<uintptr_t>(d_a) & 15u) == 0 && (reinterpret_cast<uintptr_t>(d_b) & 15u) == 0) {
     const size_t raw_stage = ((size_t)64 * (m + n) * 4 + 127) / 128 * 128;
     const size_t tsmem = 2 * 128 * 128 + 2 * (size_t)g.Np * 128 + 2 * raw_stage;

@@ -108,7 +108,8 @@ def test_gemm_nt_with_relu_mask(cuda, rows, out, inn):
     assert ((gx.double() - ref).norm() / ref.norm()).item() < 2e-6
 
 
-@pytest.mark.parametrize("rows,out,inn", [(70001, 128, 128), (40000, 128, 68), (5000, 64, 128), (333, 128, 16)])
+@pytest.mark.parametrize("rows,out,inn", [(70001, 128, 128), (40000, 128, 68), (5000, 64, 128), (333, 128, 16),
+                                          (64 * 700, 128, 141)])   # 141 columns: rows that are not 16-byte multiples, whole K-blocks only
 def test_gemm_tn_bulk_copied_operands(cuda, rows, out, inn):
     """contiguous operands without a mask: the kernel that takes its K-blocks by bulk copy (tail K-block, several splits)"""
     g = torch.Generator().manual_seed(rows + out)
