@@ -377,6 +377,23 @@ int mf_rqs_backward(const void* d_params, const void* d_x, int64_t n, int32_t bi
                     const void* d_grad_y, const void* d_grad_ladj, void* d_grad_params, void* d_grad_x, int dtype,
                     void* stream);
 
+/*
+ * Empirical maximum mean discrepancy between two samples x, y [n, d] (row-major, `dtype`), SURVEY 8(f)-4:
+ * replaces memflow/unfolding_flow/mmd_loss.py:4-41 `MMD(x, y, kernel, device, dtype)` (three torch.mm Gram matrices
+ * + one n x n accumulator per bandwidth) and, when a gradient pointer is given, what torch autograd derives from it in
+ * the reference's `loss.backward()` (scripts/run_model_labframe_sampling.py:114-127,466-520).
+ *   kernel: MF_MMD_MULTISCALE (bandwidths 0.1, 0.2, 0.5, 0.9, 1.3) or MF_MMD_RBF (10, 15, 20, 50)
+ *   d_out [1] = mean(XX + YY - 2 XY); d_grad_x / d_grad_y [n, d] = d out / d x, d out / d y (either may be NULL)
+ *   d_workspace: mf_mmd_workspace_bytes(n, d, want_grad) bytes of scratch (the ABI never allocates)
+ * Two launches (pair sums, fixed-order finish); no n x n intermediate; results do not depend on scheduling.
+ */
+#define MF_MMD_MULTISCALE 0
+#define MF_MMD_RBF 1
+#define MF_MMD_MAX_DIM 32
+int64_t mf_mmd_workspace_bytes(int64_t n, int32_t d, int32_t want_grad);
+int mf_mmd(const void* d_x, const void* d_y, int64_t n, int32_t d, int32_t kernel, void* d_workspace, void* d_out,
+           void* d_grad_x, void* d_grad_y, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -272,6 +272,23 @@ def event_reduce(logprob, mask, logw, out):
     check(rc, "mf_event_reduce")
 
 
+MF_MMD_MULTISCALE, MF_MMD_RBF, MF_MMD_MAX_DIM = 0, 1, 32
+
+
+def mmd(x, y, kernel, out, grad_x=None, grad_y=None):
+    """out[0] = MMD(x, y) and, when given, its gradients w.r.t. x and y (mf_mmd); x, y [n, d] contiguous."""
+    n, d = x.shape
+    L = lib()
+    L.mf_mmd_workspace_bytes.restype = ctypes.c_int64
+    want_grad = grad_x is not None or grad_y is not None
+    nbytes = int(L.mf_mmd_workspace_bytes(ctypes.c_int64(n), ctypes.c_int32(d), ctypes.c_int32(1 if want_grad else 0)))
+    with torch.cuda.device(x.device):
+        ws = torch.empty(max(nbytes, 8) // 8, dtype=torch.float64, device=x.device)
+        rc = L.mf_mmd(_ptr(x), _ptr(y), ctypes.c_int64(n), ctypes.c_int32(d), ctypes.c_int32(kernel), _ptr(ws), _ptr(out),
+                      _ptr(grad_x), _ptr(grad_y), ctypes.c_int(_dtype_code(x.dtype)), _stream(x.device))
+    check(rc, "mf_mmd")
+
+
 PROBE_LIB_PATH = os.path.join(_HERE, "_lib", "libmemflow_b200_probe.so")
 _probe = None
 
