@@ -394,6 +394,21 @@ int64_t mf_mmd_workspace_bytes(int64_t n, int32_t d, int32_t want_grad);
 int mf_mmd(const void* d_x, const void* d_y, int64_t n, int32_t d, int32_t kernel, void* d_workspace, void* d_out,
            void* d_grad_x, void* d_grad_y, int dtype, void* stream);
 
+/*
+ * Regression loss of a periodic variable (phi), SURVEY 8(f)-4: replaces `loss_fn_periodic(inp, target, loss_fn, device)`
+ * (scripts/run_model_labframe_sampling.py:65-77) for loss_fn = torch.nn.HuberLoss(delta) / torch.nn.MSELoss.
+ * inp is wrapped once into [-pi, pi], dphi = target - inp is wrapped into (-pi, pi], loss_i = loss_fn(dphi, 0).
+ *   d_inp, d_target [n]; kind: MF_LOSS_HUBER (huber_delta > 0) or MF_LOSS_MSE
+ *   d_elem [n] (optional): loss_i (reduction='none'); d_deriv [n] (optional): d loss_i / d dphi (= d/d target = -d/d inp)
+ *   d_total [1] (optional): sum_i loss_i, divided by n when mean != 0
+ *   d_workspace: mf_periodic_loss_workspace_bytes(n) bytes
+ */
+#define MF_LOSS_HUBER 0
+#define MF_LOSS_MSE 1
+int64_t mf_periodic_loss_workspace_bytes(int64_t n);
+int mf_periodic_loss(const void* d_inp, const void* d_target, int64_t n, int32_t kind, double huber_delta, int32_t mean,
+                     void* d_workspace, void* d_elem, void* d_deriv, void* d_total, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -289,6 +289,23 @@ def mmd(x, y, kernel, out, grad_x=None, grad_y=None):
     check(rc, "mf_mmd")
 
 
+MF_LOSS_HUBER, MF_LOSS_MSE = 0, 1
+
+
+def periodic_loss(inp, target, kind, huber_delta, mean, elem=None, deriv=None, total=None):
+    """Wrapped-phi regression loss (mf_periodic_loss); inp, target contiguous with n elements."""
+    n = inp.numel()
+    L = lib()
+    L.mf_periodic_loss_workspace_bytes.restype = ctypes.c_int64
+    nbytes = int(L.mf_periodic_loss_workspace_bytes(ctypes.c_int64(n)))
+    with torch.cuda.device(inp.device):
+        ws = torch.empty(max(nbytes, 8) // 8, dtype=torch.float64, device=inp.device)
+        rc = L.mf_periodic_loss(_ptr(inp), _ptr(target), ctypes.c_int64(n), ctypes.c_int32(kind), ctypes.c_double(huber_delta),
+                                ctypes.c_int32(1 if mean else 0), _ptr(ws), _ptr(elem), _ptr(deriv), _ptr(total),
+                                ctypes.c_int(_dtype_code(inp.dtype)), _stream(inp.device))
+    check(rc, "mf_periodic_loss")
+
+
 PROBE_LIB_PATH = os.path.join(_HERE, "_lib", "libmemflow_b200_probe.so")
 _probe = None
 

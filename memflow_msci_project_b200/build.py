@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(OUT_DIR, "libmemflow_b200.so")
-SOURCES = ["abi.cu", "rambo.cu", "rambo_bwd.cu", "flow.cu", "reduce.cu", "flow_tc.cu", "rqs.cu", "flow_mma.cu", "gemm_tc.cu", "mmd.cu"]
+SOURCES = ["abi.cu", "rambo.cu", "rambo_bwd.cu", "flow.cu", "reduce.cu", "flow_tc.cu", "rqs.cu", "flow_mma.cu", "gemm_tc.cu", "mmd.cu", "periodic.cu"]
 # micro-benchmarks / building-block checks of the tcgen05 pieces: a separate TEST-ONLY library
 # (tests/test_tc_probe_gpu.py, tools/probe_*.py); nothing of it is linked into the product library
 PROBE_LIB = os.path.join(OUT_DIR, "libmemflow_b200_probe.so")
