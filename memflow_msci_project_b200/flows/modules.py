@@ -524,10 +524,13 @@ class MAF(nn.Module):
     def _sched_words(self, device):
         """uint8 view of the [T][64] uint64 schedule words of mf_flow_set_sample_schedule (cached per device)."""
         core = self.core_transforms()
-        orders = tuple(tuple(int(v) for v in t.order.tolist()) for t in core)
+        # keyed on the identity / version of the order buffers: reading them back (a device -> host sync per
+        # transform) happens only when they changed (construction, load_state_dict), not at every re-pack
+        key = (str(device),) + tuple((t.order.data_ptr(), t.order._version) for t in core)
         cached = getattr(self, "_sched_cache", None)
-        if cached is None or cached[0] != (str(device), orders):
+        if cached is None or cached[0] != key:
             import numpy as np
+            orders = tuple(tuple(int(v) for v in t.order.tolist()) for t in core)
             words = np.zeros((len(core), 64), dtype=np.uint64)
             for ti, od in enumerate(orders):
                 for s in range(64):
@@ -537,7 +540,7 @@ class MAF(nn.Module):
                             m |= 1 << f
                     words[ti, s] = m if m else 1
             t = torch.from_numpy(words.view(np.uint8).reshape(-1).copy()).to(device)
-            cached = ((str(device), orders), t)
+            cached = (key, t)
             self._sched_cache = cached
         return cached[1]
 
