@@ -38,14 +38,10 @@ periodic_loss_kernel(const T* __restrict__ inp, const T* __restrict__ target, lo
       l = dphi * dphi;
       g = T(2) * dphi;
     } else {  // torch.nn.HuberLoss: 0.5 d^2 if |d| < delta else delta (|d| - 0.5 delta)
+      // written like torch's kernels so that a NaN input gives NaN loss AND NaN gradient as in the reference
       const T ad = fabs(dphi);
-      if (ad < delta) {
-        l = T(0.5) * dphi * dphi;
-        g = dphi;
-      } else {
-        l = delta * (ad - T(0.5) * delta);
-        g = dphi > T(0) ? delta : -delta;
-      }
+      l = ad < delta ? T(0.5) * ad * ad : delta * (ad - T(0.5) * delta);
+      g = dphi < -delta ? -delta : (dphi > delta ? delta : dphi);
     }
     if (elem) elem[i] = l;
     if (deriv) deriv[i] = g;

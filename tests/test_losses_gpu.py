@@ -65,3 +65,18 @@ def test_large_batch_against_oracle_2d_and_edge_cases(cuda):
         loss_fn_periodic(x, y, torch.nn.L1Loss(), cuda)
     with pytest.raises(RuntimeError):
         loss_fn_periodic(x, y[:5], fn, cuda)
+
+
+def test_nan_inputs_propagate_like_torch(cuda):
+    """the reference has no guard: a NaN prediction gives a NaN loss element and a NaN gradient there, nothing else"""
+    from memflow_msci_project_b200.unfolding_flow.losses import loss_fn_periodic
+    inp = torch.tensor([0.3, float("nan"), -4.0, 2.0], dtype=torch.float64, device=cuda, requires_grad=True)
+    target = torch.tensor([0.1, 0.2, 3.0, float("nan")], dtype=torch.float64, device=cuda)
+    v = loss_fn_periodic(inp, target, torch.nn.HuberLoss(delta=0.5, reduction="none"), cuda)
+    v.sum().backward()
+    nan = torch.tensor([False, True, False, True], device=cuda)
+    assert torch.equal(torch.isnan(v), nan) and torch.equal(torch.isnan(inp.grad), nan)
+    want, g = losses_oracle.loss_fn_periodic(np.array([0.3, -4.0]), np.array([0.1, 3.0]), "huber", 0.5, "none")
+    assert np.abs(v.detach().cpu().numpy()[[0, 2]] - want).max() <= 1e-15
+    assert np.abs(inp.grad.cpu().numpy()[[0, 2]] + g).max() <= 1e-15
+    assert torch.isnan(loss_fn_periodic(inp.detach(), target, torch.nn.HuberLoss(delta=0.5), cuda))
